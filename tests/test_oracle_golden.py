@@ -1,0 +1,135 @@
+"""CPU: pin the oracle restatement (oracle/restate.py) to the golden vectors produced by the
+verbatim reference (oracle/make_golden.py).  fp32 tolerance 1e-5 relative (north_star); the
+fp64 twins must agree to 1e-12."""
+import pytest
+import torch
+
+from conftest import as_data, grads_mismatch, load_golden, rel_err
+from oracle import restate as R
+
+TOL32 = 1e-5
+TOL64 = 1e-12
+
+
+def _leafs(sd, dtype=None):
+    out = {}
+    for k, v in sd.items():
+        v = v.clone()
+        if v.is_floating_point():
+            if dtype is not None:
+                v = v.to(dtype)
+            v.requires_grad_(True)
+        out[k] = v
+    return out
+
+
+def _check_grads(p, golden, prefix, tol):
+    for k, g in golden.items():
+        t = p[prefix + k]
+        if g is None:
+            assert t.grad is None or float(t.grad.abs().max()) == 0.0, k
+        else:
+            assert t.grad is not None, k
+            assert rel_err(t.grad, g) < tol, (k, rel_err(t.grad, g))
+
+
+def test_scatter_matches_reference_semantics():
+    fx = load_golden("scatter")
+    for red in ("sum", "mean"):
+        out = R.scatter_rows(fx["src"], fx["index"], fx["n"], red)
+        assert torch.equal(out, fx[f"{red}_dimsize"])          # sequential adds in index order: bit-exact
+        out = R.scatter_rows(fx["src"], fx["index"], None, red)
+        assert torch.equal(out, fx[f"{red}_auto"])
+        assert out.shape[0] == int(fx["index"].max()) + 1
+    assert torch.equal(R.scatter_rows(fx["src3"], fx["index"], fx["n"], "mean"), fx["mean3"])
+    # empty segments give 0, also for mean (count clamped to 1)
+    assert float(fx["mean_dimsize"][3].abs().max()) == 0.0 and float(fx["mean_dimsize"][-1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("norm", ["ln", "None", "bn"])
+@pytest.mark.parametrize("nl", [1, 2, 3])
+@pytest.mark.parametrize("inorm", [0, 1])
+def test_mlp(norm, nl, inorm):
+    fx = load_golden("mlp")
+    c = fx[f"{norm}_{nl}_{inorm}"]
+    p = _leafs({"m." + k: v for k, v in c["sd"].items() if "running" not in k and "num_batches" not in k})
+    x = fx["x"].clone().requires_grad_(True)
+    y = R.mlp(p, "m", x, norm)
+    assert rel_err(y, c["y"]) < TOL32
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(y.shape, generator=g)
+    (y * w).sum().backward()
+    assert rel_err(x.grad, c["dx"]) < TOL32
+    _check_grads(p, c["grads"], "m.", TOL32)
+
+
+@pytest.mark.parametrize("name,tol", [("mhnns_ln_mean_c64", TOL32), ("mhnns_none_sum_c32", TOL32),
+                                      ("mhnns_ln_mean_l131_c32", TOL32), ("mhnns_ln_mean_l012_c32", TOL32),
+                                      ("mhnns_ln_mean_opv_c32", TOL32), ("mhnns_ln_mean_c32_f64", TOL64)])
+def test_mhnns_conv(name, tol):
+    fx = load_golden(name)
+    p = _leafs({"conv." + k: v for k, v in fx["sd"].items()})
+    X = fx["X"].clone().requires_grad_(True)
+    X0 = fx["X0"].clone().requires_grad_(True)
+    out = R.mhnns_conv(p, "conv", X, fx["vertex"], fx["edges"], X0, fx["aggr"], 0.5, fx["norm"])
+    assert rel_err(out, fx["out"]) < tol
+    (out * fx["w"].to(out.dtype)).sum().backward()
+    assert rel_err(X.grad, fx["dX"]) < tol and rel_err(X0.grad, fx["dX0"]) < tol
+    _check_grads(p, fx["grads"], "conv.", tol)
+
+
+@pytest.mark.parametrize("name", ["mhnn_ln_mean_c64", "mhnn_none_sum_c32", "mhnn_ln_mean_l1031_c32",
+                                  "mhnn_bn_mean_c32"])
+def test_mhnn_conv(name):
+    fx = load_golden(name)
+    p = _leafs({"conv." + k: v for k, v in fx["sd"].items() if "running" not in k and "num_batches" not in k})
+    X = fx["X"].clone().requires_grad_(True)
+    E = fx["E"].clone().requires_grad_(True)
+    Xo, Eo = R.mhnn_conv(p, "conv", X, E, fx["vertex"], fx["edges"], fx["aggr"], fx["norm"])
+    assert rel_err(Xo, fx["Xo"]) < TOL32 and rel_err(Eo, fx["Eo"]) < TOL32
+    ((Xo * fx["wx"]).sum() + (Eo * fx["we"]).sum()).backward()
+    assert rel_err(X.grad, fx["dX"]) < TOL32 and rel_err(E.grad, fx["dE"]) < TOL32
+    _check_grads(p, fx["grads"], "conv.", TOL32)
+
+
+@pytest.mark.parametrize("name,tol", [("egnn_c64_eps0.1", TOL32), ("egnn_c64_default", TOL32),
+                                      ("egnn_c32_coors", TOL32), ("egnn_c32_f64", TOL64)])
+def test_egnn(name, tol):
+    fx = load_golden(name)
+    p = _leafs({"egnn." + k: v for k, v in fx["sd"].items()})
+    h = fx["h"].clone().requires_grad_(True)
+    nbhd, d2 = R.knn(fx["pos"], 16)
+    assert torch.equal(nbhd, fx["nbhd"])                       # index construction: bit-exact
+    assert torch.equal(d2, fx["nbhd_d2"])
+    assert torch.equal(nbhd[:, 0], torch.arange(h.shape[0]))   # self is always neighbour rank 0 (fact 3)
+    node_out, coors_out = R.egnn(p, "egnn", h, fx["pos"], 16)
+    assert rel_err(node_out, fx["node_out"]) < tol
+    assert rel_err(coors_out, fx["coors_out"]) < tol
+    loss = (node_out * fx["w"][0].to(node_out.dtype)).sum()
+    if fx["wc"] is not None:
+        loss = loss + (coors_out * fx["wc"][0].to(node_out.dtype)).sum()
+    loss.backward()
+    assert rel_err(h.grad, fx["dh"]) < tol
+    _check_grads(p, fx["grads"], "egnn.", tol)
+    if fx["wc"] is None:   # fact 4: phi_x parameters get no gradient when coors_out is discarded
+        for k in ("coors_mlp.0.weight", "coors_mlp.3.weight", "coors_norm.scale"):
+            assert fx["grads"][k] is None
+
+
+def test_knn_k_larger_than_n_raises():
+    with pytest.raises(RuntimeError):
+        R.knn(torch.randn(10, 3), 16)
+
+
+@pytest.mark.parametrize("name,fn", [("model_egnn_equihnns_c64", R.egnn_equihnns), ("model_mhnnm_c64", R.mhnnm)])
+def test_models(name, fn):
+    fx = load_golden(name)
+    p = _leafs({k: v for k, v in fx["sd"].items() if "running" not in k and "num_batches" not in k})
+    data = as_data(fx["batch"])
+    pred = fn(p, data)
+    assert rel_err(pred, fx["pred"]) < TOL32
+    loss = torch.nn.functional.mse_loss(pred, data.y)
+    assert abs(float(loss.detach()) - float(fx["loss"])) < TOL32 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    bad = grads_mismatch({k: p[k].grad for k in fx["grads"]}, fx["grads"], 5e-5)
+    assert not bad, bad
