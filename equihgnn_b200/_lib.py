@@ -1,0 +1,69 @@
+"""ctypes binding of libeqh_b200.so (the C ABI declared in include/eqh_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, a RuntimeError (or
+NotImplementedError for EQH_ERR_UNSUPPORTED) is raised.  ctypes releases the GIL for the
+duration of every call, and each call only enqueues kernels on the caller's current stream,
+so the binding is safe from the autograd engine's device thread as well.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libeqh_b200.so")
+
+EQH_ERR_UNSUPPORTED = -2
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "eqh_version": (c_int, []),
+    "eqh_error_string": (c_char_p, [c_int]),
+    "eqh_partial_rows": (c_int, []),
+    "eqh_incidence_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "eqh_incidence_build_i64": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "eqh_incidence_build_i32": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "eqh_gather_reduce": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _P, _P]),
+    "eqh_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
+    "eqh_fused_msg_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, c_int, _P, _P]),
+    "eqh_fused_msg_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, _P, _P, _P]),
+    "eqh_colsum": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
+    "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
+    "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
+    "eqh_egnn_edge_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
+                              c_float, _P]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library (once).  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m equihgnn_b200.build` "
+            "(equihgnn_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = load().eqh_error_string(rc).decode()
+    if rc == EQH_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,255 @@
+// Fused per-incidence message (gather-add -> ReLU -> LayerNorm) + deterministic segmented
+// reduction, forward and backward.  The [Z,C] / [Z,2C] per-incidence tensors of the reference
+// (conv.py:90,96,175-176: X[vertex], E[edges], cat; mlp.py:94-96: relu_, LayerNorm) never
+// touch HBM.  HBM-bound; algorithmic bytes per forward call (figure F):
+//     4C(rows_A + rows_B + n_out) + 4(2Z + n_out + 1).
+// One warp owns one segment; a feature row is spread over the warp (Row<V>), LayerNorm
+// statistics are two warp-shuffle reductions (two-pass mean / variance, like ATen).
+#include "common.cuh"
+
+namespace eqh {
+
+template <int V>
+__device__ __forceinline__ void ln_stats(const Row<V>& t, float eps, float& mean, float& rstd) {
+  constexpr float invC = 1.f / (32 * V);
+  mean = warp_sum(t.sum()) * invC;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { float d = t.v[i] - mean; q += d * d; }
+  const float var = warp_sum(q) * invC;
+  rstd = 1.f / sqrtf(var + eps);
+}
+
+template <int V, bool LN>
+__global__ void __launch_bounds__(256) k_fused_fwd(const float* __restrict__ A, const float* __restrict__ B,
+                                                    const int32_t* __restrict__ ia, const int32_t* __restrict__ ib,
+                                                    const int32_t* __restrict__ rowptr, int64_t n_out,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float eps, int mode, float* __restrict__ U) {
+  constexpr int C = 32 * V;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Row<V> g, bt;
+  if constexpr (LN) { g.load(gamma, lane); bt.load(beta, lane); }
+  for (int64_t s = warp; s < n_out; s += nwarps) {
+    const int32_t lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+    Row<V> ac, bc, acc;
+    if (!ia) ac.load(A + s * C, lane);
+    if (!ib) bc.load(B + s * C, lane);
+    acc.zero();
+    // software prefetch: operands of incidence k+1 are requested before k is normalised
+    Row<V> an, bn;
+    if (lo < hi) {
+      if (ia) an.load(A + (int64_t)__ldg(ia + lo) * C, lane);
+      if (ib) bn.load(B + (int64_t)__ldg(ib + lo) * C, lane);
+    }
+    for (int32_t k = lo; k < hi; ++k) {
+      Row<V> t;
+#pragma unroll
+      for (int i = 0; i < V; ++i) t.v[i] = fmaxf((ia ? an.v[i] : ac.v[i]) + (ib ? bn.v[i] : bc.v[i]), 0.f);
+      if (k + 1 < hi) {
+        if (ia) an.load(A + (int64_t)__ldg(ia + k + 1) * C, lane);
+        if (ib) bn.load(B + (int64_t)__ldg(ib + k + 1) * C, lane);
+      }
+      if constexpr (LN) {
+        float mean, rstd;
+        ln_stats<V>(t, eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] += (t.v[i] - mean) * rstd;
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] += t.v[i];
+      }
+    }
+    const float cnt = (float)(hi - lo);
+    if constexpr (LN) {  // sum_k (xhat_k * gamma + beta) = gamma * sum_k xhat_k + cnt * beta
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] = acc.v[i] * g.v[i] + cnt * bt.v[i];
+    }
+    if (mode == EQH_REDUCE_MEAN) {
+      const float d = fmaxf(cnt, 1.f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] = acc.v[i] / d;
+    }
+    acc.store(U + s * C, lane);
+  }
+}
+
+template <int V, bool LN, bool DGB>
+__global__ void __launch_bounds__(256) k_fused_bwd(const float* __restrict__ A, const float* __restrict__ B,
+                                                    const int32_t* __restrict__ ia, const int32_t* __restrict__ ib,
+                                                    const int32_t* __restrict__ iu, const int32_t* __restrict__ rowptr,
+                                                    int64_t n_seg, const float* __restrict__ gamma, float eps,
+                                                    const float* __restrict__ dU, const int32_t* __restrict__ u_rowptr,
+                                                    float* __restrict__ dOp, float* __restrict__ dgb_partial) {
+  constexpr int C = 32 * V;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Row<V> g, dg, db;
+  if constexpr (LN) g.load(gamma, lane);
+  if constexpr (DGB) { dg.zero(); db.zero(); }
+  for (int64_t s = warp; s < n_seg; s += nwarps) {
+    const int32_t lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+    Row<V> ac, bc, uc, acc;
+    if (!ia) ac.load(A + s * C, lane);
+    if (!ib) bc.load(B + s * C, lane);
+    if (!iu) {
+      uc.load(dU + s * C, lane);
+      const float w = u_rowptr ? 1.f / (float)max(hi - lo, 1) : 1.f;  // iu == NULL: U's grouping is this grouping
+#pragma unroll
+      for (int i = 0; i < V; ++i) uc.v[i] *= w;
+    }
+    acc.zero();
+    for (int32_t k = lo; k < hi; ++k) {
+      Row<V> a, b, gk;
+      if (ia) a.load(A + (int64_t)__ldg(ia + k) * C, lane);
+      if (ib) b.load(B + (int64_t)__ldg(ib + k) * C, lane);
+      if (iu) {
+        const int32_t r = __ldg(iu + k);
+        gk.load(dU + (int64_t)r * C, lane);
+        const float w = inv_count(u_rowptr, r);
+#pragma unroll
+        for (int i = 0; i < V; ++i) gk.v[i] *= w;
+      }
+      Row<V> pre, t;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        pre.v[i] = (ia ? a.v[i] : ac.v[i]) + (ib ? b.v[i] : bc.v[i]);
+        t.v[i] = fmaxf(pre.v[i], 0.f);
+      }
+      if constexpr (LN) {
+        float mean, rstd;
+        ln_stats<V>(t, eps, mean, rstd);
+        float s1 = 0.f, s2 = 0.f;
+        Row<V> xh, dx;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float gv = iu ? gk.v[i] : uc.v[i];
+          xh.v[i] = (t.v[i] - mean) * rstd;
+          dx.v[i] = gv * g.v[i];
+          s1 += dx.v[i];
+          s2 += dx.v[i] * xh.v[i];
+          if constexpr (DGB) { dg.v[i] += gv * xh.v[i]; db.v[i] += gv; }
+        }
+        constexpr float invC = 1.f / C;
+        s1 = warp_sum(s1) * invC;
+        s2 = warp_sum(s2) * invC;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float dt = rstd * (dx.v[i] - s1 - xh.v[i] * s2);
+          acc.v[i] += pre.v[i] > 0.f ? dt : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] += pre.v[i] > 0.f ? (iu ? gk.v[i] : uc.v[i]) : 0.f;
+      }
+    }
+    acc.store(dOp + s * C, lane);
+  }
+  if constexpr (DGB) {
+    __shared__ __align__(16) float sm[8][2 * C];
+    dg.store(&sm[wib][0], lane);
+    db.store(&sm[wib][C], lane);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += sm[w][c];  // fixed order
+      dgb_partial[(int64_t)blockIdx.x * 2 * C + c] = v;
+    }
+  }
+}
+
+// out[c] = sum_r partial[r,c], r ascending within each of 8 interleaved groups, groups combined in fixed order
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partial, int64_t rows, int64_t cols,
+                                                 float* __restrict__ out) {
+  __shared__ float sm[8][32];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int64_t c = blockIdx.x * 32 + cx;
+  float v = 0.f;
+  if (c < cols)
+    for (int64_t r = rg; r < rows; r += 8) v += __ldg(partial + r * cols + c);
+  sm[rg][cx] = v;
+  __syncthreads();
+  if (rg == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][cx];
+    out[c] = t;
+  }
+}
+
+}  // namespace eqh
+
+extern "C" {
+
+int eqh_partial_rows(void) { return eqh::kPartialRows; }
+
+int eqh_fused_msg_fwd(const float* A, const float* B, const int32_t* ia, const int32_t* ib, const int32_t* rowptr,
+                      int64_t n_out, int64_t C, const float* gamma, const float* beta, float eps, int mode, float* U,
+                      eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(n_out >= 0 && rowptr && A && B && (n_out == 0 || U));
+  EQH_CHECK_ARG((gamma == nullptr) == (beta == nullptr));
+  EQH_CHECK_ARG(mode == EQH_REDUCE_SUM || mode == EQH_REDUCE_MEAN);
+  EQH_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(U) && aligned16(gamma) && aligned16(beta));
+  if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
+  if (n_out == 0) return EQH_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t blocks = (n_out + 7) / 8;
+  if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
+  EQH_DISPATCH_V(C, {
+    if (gamma)
+      k_fused_fwd<V, true><<<(unsigned)blocks, 256, 0, st>>>(A, B, ia, ib, rowptr, n_out, gamma, beta, eps, mode, U);
+    else
+      k_fused_fwd<V, false><<<(unsigned)blocks, 256, 0, st>>>(A, B, ia, ib, rowptr, n_out, gamma, beta, eps, mode, U);
+  });
+  EQH_LAUNCH_RC();
+}
+
+int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const int32_t* ib, const int32_t* iu,
+                      const int32_t* rowptr, int64_t n_seg, int64_t C, const float* gamma, const float* beta,
+                      float eps, const float* dU, const int32_t* u_rowptr, float* dOp, float* dgb_partial,
+                      eqh_stream_t stream) {
+  using namespace eqh;
+  (void)beta;
+  EQH_CHECK_ARG(n_seg >= 0 && rowptr && A && B && dU && (n_seg == 0 || dOp));
+  EQH_CHECK_ARG(!(dgb_partial && !gamma));
+  EQH_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(dU) && aligned16(dOp) && aligned16(gamma) &&
+                aligned16(dgb_partial));
+  if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dgb_partial) {
+    // persistent launch: every one of the kPartialRows CTAs writes its partial row (zeros if idle)
+    EQH_DISPATCH_V(C, {
+      k_fused_bwd<V, true, true><<<kPartialRows, 256, 0, st>>>(A, B, ia, ib, iu, rowptr, n_seg, gamma, eps, dU, u_rowptr,
+                                                              dOp, dgb_partial);
+    });
+  } else {
+    if (n_seg == 0) return EQH_OK;
+    int64_t blocks = (n_seg + 7) / 8;
+    if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
+    EQH_DISPATCH_V(C, {
+      if (gamma)
+        k_fused_bwd<V, true, false><<<(unsigned)blocks, 256, 0, st>>>(A, B, ia, ib, iu, rowptr, n_seg, gamma, eps, dU,
+                                                                    u_rowptr, dOp, nullptr);
+      else
+        k_fused_bwd<V, false, false><<<(unsigned)blocks, 256, 0, st>>>(A, B, ia, ib, iu, rowptr, n_seg, gamma, eps, dU,
+                                                                     u_rowptr, dOp, nullptr);
+    });
+  }
+  EQH_LAUNCH_RC();
+}
+
+int eqh_colsum(const float* partial, int64_t rows, int64_t cols, float* out, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && (cols == 0 || (partial && out)));
+  if (cols == 0) return EQH_OK;
+  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, cols, out);
+  EQH_LAUNCH_RC();
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Incidence CSR build: stable counting sort by destination, on device, int32 outputs.
+// HBM-bound integer work: every pass is a coalesced stream over the Z incidences plus
+// L2-resident histogram traffic.  The result (rowptr, perm) is unique, so the integer atomics
+// used for counting / slot claiming do not affect determinism: each segment is put into
+// ascending incidence order afterwards (== torch.sort(stable=True) by destination).
+#include "common.cuh"
+
+namespace eqh {
+
+template <typename IdxT>
+__global__ void k_hist(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, int32_t* __restrict__ cnt,
+                       int32_t* __restrict__ dst32, int32_t* __restrict__ status) {
+  int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  int64_t d = (int64_t)dst[z];
+  if (d < 0 || d >= n_dst) {
+    if (status) atomicExch(status, 1);
+    if (dst32) dst32[z] = -1;
+    return;
+  }
+  if (dst32) dst32[z] = (int32_t)d;
+  atomicAdd(cnt + d, 1);
+}
+
+// exclusive scan of cnt[0..n) -> rowptr[0..n], cursor[0..n) ; one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan(const int32_t* cnt, int64_t n, int32_t* rowptr, int32_t* cursor /* may alias cnt */) {
+  __shared__ int32_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = t * per, hi = min(n, lo + per);
+  int32_t s = 0;
+  for (int64_t i = lo; i < hi; ++i) s += cnt[i];
+  part[t] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    int32_t v = (t >= o) ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = (t == 0) ? 0 : part[t - 1];
+  for (int64_t i = lo; i < hi; ++i) {
+    int32_t c = cnt[i];
+    rowptr[i] = run;
+    cursor[i] = run;
+    run += c;
+  }
+  if (t == 1023) rowptr[n] = part[1023];
+}
+
+template <typename IdxT>
+__global__ void k_place(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, int32_t* __restrict__ cursor,
+                        int32_t* __restrict__ slot_z) {
+  int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  int64_t d = (int64_t)dst[z];
+  if (d < 0 || d >= n_dst) return;
+  int32_t p = atomicAdd(cursor + d, 1);
+  slot_z[p] = (int32_t)z;
+}
+
+// one warp per segment: order the segment's incidence ids ascending by counting ranks.
+template <typename IdxT>
+__global__ void k_order(const int32_t* __restrict__ rowptr, int64_t n_dst, const int32_t* __restrict__ slot_z,
+                        const IdxT* __restrict__ other, int32_t* __restrict__ perm, int32_t* __restrict__ other_sorted) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp; s < n_dst; s += nwarps) {
+    const int32_t lo = rowptr[s], hi = rowptr[s + 1];
+    const int32_t len = hi - lo;
+    if (len <= 32) {
+      int32_t mine = (lane < len) ? slot_z[lo + lane] : 0x7fffffff;
+      int32_t rank = 0;
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) rank += (__shfl_sync(kFull, mine, k) < mine);
+      if (lane < len) {
+        perm[lo + rank] = mine;
+        if (other_sorted) other_sorted[lo + rank] = (int32_t)other[mine];
+      }
+    } else {
+      for (int32_t a = lo + lane; a < hi; a += 32) {
+        const int32_t mine = slot_z[a];
+        int32_t rank = 0;
+        for (int32_t b = lo; b < hi; ++b) rank += (slot_z[b] < mine);
+        perm[lo + rank] = mine;
+        if (other_sorted) other_sorted[lo + rank] = (int32_t)other[mine];
+      }
+    }
+  }
+}
+
+template <typename IdxT>
+static int build(const IdxT* dst, const IdxT* other, int64_t Z, int64_t n_dst, int32_t* rowptr, int32_t* perm,
+                 int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  EQH_CHECK_ARG(Z >= 0 && n_dst >= 0 && rowptr && (Z == 0 || (dst && perm)));
+  EQH_CHECK_ARG(Z < (int64_t)1 << 31 && n_dst < (int64_t)1 << 31);
+  EQH_CHECK_ARG(!(other_sorted && !other) || Z == 0);
+  if (ws_bytes < eqh_incidence_workspace_bytes(Z, n_dst) || (!ws && ws_bytes)) return EQH_ERR_WORKSPACE;
+  int32_t* cnt = static_cast<int32_t*>(ws);        // [n_dst + 1]  (counts, then cursors)
+  int32_t* slot_z = cnt + (n_dst + 1);             // [Z]
+  cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)(n_dst + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  const int T = 256;
+  if (Z > 0) k_hist<IdxT><<<(unsigned)((Z + T - 1) / T), T, 0, st>>>(dst, Z, n_dst, cnt, dst32, status);
+  // in-place: the scan reads cnt[i] before overwriting cursor[i] (same thread, same i)
+  k_scan<<<1, 1024, 0, st>>>(cnt, n_dst, rowptr, cnt);
+  if (Z > 0) {
+    k_place<IdxT><<<(unsigned)((Z + T - 1) / T), T, 0, st>>>(dst, Z, n_dst, cnt, slot_z);
+    int64_t warps = n_dst;
+    int64_t blocks = (warps * 32 + T - 1) / T;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    if (blocks < 1) blocks = 1;
+    k_order<IdxT><<<(unsigned)blocks, T, 0, st>>>(rowptr, n_dst, slot_z, other, perm, other_sorted);
+  }
+  EQH_LAUNCH_RC();
+}
+
+}  // namespace eqh
+
+extern "C" {
+
+size_t eqh_incidence_workspace_bytes(int64_t Z, int64_t n_dst) {
+  if (Z < 0 || n_dst < 0) return 0;
+  return sizeof(int32_t) * (size_t)(n_dst + 1 + Z);
+}
+
+int eqh_incidence_build_i64(const int64_t* dst, const int64_t* other, int64_t Z, int64_t n_dst, int32_t* rowptr,
+                            int32_t* perm, int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws,
+                            size_t ws_bytes, eqh_stream_t stream) {
+  return eqh::build<int64_t>(dst, other, Z, n_dst, rowptr, perm, dst32, other_sorted, status, ws, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int eqh_incidence_build_i32(const int32_t* dst, const int32_t* other, int64_t Z, int64_t n_dst, int32_t* rowptr,
+                            int32_t* perm, int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws,
+                            size_t ws_bytes, eqh_stream_t stream) {
+  return eqh::build<int32_t>(dst, other, Z, n_dst, rowptr, perm, dst32, other_sorted, status, ws, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

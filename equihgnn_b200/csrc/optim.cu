@@ -1,0 +1,56 @@
+// Flat fused Adam over one contiguous fp32 buffer (torch.optim.Adam semantics, main.py:137-140).
+// Pure streaming kernel: 4 loads + 3 stores of 4 B per element, HBM-bound.
+#include "common.cuh"
+
+namespace eqh {
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                               float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                               float wd, float bc1, float bc2_sqrt, float gscale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i];
+    float gi = g[i] * gscale;
+    if (wd != 0.f) gi += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace eqh
+
+extern "C" {
+
+int eqh_version(void) { return 100; /* 0.1.0 */ }
+
+const char* eqh_error_string(int rc) {
+  switch (rc) {
+    case EQH_OK: return "ok";
+    case EQH_ERR_ARG: return "invalid argument (null pointer, negative size or misaligned buffer)";
+    case EQH_ERR_UNSUPPORTED: return "unsupported configuration (feature width / hidden width / K outside the implemented set)";
+    case EQH_ERR_WORKSPACE: return "workspace too small";
+    default: return rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "unknown error";
+  }
+}
+
+int eqh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(n >= 0 && step >= 1 && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
+  if (n == 0) return EQH_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  k_adam<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                         beta2, eps, weight_decay, bc1, sqrtf(bc2),
+                                                                         grad_scale);
+  EQH_LAUNCH_RC();
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Deterministic segmented reductions over CSR-grouped rows (no atomics) and the matching row
+// gather.  HBM-bound: one warp streams one segment with 128-bit coalesced loads (a 512 B
+// contiguous run per warp instruction for C >= 128), four rows in flight per warp.
+//
+// Algorithmic bytes per call (figure P): 4C(Z + n_out) + 4(Z + n_out + 1).
+#include "common.cuh"
+
+namespace eqh {
+
+template <int V, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__ table, const int32_t* __restrict__ idx,
+                                                        const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ src_rowptr, int64_t n_out, int mode,
+                                                        float* __restrict__ out, int64_t ld) {
+  table += (int64_t)blockIdx.y * (32 * V);  // column block of a wider row (row stride ld)
+  out += (int64_t)blockIdx.y * (32 * V);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp; s < n_out; s += nwarps) {
+    const int32_t lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+    Row<V> acc;
+    acc.zero();
+    int32_t k = lo;
+    for (; k + 4 <= hi; k += 4) {
+      int32_t r[4];
+      float w[4];
+      Row<V> x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = idx ? __ldg(idx + k + u) : (k + u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u].load(table + (int64_t)r[u] * ld, lane);
+      if constexpr (WEIGHTED) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = inv_count(src_rowptr, r[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // strictly ascending k: same association as a sequential scatter_add_
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] += WEIGHTED ? w[u] * x[u].v[i] : x[u].v[i];
+      }
+    }
+    for (; k < hi; ++k) {
+      const int32_t r = idx ? __ldg(idx + k) : k;
+      Row<V> x;
+      x.load(table + (int64_t)r * ld, lane);
+      const float w = WEIGHTED ? inv_count(src_rowptr, r) : 1.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] += WEIGHTED ? w * x.v[i] : x.v[i];
+    }
+    if (mode == EQH_REDUCE_MEAN) {
+      const float cnt = (float)max(hi - lo, 1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] = acc.v[i] / cnt;  // true division, as torch_scatter's true_divide_
+    }
+    acc.store(out + s * ld, lane);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ table, const int32_t* __restrict__ idx,
+                                                      const int32_t* __restrict__ scale_rowptr, int64_t n_rows,
+                                                      float* __restrict__ out, int64_t ld) {
+  table += (int64_t)blockIdx.y * (32 * V);
+  out += (int64_t)blockIdx.y * (32 * V);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp * 2; r0 < n_rows; r0 += nwarps * 2) {
+    const bool two = r0 + 1 < n_rows;
+    const int32_t s0 = idx ? __ldg(idx + r0) : (int32_t)r0;
+    const int32_t s1 = two ? (idx ? __ldg(idx + r0 + 1) : (int32_t)(r0 + 1)) : s0;
+    Row<V> a, b;
+    a.load(table + (int64_t)s0 * ld, lane);
+    b.load(table + (int64_t)s1 * ld, lane);
+    const float w0 = inv_count(scale_rowptr, s0), w1 = inv_count(scale_rowptr, s1);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a.v[i] *= w0; b.v[i] *= w1; }
+    a.store(out + r0 * ld, lane);
+    if (two) b.store(out + (r0 + 1) * ld, lane);
+  }
+}
+
+// widest supported column block (32*V, V in {16,8,4,2,1}) dividing C; 0 if C % 32 != 0
+static int64_t col_block(int64_t C) {
+  for (int64_t cb = 512; cb >= 32; cb >>= 1)
+    if (C % cb == 0) return cb;
+  return 0;
+}
+
+static unsigned grid_for_warps(int64_t warps_needed, int threads) {
+  int64_t per = threads / 32;
+  int64_t blocks = (warps_needed + per - 1) / per;
+  const int64_t cap = (int64_t)kSMs * 8 * 4;  // 8 CTAs of 256 threads per SM resident; allow 4 waves before striding
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace eqh
+
+extern "C" {
+
+int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* rowptr, const int32_t* src_rowptr,
+                      int64_t n_out, int64_t C, int mode, float* out, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(n_out >= 0 && rowptr && (n_out == 0 || (out && table)));
+  EQH_CHECK_ARG(mode == EQH_REDUCE_SUM || mode == EQH_REDUCE_MEAN);
+  EQH_CHECK_ARG(aligned16(table) && aligned16(out));
+  const int64_t CB = col_block(C);
+  if (C <= 0 || CB == 0 || C / CB > 65535) return EQH_ERR_UNSUPPORTED;
+  if (n_out == 0) return EQH_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(grid_for_warps(n_out, 256), (unsigned)(C / CB));
+  EQH_DISPATCH_V(CB, {
+    if (src_rowptr)
+      k_gather_reduce<V, true><<<grid, 256, 0, st>>>(table, idx, rowptr, src_rowptr, n_out, mode, out, C);
+    else
+      k_gather_reduce<V, false><<<grid, 256, 0, st>>>(table, idx, rowptr, nullptr, n_out, mode, out, C);
+  });
+  EQH_LAUNCH_RC();
+}
+
+int eqh_gather_rows(const float* table, const int32_t* idx, const int32_t* scale_rowptr, int64_t n_rows, int64_t C,
+                    float* out, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (out && table)));
+  EQH_CHECK_ARG(aligned16(table) && aligned16(out));
+  const int64_t CB = col_block(C);
+  if (C <= 0 || CB == 0 || C / CB > 65535) return EQH_ERR_UNSUPPORTED;
+  if (n_rows == 0) return EQH_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(grid_for_warps((n_rows + 1) / 2, 256), (unsigned)(C / CB));
+  EQH_DISPATCH_V(CB, { k_gather_rows<V><<<grid, 256, 0, st>>>(table, idx, scale_rowptr, n_rows, out, C); });
+  EQH_LAUNCH_RC();
+}
+
+}  // extern "C"

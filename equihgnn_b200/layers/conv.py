@@ -1,0 +1,144 @@
+"""MHNN hypergraph convolutions on the B200 kernels -- drop-ins for the reference's
+`MHNNConv` / `MHNNSConv` (equihgnn/models/layers/conv.py:8-182): same constructor and forward
+signatures, same parameter names / shapes / seeded initial values.
+
+How a layer maps onto the kernels (C = hid_dim, Z incidences, CSR built once per batch):
+
+  W(cat(a[ia], b[ib])) followed by scatter(mean|sum)         (conv.py:90-93, 96-97, 175-177)
+    with a 2-layer MLP W = lin1 o LN o ReLU o lin0:
+      * lin0 is split over the concat and applied to the source rows (N or E of them, not Z):
+            A = a @ W0[:, :C]^T,   B = b @ W0[:, C:]^T + b0
+      * one kernel does gather-add -> ReLU -> LayerNorm -> segmented reduce (eqh_fused_msg_*),
+        the [Z,2C] / [Z,C] per-incidence tensors never exist;
+      * lin1 commutes with the reduction: out = U @ W1^T + b1 * (count>0)   (mean)
+                                          out = U @ W1^T + b1 * count       (sum)
+  W1(X)[vertex] -> scatter                                    (conv.py:172-173)
+      gather fused into the segmented reduction (eqh_gather_reduce).
+
+Anything outside that shape (1-, 3+-layer or absent MLPs, BatchNorm, dropout in training,
+input norm) runs as an unfused composition of the same CUDA primitives: row gather kernel ->
+torch MLP on Z rows -> deterministic segmented reduction kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .mlp import MLP
+
+
+def _mk(in_mult, hid, layers, dropout, normalization, input_norm):
+    return MLP(hid * in_mult, hid, hid, layers, dropout=dropout, Normalization=normalization, InputNorm=input_norm)
+
+
+class _TakeSecondHalf:
+    """mlpK_layers == 0 in the reference is `lambda X: X[..., hid_dim:]` (conv.py:34,47,60,73,143)."""
+
+    def __init__(self, hid):
+        self.hid = hid
+
+    def __call__(self, x):
+        return x[..., self.hid:]
+
+
+def _pair_scatter(W, a, b, inc: ops.Incidence, group: str, aggr: str):
+    """reduce over `group` of W(cat(a[vertex], b[edges])); a is [N,C], b is [E,C]."""
+    C = a.shape[-1]
+    if isinstance(W, MLP) and W.fusable():
+        w0, b0 = W.lins[0].weight, W.lins[0].bias
+        A = F.linear(a, w0[:, :C])
+        B = F.linear(b, w0[:, C:], b0)
+        gamma, beta, eps = W.ln_affine()
+        U = ops.fused_message(A, B, gamma, beta, inc, group, aggr, eps)
+        scale = inc.nonempty(group) if aggr == "mean" else inc.counts(group)
+        return F.linear(U, W.lins[1].weight) + W.lins[1].bias * scale
+    # unfused composition of the same primitives
+    av = ops.gather_rows(a, inc.vertex32, inc.rowptr_v, inc.perm_v)
+    be = ops.gather_rows(b, inc.edges32, inc.rowptr_e, inc.perm_e)
+    msg = W(torch.cat((av, be), -1))
+    if group == "e":
+        return ops.segment_reduce(msg, inc.rowptr_e, inc.perm_e, inc.edges32, inc.E, aggr)
+    return ops.segment_reduce(msg, inc.rowptr_v, inc.perm_v, inc.vertex32, inc.N, aggr)
+
+
+def _fold_leading(fn, tensors, n_out_tensors):
+    """Run `fn` on 2-D slices when the caller passes leading dims ([..., rows, C]; the Equiformer
+    wrapper passes [1,N,C], equihnn_equiformer.py:83-88)."""
+    lead = tensors[0].shape[:-2]
+    if len(lead) == 0:
+        return fn(*tensors)
+    flats = [t.reshape(-1, t.shape[-2], t.shape[-1]) for t in tensors]
+    outs = [fn(*[f[i] for f in flats]) for i in range(flats[0].shape[0])]
+    if n_out_tensors == 1:
+        return torch.stack(outs, 0).reshape(*lead, *outs[0].shape)
+    return tuple(torch.stack([o[j] for o in outs], 0).reshape(*lead, *outs[0][j].shape) for j in range(n_out_tensors))
+
+
+class MHNNConv(nn.Module):
+    def __init__(self, hid_dim, mlp1_layers=1, mlp2_layers=1, mlp3_layers=1, mlp4_layers=1, aggr="mean", dropout=0.0,
+                 normalization="None", input_norm=False):
+        super().__init__()
+        for k, layers in enumerate((mlp1_layers, mlp2_layers, mlp3_layers, mlp4_layers), start=1):
+            w = _mk(2, hid_dim, layers, dropout, normalization, input_norm) if layers > 0 else _TakeSecondHalf(hid_dim)
+            setattr(self, f"W{k}", w)
+        self.hid_dim = hid_dim
+        self.aggr = aggr
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for k in (1, 2, 3, 4):
+            w = getattr(self, f"W{k}")
+            if isinstance(w, MLP):
+                w.reset_parameters()
+
+    def forward(self, X, E, vertex, edges, incidence: "ops.Incidence | None" = None):
+        N, Eh = X.shape[-2], E.shape[-2]
+        inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, N, Eh)
+
+        def layer(x, e):
+            Me = _pair_scatter(self.W1, x, e, inc, "e", self.aggr)       # conv.py:90-93
+            e = self.W2(torch.cat((e, Me), -1))                           # conv.py:94
+            Mv = _pair_scatter(self.W3, x, e, inc, "v", self.aggr)       # conv.py:96-97
+            x = self.W4(torch.cat((x, Mv), -1))                           # conv.py:98
+            return x, e
+
+        return _fold_leading(layer, (X, E), 2)
+
+
+class MHNNSConv(nn.Module):
+    def __init__(self, hid_dim, mlp1_layers=1, mlp2_layers=1, mlp3_layers=1, aggr="mean", alpha=0.5, dropout=0.0,
+                 normalization="None", input_norm=False):
+        super().__init__()
+        self.W1 = _mk(1, hid_dim, mlp1_layers, dropout, normalization, input_norm) if mlp1_layers > 0 else nn.Identity()
+        self.W2 = _mk(2, hid_dim, mlp2_layers, dropout, normalization, input_norm) if mlp2_layers > 0 \
+            else _TakeSecondHalf(hid_dim)
+        if mlp3_layers > 0:
+            self.W3 = _mk(1, hid_dim, mlp3_layers, dropout, normalization, input_norm)
+        else:
+            # reference quirk kept on purpose (conv.py:155-156): the Identity is stored as `W`,
+            # so forward raises AttributeError on `self.W3` exactly like the reference does.
+            self.W = nn.Identity()
+        self.hid_dim = hid_dim
+        self.aggr = aggr
+        self.alpha = alpha
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for k in (1, 2, 3):
+            w = getattr(self, f"W{k}", None)
+            if isinstance(w, MLP):
+                w.reset_parameters()
+
+    def forward(self, X, vertex, edges, X0, incidence: "ops.Incidence | None" = None, num_hyperedges=None):
+        N = X.shape[-2]
+        inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, N, num_hyperedges)
+
+        def layer(x, x0):
+            Xe = ops.v2e_gather_reduce(self.W1(x), inc, self.aggr)        # conv.py:172-173
+            Xv = _pair_scatter(self.W2, x, Xe, inc, "v", self.aggr)       # conv.py:175-177
+            x = (1 - self.alpha) * Xv + self.alpha * x0                   # conv.py:179
+            return self.W3(x)                                             # conv.py:180
+
+        return _fold_leading(layer, (X, X0), 1)

@@ -1,0 +1,510 @@
+"""Tensor-level operators over the C ABI (device pointers in, kernels enqueued on the current
+stream) and the autograd Functions the drop-in modules are made of.
+
+PyTorch is plumbing here: it owns the device memory, the stream and the autograd tape; every
+index build, gather, segmented reduction, kNN and edge-model evaluation is a hand-written
+sm_100a kernel in csrc/.
+"""
+from __future__ import annotations
+
+import os
+import weakref
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+SUM, MEAN = 0, 1
+_MODES = {"sum": SUM, "add": SUM, "mean": MEAN}
+KNN_K = 16
+M_DIM = 16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (equihgnn_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.int32:
+        raise RuntimeError(f"{what}: expected a CUDA int32 tensor")
+    return t.contiguous()
+
+
+def partial_rows() -> int:
+    return _lib.load().eqh_partial_rows()
+
+
+# ----------------------------------------------------------------------------------------------
+# incidence CSR
+# ----------------------------------------------------------------------------------------------
+def csr_build(dst: torch.Tensor, n_dst: int, other: Optional[torch.Tensor] = None):
+    """Stable group-by-destination.  Returns (rowptr[n_dst+1], perm[Z], dst32[Z], other_sorted[Z] | None),
+    all int32 on dst's device.  dst / other are int64 or int32."""
+    lib = _lib.load()
+    if not dst.is_cuda:
+        raise RuntimeError("csr_build: expected a CUDA index tensor")
+    if dst.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError(f"csr_build: index dtype {dst.dtype} not supported")
+    dst = dst.contiguous().view(-1)
+    Z = dst.numel()
+    dev = dst.device
+    if other is not None:
+        other = other.contiguous().view(-1).to(dst.dtype)
+        if other.numel() != Z:
+            raise RuntimeError("csr_build: dst / other length mismatch")
+    rowptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(Z, dtype=torch.int32, device=dev)
+    dst32 = torch.empty(Z, dtype=torch.int32, device=dev)
+    osort = torch.empty(Z, dtype=torch.int32, device=dev) if other is not None else None
+    nbytes = lib.eqh_incidence_workspace_bytes(Z, n_dst)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
+    check_idx = os.environ.get("EQH_CHECK_INDEX", "0") == "1"
+    status = torch.zeros(1, dtype=torch.int32, device=dev) if check_idx else None
+    fn = lib.eqh_incidence_build_i64 if dst.dtype == torch.int64 else lib.eqh_incidence_build_i32
+    rc = fn(_p(dst), _p(other), Z, n_dst, _p(rowptr), _p(perm), _p(dst32), _p(osort), _p(status), _p(ws), nbytes,
+            _stream())
+    _lib.check(rc, "eqh_incidence_build")
+    if check_idx and int(status.item()) != 0:
+        raise RuntimeError("index out of range in incidence build (EQH_CHECK_INDEX=1)")
+    return rowptr, perm, dst32, osort
+
+
+@dataclass
+class Incidence:
+    """Device CSR of a batched hypergraph in both directions, built once per batch.
+
+    by hyperedge: rowptr_e[E+1], perm_e[Z] (incidences sorted by hyperedge, stable), vtx_by_e[Z]
+    by vertex   : rowptr_v[N+1], perm_v[Z], edge_by_v[Z]
+    vertex32 / edges32: the original (unsorted) incidence lists as int32.
+    """
+    N: int
+    E: int
+    Z: int
+    rowptr_e: torch.Tensor
+    perm_e: torch.Tensor
+    vtx_by_e: torch.Tensor
+    rowptr_v: torch.Tensor
+    perm_v: torch.Tensor
+    edge_by_v: torch.Tensor
+    vertex32: torch.Tensor
+    edges32: torch.Tensor
+    _nonempty_e: Optional[torch.Tensor] = None
+    _nonempty_v: Optional[torch.Tensor] = None
+    _cnt_e: Optional[torch.Tensor] = None
+    _cnt_v: Optional[torch.Tensor] = None
+
+    def counts(self, which: str) -> torch.Tensor:
+        """float32 [n,1] incidence count per hyperedge ('e') or vertex ('v')."""
+        if which == "e":
+            if self._cnt_e is None:
+                self._cnt_e = (self.rowptr_e[1:] - self.rowptr_e[:-1]).to(torch.float32).unsqueeze(-1)
+            return self._cnt_e
+        if self._cnt_v is None:
+            self._cnt_v = (self.rowptr_v[1:] - self.rowptr_v[:-1]).to(torch.float32).unsqueeze(-1)
+        return self._cnt_v
+
+    def nonempty(self, which: str) -> torch.Tensor:
+        """float32 [n,1] mask: 1 where the segment has at least one incidence."""
+        if which == "e":
+            if self._nonempty_e is None:
+                self._nonempty_e = (self.counts("e") > 0).to(torch.float32)
+            return self._nonempty_e
+        if self._nonempty_v is None:
+            self._nonempty_v = (self.counts("v") > 0).to(torch.float32)
+        return self._nonempty_v
+
+
+def build_incidence(vertex: torch.Tensor, edges: torch.Tensor, num_vertices: int,
+                    num_hyperedges: Optional[int] = None) -> Incidence:
+    """vertex / edges: the reference's data.edge_index0 / edge_index1 ([Z] int64, HData numbering,
+    data/utils.py:172-178).  num_hyperedges=None reproduces torch_scatter's `index.max()+1`
+    (one host sync, exactly like the reference at conv.py:173); pass it to stay asynchronous."""
+    if num_hyperedges is None:
+        num_hyperedges = int(edges.max().item()) + 1 if edges.numel() else 0
+    rowptr_e, perm_e, edges32, vtx_by_e = csr_build(edges, num_hyperedges, vertex)
+    rowptr_v, perm_v, vertex32, edge_by_v = csr_build(vertex, num_vertices, edges)
+    return Incidence(num_vertices, num_hyperedges, vertex.numel(), rowptr_e, perm_e, vtx_by_e, rowptr_v, perm_v,
+                     edge_by_v, vertex32, edges32)
+
+
+class _IncidenceCache:
+    """Keyed by the *identity* of the caller's index tensors (weak references + version counters),
+    so the three conv layers of a forward pass share one build; never by data pointer, which the
+    caching allocator recycles."""
+
+    def __init__(self):
+        self._slot = None
+
+    def get(self, vertex, edges, N, E) -> Incidence:
+        s = self._slot
+        if s is not None:
+            v_ref, e_ref, v_ver, e_ver, n, e_req, inc = s
+            if v_ref() is vertex and e_ref() is edges and v_ver == vertex._version and e_ver == edges._version \
+                    and n == N and e_req == E:
+                return inc
+        inc = build_incidence(vertex, edges, N, E)
+        self._slot = (weakref.ref(vertex), weakref.ref(edges), vertex._version, edges._version, N, E, inc)
+        return inc
+
+
+incidence_cache = _IncidenceCache()
+
+
+# ----------------------------------------------------------------------------------------------
+# raw launches
+# ----------------------------------------------------------------------------------------------
+def gather_reduce_raw(table, idx, rowptr, src_rowptr, n_out: int, mode: int) -> torch.Tensor:
+    C = table.shape[-1]
+    out = torch.empty((n_out, C), dtype=torch.float32, device=table.device)
+    rc = _lib.load().eqh_gather_reduce(_p(table), _p(idx), _p(rowptr), _p(src_rowptr), n_out, C, mode, _p(out),
+                                       _stream())
+    _lib.check(rc, f"eqh_gather_reduce(C={C})")
+    return out
+
+
+def gather_rows_raw(table, idx, scale_rowptr, n_rows: int) -> torch.Tensor:
+    C = table.shape[-1]
+    out = torch.empty((n_rows, C), dtype=torch.float32, device=table.device)
+    rc = _lib.load().eqh_gather_rows(_p(table), _p(idx), _p(scale_rowptr), n_rows, C, _p(out), _stream())
+    _lib.check(rc, f"eqh_gather_rows(C={C})")
+    return out
+
+
+def colsum_raw(partial: torch.Tensor) -> torch.Tensor:
+    rows, cols = partial.shape
+    out = torch.empty(cols, dtype=torch.float32, device=partial.device)
+    _lib.check(_lib.load().eqh_colsum(_p(partial), rows, cols, _p(out), _stream()), "eqh_colsum")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd Functions
+# ----------------------------------------------------------------------------------------------
+class _SegmentReduce(torch.autograd.Function):
+    """out[s] = reduce over the rows z of src with dst[z] == s (torch_scatter.scatter replacement)."""
+
+    @staticmethod
+    def forward(ctx, src, rowptr, perm, dst32, n_out, mode):
+        src = _f32(src, "segment_reduce src")
+        ctx.save_for_backward(rowptr, dst32)
+        ctx.mode = mode
+        ctx.Z = src.shape[0]
+        return gather_reduce_raw(src, perm, rowptr, None, n_out, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        rowptr, dst32 = ctx.saved_tensors
+        g = _f32(g, "segment_reduce grad")
+        return gather_rows_raw(g, dst32, rowptr if ctx.mode == MEAN else None, ctx.Z), None, None, None, None, None
+
+
+class _GatherRows(torch.autograd.Function):
+    """out[z] = table[idx[z]]; backward is a deterministic segmented sum over the CSR of idx."""
+
+    @staticmethod
+    def forward(ctx, table, idx32, rowptr, perm):
+        table = _f32(table, "gather_rows table")
+        ctx.save_for_backward(rowptr, perm)
+        ctx.n = table.shape[0]
+        return gather_rows_raw(table, idx32, None, idx32.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        rowptr, perm = ctx.saved_tensors
+        return gather_reduce_raw(_f32(g, "gather_rows grad"), perm, rowptr, None, ctx.n, SUM), None, None, None
+
+
+class _GatherReduce(torch.autograd.Function):
+    """out[s] = reduce_{k in segment s} table[idx_sorted[k]]  (gather fused into the reduction).
+
+    Backward: dtable[r] = sum over the incidences of r (the other grouping) of w * dout[seg]."""
+
+    @staticmethod
+    def forward(ctx, table, rowptr, idx_sorted, rowptr_other, seg_by_other, n_out, mode):
+        table = _f32(table, "gather_reduce table")
+        ctx.save_for_backward(rowptr, rowptr_other, seg_by_other)
+        ctx.mode = mode
+        ctx.n_src = table.shape[0]
+        return gather_reduce_raw(table, idx_sorted, rowptr, None, n_out, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        rowptr, rowptr_other, seg_by_other = ctx.saved_tensors
+        g = _f32(g, "gather_reduce grad")
+        d = gather_reduce_raw(g, seg_by_other, rowptr_other, rowptr if ctx.mode == MEAN else None, ctx.n_src, SUM)
+        return d, None, None, None, None, None, None
+
+
+class _FusedMsg(torch.autograd.Function):
+    """U[s] = reduce_{k in s} LN(ReLU(A[ia(k)] + B[ib(k)])) -- see eqh_fused_msg_fwd.
+
+    group == 'v': segments are vertices (A row = the vertex, B gathered by hyperedge)  -> E2V
+    group == 'e': segments are hyperedges (A gathered by vertex, B row = the hyperedge) -> V2E
+    """
+
+    @staticmethod
+    def forward(ctx, A, B, gamma, beta, inc: Incidence, group: str, mode: int, eps: float):
+        lib = _lib.load()
+        A = _f32(A, "fused_msg A")
+        B = _f32(B, "fused_msg B")
+        C = A.shape[-1]
+        if gamma is not None:
+            gamma = _f32(gamma, "fused_msg gamma")
+            beta = _f32(beta, "fused_msg beta")
+        if group == "v":
+            n_out, rowptr, ia, ib = inc.N, inc.rowptr_v, None, inc.edge_by_v
+        else:
+            n_out, rowptr, ia, ib = inc.E, inc.rowptr_e, inc.vtx_by_e, None
+        U = torch.empty((n_out, C), dtype=torch.float32, device=A.device)
+        rc = lib.eqh_fused_msg_fwd(_p(A), _p(B), _p(ia), _p(ib), _p(rowptr), n_out, C, _p(gamma), _p(beta), eps, mode,
+                                   _p(U), _stream())
+        _lib.check(rc, f"eqh_fused_msg_fwd(C={C})")
+        ctx.save_for_backward(A, B, gamma, beta)
+        ctx.inc, ctx.group, ctx.mode, ctx.eps = inc, group, mode, eps
+        return U
+
+    @staticmethod
+    def backward(ctx, dU):
+        lib = _lib.load()
+        A, B, gamma, beta = ctx.saved_tensors
+        inc, group, mode, eps = ctx.inc, ctx.group, ctx.mode, ctx.eps
+        dU = _f32(dU, "fused_msg grad")
+        C = A.shape[-1]
+        dev = A.device
+        dA = torch.empty_like(A)
+        dB = torch.empty_like(B)
+        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev) if gamma is not None else None
+        st = _stream()
+        if group == "v":
+            u_rp = inc.rowptr_v if mode == MEAN else None
+            # primary grouping (vertices): gradient of the segment-constant operand A + LayerNorm affine partials
+            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), inc.N, C, _p(gamma),
+                                       _p(beta), eps, _p(dU), _p(u_rp), _p(dA), _p(part), st)
+            _lib.check(rc, "eqh_fused_msg_bwd[v/primary]")
+            # secondary grouping (hyperedges): gradient of the gathered operand B
+            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), inc.E, C,
+                                       _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dB), None, st)
+            _lib.check(rc, "eqh_fused_msg_bwd[v/secondary]")
+        else:
+            u_rp = inc.rowptr_e if mode == MEAN else None
+            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), _p(inc.vtx_by_e), None, None, _p(inc.rowptr_e), inc.E, C, _p(gamma),
+                                       _p(beta), eps, _p(dU), _p(u_rp), _p(dB), _p(part), st)
+            _lib.check(rc, "eqh_fused_msg_bwd[e/primary]")
+            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), None, _p(inc.edge_by_v), _p(inc.edge_by_v), _p(inc.rowptr_v), inc.N, C,
+                                       _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dA), None, st)
+            _lib.check(rc, "eqh_fused_msg_bwd[e/secondary]")
+        dgamma = dbeta = None
+        if gamma is not None:
+            gb = colsum_raw(part)
+            dgamma, dbeta = gb[:C], gb[C:]
+        return dA, dB, dgamma, dbeta, None, None, None, None
+
+
+def knn16(pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """pos [N,3] float32 -> (idx [N,16] int32, d2 [N,16] float32), ascending, self first.
+    Raises RuntimeError when N < 16, as the reference's topk does (egnn_layer.py:281-283)."""
+    pos = _f32(pos.detach(), "knn16 pos")
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise RuntimeError(f"knn16: expected [N,3] coordinates, got {tuple(pos.shape)}")
+    N = pos.shape[0]
+    if N < KNN_K:
+        raise RuntimeError(f"selected index k out of range (k={KNN_K} > n={N})")
+    idx = torch.empty((N, KNN_K), dtype=torch.int32, device=pos.device)
+    d2 = torch.empty((N, KNN_K), dtype=torch.float32, device=pos.device)
+    _lib.check(_lib.load().eqh_knn16(_p(pos), N, _p(idx), _p(d2), _stream()), "eqh_knn16")
+    return idx, d2
+
+
+@dataclass
+class KnnGraph:
+    """kNN edges (i -> idx[i,k]) plus the transposed incidence (grouped by neighbour j) that the
+    deterministic dQ scatter of the backward needs."""
+    idx: torch.Tensor        # [N,16] int32
+    d2: torch.Tensor         # [N,16] float32
+    rowptr_j: torch.Tensor   # [N+1] int32
+    perm_j: torch.Tensor     # [N*16] int32 edge ids sorted by j (stable)
+
+
+def build_knn_graph(pos: torch.Tensor, need_transpose: bool = True) -> KnnGraph:
+    idx, d2 = knn16(pos)
+    if need_transpose:
+        rowptr_j, perm_j, _, _ = csr_build(idx.view(-1), idx.shape[0], None)
+    else:
+        rowptr_j = perm_j = None
+    return KnnGraph(idx, d2, rowptr_j, perm_j)
+
+
+class _EgnnEdge(torch.autograd.Function):
+    """(P, Q, wc, W2, b2, d2) -> (m_i [N,16], m_ij [N,16,16]) -- see eqh_egnn_edge_fwd."""
+
+    @staticmethod
+    def forward(ctx, P, Q, wc, W2, b2, d2, graph: KnnGraph):
+        lib = _lib.load()
+        P, Q, wc, W2, b2, d2 = (_f32(t, "egnn_edge") for t in (P, Q, wc, W2, b2, d2))
+        N, H = P.shape
+        dev = P.device
+        S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
+        Mij = torch.empty((N, KNN_K, M_DIM), dtype=torch.float32, device=dev)
+        Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
+        rc = lib.eqh_egnn_edge_fwd(_p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij),
+                                   _p(Mi), _stream())
+        _lib.check(rc, f"eqh_egnn_edge_fwd(H={H})")
+        ctx.save_for_backward(P, Q, wc, W2, b2, d2, S2)
+        ctx.graph = graph
+        ctx.set_materialize_grads(False)
+        return Mi, Mij
+
+    @staticmethod
+    def backward(ctx, dMi, dMij):
+        lib = _lib.load()
+        P, Q, wc, W2, b2, d2, S2 = ctx.saved_tensors
+        g = ctx.graph
+        N, H = P.shape
+        dev = P.device
+        if dMi is None and dMij is None:
+            return (None,) * 7
+        dMi = _f32(dMi, "egnn_edge dMi") if dMi is not None else None
+        dMij = _f32(dMij, "egnn_edge dMij") if dMij is not None else None
+        if g.rowptr_j is None:
+            g.rowptr_j, g.perm_j, _, _ = csr_build(g.idx.view(-1), N, None)
+        rows = partial_rows()
+        cols = (M_DIM + 1) * H + M_DIM
+        dP = torch.empty_like(P)
+        dPre = torch.empty((N * KNN_K, H), dtype=torch.float32, device=dev)
+        dd2 = torch.empty_like(d2) if ctx.needs_input_grad[5] else None
+        part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        rc = lib.eqh_egnn_edge_bwd(_p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi), _p(dMij), N, H,
+                                   _p(dP), _p(dPre), _p(dd2), _p(part), _stream())
+        _lib.check(rc, f"eqh_egnn_edge_bwd(H={H})")
+        red = colsum_raw(part)
+        dW2 = red[:M_DIM * H].view(M_DIM, H)
+        dwc = red[M_DIM * H:(M_DIM + 1) * H]
+        db2 = red[(M_DIM + 1) * H:]
+        # dQ[j] = sum over incoming edges (i,k) with idx[i,k] == j, in ascending edge order (deterministic)
+        dQ = gather_reduce_raw(dPre, g.perm_j, g.rowptr_j, None, N, SUM)
+        return dP, dQ, dwc, dW2, db2, dd2, None
+
+
+# ----------------------------------------------------------------------------------------------
+# public functional API
+# ----------------------------------------------------------------------------------------------
+def segment_reduce(src: torch.Tensor, rowptr, perm, dst32, n_out: int, reduce: str = "sum") -> torch.Tensor:
+    return _SegmentReduce.apply(src, rowptr, perm, dst32, n_out, _MODES[reduce])
+
+
+def gather_rows(table: torch.Tensor, idx32, rowptr, perm) -> torch.Tensor:
+    return _GatherRows.apply(table, idx32, rowptr, perm)
+
+
+def v2e_gather_reduce(Y: torch.Tensor, inc: Incidence, reduce: str) -> torch.Tensor:
+    """Xe[e] = reduce_{z in e} Y[vertex[z]]   (conv.py:172-173 without the [Z,C] intermediate)."""
+    return _GatherReduce.apply(Y, inc.rowptr_e, inc.vtx_by_e, inc.rowptr_v, inc.edge_by_v, inc.E, _MODES[reduce])
+
+
+def e2v_gather_reduce(Y: torch.Tensor, inc: Incidence, reduce: str) -> torch.Tensor:
+    """Xv[n] = reduce_{z in n} Y[edges[z]]."""
+    return _GatherReduce.apply(Y, inc.rowptr_v, inc.edge_by_v, inc.rowptr_e, inc.vtx_by_e, inc.N, _MODES[reduce])
+
+
+def fused_message(A, B, gamma, beta, inc: Incidence, group: str, reduce: str, eps: float = 1e-5) -> torch.Tensor:
+    return _FusedMsg.apply(A, B, gamma, beta, inc, group, _MODES[reduce], eps)
+
+
+def egnn_edge(P, Q, wc, W2, b2, d2, graph: KnnGraph):
+    return _EgnnEdge.apply(P, Q, wc, W2, b2, d2, graph)
+
+
+class _IndexCache:
+    def __init__(self):
+        self._slot = None
+
+    def get(self, index: torch.Tensor, n_out: Optional[int]):
+        s = self._slot
+        if s is not None:
+            ref, ver, n_req, val = s
+            if ref() is index and ver == index._version and n_req == n_out:
+                return val
+        n = n_out
+        if n is None:
+            n = int(index.max().item()) + 1 if index.numel() else 0   # torch_scatter's dim_size=None
+        rowptr, perm, dst32, _ = csr_build(index, n, None)
+        val = (n, rowptr, perm, dst32)
+        self._slot = (weakref.ref(index), index._version, n_out, val)
+        return val
+
+
+_index_cache = _IndexCache()
+
+
+def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out=None, dim_size: Optional[int] = None,
+            reduce: str = "sum") -> torch.Tensor:
+    """Drop-in for `torch_scatter.scatter` as the reference calls it (conv.py:91-93,97,173,177):
+    1-D index over dim=-2, reduce in {sum, add, mean}, deterministic (no atomics)."""
+    if out is not None:
+        raise NotImplementedError("scatter(out=...) is not used by the reference and is not implemented")
+    if reduce not in _MODES:
+        raise NotImplementedError(f"scatter reduce={reduce!r}: only sum/add/mean are implemented")
+    if src.dim() < 2 or index.dim() != 1 or (dim != -2 and dim != src.dim() - 2):
+        raise NotImplementedError("scatter: only a 1-D index over dim=-2 (rows of [..., Z, C]) is implemented")
+    if index.numel() != src.shape[-2]:
+        raise RuntimeError("scatter: index length must match src.shape[-2]")
+    n, rowptr, perm, dst32 = _index_cache.get(index, dim_size)
+    lead = src.shape[:-2]
+    if len(lead) == 0:
+        return segment_reduce(src, rowptr, perm, dst32, n, reduce)
+    flat = src.reshape(-1, src.shape[-2], src.shape[-1])
+    outs = [segment_reduce(flat[b], rowptr, perm, dst32, n, reduce) for b in range(flat.shape[0])]
+    return torch.stack(outs, 0).reshape(*lead, n, src.shape[-1])
+
+
+class _PoolCache:
+    def __init__(self):
+        self._slot = None
+
+    def get(self, batch: torch.Tensor, size: Optional[int]):
+        s = self._slot
+        if s is not None:
+            ref, ver, n_req, val = s
+            if ref() is batch and ver == batch._version and n_req == size:
+                return val
+        n = size
+        if n is None:
+            n = int(batch.max().item()) + 1 if batch.numel() else 0
+        rowptr, perm, dst32, _ = csr_build(batch, n, None)
+        val = (n, rowptr, perm, dst32)
+        self._slot = (weakref.ref(batch), batch._version, size, val)
+        return val
+
+
+_pool_cache = _PoolCache()
+
+
+def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = None) -> torch.Tensor:
+    """Drop-in for torch_geometric.nn.global_add_pool (mhnn.py:216, equihnn_egnn.py:167)."""
+    n, rowptr, perm, dst32 = _pool_cache.get(batch, size)
+    return segment_reduce(x, rowptr, perm, dst32, n, "sum")
+
+
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+               weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """In-place fused Adam on flat fp32 buffers (torch.optim.Adam semantics)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("adam_step_: flat contiguous CUDA float32 buffers required")
+    rc = _lib.load().eqh_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, betas[0], betas[1],
+                                   eps, weight_decay, step, grad_scale, _stream())
+    _lib.check(rc, "eqh_adam_step")

@@ -1,0 +1,169 @@
+/*
+ * eqh_b200.h -- C ABI of libeqh_b200.so: the B200 (sm_100a) kernels behind EquiHGNN's
+ * message-passing hot path.
+ *
+ * The reference (HySonLab/EquiHGNN) is pure Python and has no FFI of its own; the seam it
+ * offers is the nn.Module surface (MHNNConv / MHNNSConv / EGNN) and the third-party
+ * `torch_scatter.scatter` call.  Every entry point below replaces a specific group of ATen /
+ * torch_scatter calls inside those modules; the reference lines are cited per function.
+ * INTEGRATION.md shows the Python (ctypes) binding a maintainer adds on the reference side.
+ *
+ * Conventions (all functions):
+ *   - plain C types only: device pointers, explicit sizes, a CUDA stream handle;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated here;
+ *   - launches are asynchronous on `stream`; no function synchronises or throws;
+ *   - inputs are never modified;
+ *   - return value: 0 = EQH_OK, <0 = argument/support error (EQH_ERR_*), >0 = cudaError_t;
+ *   - feature matrices are row-major fp32 with row stride == C (contiguous), 16-byte aligned;
+ *   - device index arrays are int32 unless the name says i64;
+ *   - re-entrant: no global mutable state.
+ */
+#ifndef EQH_B200_H_
+#define EQH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* eqh_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define EQH_API __attribute__((visibility("default")))
+#else
+#define EQH_API
+#endif
+
+#define EQH_OK 0
+#define EQH_ERR_ARG (-1)         /* null pointer / negative size / misaligned buffer            */
+#define EQH_ERR_UNSUPPORTED (-2) /* valid request outside the implemented set (e.g. C % 32 != 0) */
+#define EQH_ERR_WORKSPACE (-3)   /* workspace too small                                          */
+
+#define EQH_REDUCE_SUM 0
+#define EQH_REDUCE_MEAN 1
+
+#define EQH_KNN_K 16 /* neighbours per atom (equihnn_egnn.py:128 num_nearest_neighbors=16) */
+#define EQH_M_DIM 16 /* EGNN message width (egnn_layer.py:150 m_dim=16)                     */
+
+EQH_API int eqh_version(void);
+EQH_API const char* eqh_error_string(int rc);
+/* number of CTAs the persistent kernels launch (= partial-buffer rows the caller must provide) */
+EQH_API int eqh_partial_rows(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Incidence CSR (stable sort by destination).
+ * Replaces: the implicit grouping done by torch_scatter's scatter_add_ over `index`
+ * (conv.py:91-93,97,173,177) and fixes the batched numbering of HData.__inc__
+ * (data/utils.py:172-178).  For dst[z] in [0,n_dst):
+ *     rowptr[s]            = #{z : dst[z] < s}                       (n_dst+1 entries)
+ *     perm[rowptr[s] + r]  = the r-th smallest z with dst[z] == s     (stable)
+ *     dst32[z]             = (int32) dst[z]
+ *     other_sorted[k]      = (int32) other[perm[k]]    (optional, other may be NULL)
+ * Bit-exact against torch.sort(stable=True) / bincount / cumsum.
+ * status (optional, 1 int32, caller zeroes it): set to 1 if any dst is outside [0,n_dst).
+ * ---------------------------------------------------------------------------------------- */
+EQH_API size_t eqh_incidence_workspace_bytes(int64_t Z, int64_t n_dst);
+EQH_API int eqh_incidence_build_i64(const int64_t* dst, const int64_t* other, int64_t Z, int64_t n_dst, int32_t* rowptr,
+                            int32_t* perm, int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws,
+                            size_t ws_bytes, eqh_stream_t stream);
+EQH_API int eqh_incidence_build_i32(const int32_t* dst, const int32_t* other, int64_t Z, int64_t n_dst, int32_t* rowptr,
+                            int32_t* perm, int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws,
+                            size_t ws_bytes, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Deterministic segmented reduction (no atomics), the replacement of
+ * torch_scatter.scatter(src, index, dim=-2, reduce="sum"|"mean") (conv.py:91-93,97,173,177)
+ * and of torch_geometric global_add_pool (mhnn.py:216, equihnn_egnn.py:167).
+ *     out[s,:] = reduce_{k in [rowptr[s],rowptr[s+1])}  w(k) * table[row(k),:]
+ *     row(k) = idx ? idx[k] : k ;  w(k) = 1 / max(1, src_rowptr[row+1]-src_rowptr[row]) if src_rowptr else 1
+ *     mean divides by max(1,count) (empty segments give 0, as torch_scatter does).
+ * Rows are added in ascending k, i.e. in original incidence order when idx = perm: the fp32
+ * result is bit-identical to the sequential CPU scatter_add_ of the reference.
+ * The same kernel is the backward of a gather+mean (src_rowptr carries the forward counts).
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* rowptr, const int32_t* src_rowptr,
+                      int64_t n_out, int64_t C, int mode, float* out, eqh_stream_t stream);
+/* out[r,:] = w(r) * table[idx[r],:]  for r in [0,n_rows): the backward of a segmented reduction
+ * (w = 1/max(1,count of segment idx[r]) when scale_rowptr != NULL) and the row gather X[vertex]. */
+EQH_API int eqh_gather_rows(const float* table, const int32_t* idx, const int32_t* scale_rowptr, int64_t n_rows, int64_t C,
+                    float* out, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused per-incidence message + segmented reduction:
+ *     t_k   = ReLU( A[ia(k),:] + B[ib(k),:] )            ia/ib == NULL -> the segment id
+ *     u_k   = gamma ? LayerNorm(t_k; gamma, beta, eps) : t_k
+ *     U[s,:] = reduce_{k in segment s} u_k               (sum | mean, empty -> 0)
+ * Replaces, per MLP(2 layers) applied to cat(X[vertex], E[edges]) and scattered
+ * (conv.py:90-93, 96-97, 175-177 with mlp.py:91-99): the gathers, the concat, ReLU, LayerNorm
+ * and the scatter.  The first Linear is split over the concat and applied to the N / E rows
+ * beforehand (A, B; bias folded into one of them), the last Linear commutes with the
+ * reduction and is applied to U afterwards -- both by the host module.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_fused_msg_fwd(const float* A, const float* B, const int32_t* ia, const int32_t* ib, const int32_t* rowptr,
+                      int64_t n_out, int64_t C, const float* gamma, const float* beta, float eps, int mode, float* U,
+                      eqh_stream_t stream);
+/* Backward of the above, evaluated per grouping (call once per operand):
+ *     g_k    = su(k) * dU[iu(k),:]      su = 1/max(1,count) from u_rowptr (mean) or 1 (NULL)
+ *     dpre_k = ReLU'( . ) * LayerNormBackward(g_k)   (t_k recomputed from A, B)
+ *     dOp[s,:] = sum_{k in segment s} dpre_k         (gradient of the operand that is constant
+ *                                                     over this grouping's segments)
+ *     dgb_partial[cta, 0:C] += sum g_k * xhat_k ; dgb_partial[cta, C:2C] += sum g_k
+ *         (optional; eqh_partial_rows() x 2C floats, then eqh_colsum)
+ * ia / ib / iu == NULL mean "the segment id".
+ */
+EQH_API int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const int32_t* ib, const int32_t* iu,
+                      const int32_t* rowptr, int64_t n_seg, int64_t C, const float* gamma, const float* beta,
+                      float eps, const float* dU, const int32_t* u_rowptr, float* dOp, float* dgb_partial,
+                      eqh_stream_t stream);
+/* out[c] = sum_r partial[r,c] for r in [0,rows): fixed-order (deterministic) column sum */
+EQH_API int eqh_colsum(const float* partial, int64_t rows, int64_t cols, float* out, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batch-wide 16-nearest-neighbour search on squared distance.
+ * Replaces egnn_layer.py:253-259,281-283: the [1,N,N,3] rel_coors, [1,N,N] ranking and topk(16,
+ * largest=False).  d2 = (dx*dx + dy*dy) + dz*dz evaluated with separate fp32 multiplies and adds
+ * (no FMA contraction), identical to the reference's (rel**2).sum(-1), so the neighbour set is
+ * bit-identical for tie-free inputs.  Output ascending by (d2, index); self is rank 0.
+ * N < 16 is an argument error (the reference's topk raises).  O(N*K) memory.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_knn16(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /*[N,16]*/, float* d2 /*[N,16]*/,
+              eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EGNN edge model phi_e + neighbour pooling (egnn_layer.py:298-310,357-358).
+ *   With W1 = edge_mlp.0.weight [H, 2C+1] (H = 2(2C+1), zero-padded by the host to a multiple of 64) split by columns into W1a|W1b|wc, the
+ *   host computes P = h W1a^T + b1 and Q = h W1b^T on the N atom rows; per kNN edge (i,k), j=idx[i,k]:
+ *     pre  = P[i,:] + Q[j,:] + d2[i,k] * wc
+ *     s2   = W2 silu(pre) + b2                 (W2 = edge_mlp.3.weight [16,H])
+ *     m_ij = silu(s2) ;  m_i = sum_k m_ij      (m_pool_method="sum")
+ *   S2 [N*16,16] (pre-activations) is kept for the backward; Mij [N*16,16] (optional) feeds phi_x.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_egnn_edge_fwd(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                      const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
+                      float* Mi, eqh_stream_t stream);
+EQH_API size_t eqh_egnn_edge_fwd_smem_bytes(int64_t H);
+/* Backward.  dMi [N,16] and/or dMij [N*16,16] (either may be NULL).  Outputs:
+ *   dP [N,H]; dPre [N*16,H] (per-edge gradient of `pre`: dQ[j] = sum over incoming edges, done by
+ *   eqh_gather_reduce over the transposed kNN incidence); dd2 [N,16] (optional);
+ *   part [eqh_partial_rows(), 17*H + 16]: per-CTA partial sums of dW2 (16*H), dwc (H), db2 (16),
+ *   to be finished with eqh_colsum.
+ */
+EQH_API int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                      const int32_t* idx, const float* d2, const float* S2, const float* dMi, const float* dMij,
+                      int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Flat fused Adam step over one contiguous fp32 parameter buffer (main.py:137-140:
+ * torch.optim.Adam(lr, weight_decay)); grad is multiplied by grad_scale first (1/world after the
+ * summed all-reduce).  L2 weight decay as torch.optim.Adam (not AdamW).
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  eqh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQH_B200_H_ */

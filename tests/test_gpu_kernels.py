@@ -1,0 +1,264 @@
+"""GPU parity tests for the kernels, called through the C ABI (ctypes binding in
+equihgnn_b200/_lib.py via ops.*_raw), against the CPU oracle (oracle/restate.py) on the same
+seeded inputs.  Bars (BASELINE.json north_star): bit-exact for index construction and for the
+plain segmented sum/mean; 1e-5 relative for fp32 floating point."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_err
+from equihgnn_b200 import ops, synthetic
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _ref_csr(dst, n):
+    order = torch.sort(dst, stable=True).indices
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    return rowptr.int(), order.int()
+
+
+@pytest.mark.parametrize("Z,n,seed", [(0, 5, 0), (1, 1, 1), (1000, 37, 2), (5000, 5000, 3), (4096, 3, 4),
+                                      (20000, 1, 5), (70000, 30000, 6)])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_incidence_build_bit_exact(Z, n, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    dst = torch.randint(0, n, (Z,), generator=g)
+    other = torch.randint(0, 1000, (Z,), generator=g)
+    rowptr, perm, dst32, osort = ops.csr_build(dst.to(dtype).to(DEV), n, other.to(dtype).to(DEV))
+    rp, pm = _ref_csr(dst, n)
+    assert torch.equal(rowptr.cpu(), rp)
+    assert torch.equal(perm.cpu(), pm)                       # stable: ascending incidence id inside a segment
+    assert torch.equal(dst32.cpu(), dst.int())
+    assert torch.equal(osort.cpu(), other[pm.long()].int())
+
+
+@pytest.mark.parametrize("profile,B", [("qm9", 128), ("opv", 16), ("molecule3d", 256)])
+def test_incidence_on_hypergraph_batches(profile, B):
+    b = synthetic.make_batch(profile, B, 3)
+    inc = ops.build_incidence(b.edge_index0.to(DEV), b.edge_index1.to(DEV), b.num_atoms, b.num_hyperedges)
+    rp_e, pm_e = _ref_csr(b.edge_index1, b.num_hyperedges)
+    rp_v, pm_v = _ref_csr(b.edge_index0, b.num_atoms)
+    assert torch.equal(inc.rowptr_e.cpu(), rp_e) and torch.equal(inc.perm_e.cpu(), pm_e)
+    assert torch.equal(inc.rowptr_v.cpu(), rp_v) and torch.equal(inc.perm_v.cpu(), pm_v)
+    assert torch.equal(inc.vtx_by_e.cpu().long(), b.edge_index0[pm_e.long()])
+    assert torch.equal(inc.edge_by_v.cpu().long(), b.edge_index1[pm_v.long()])
+    # auto hyperedge count == index.max()+1 (torch_scatter dim_size=None, conv.py:173)
+    inc2 = ops.build_incidence(b.edge_index0.to(DEV), b.edge_index1.to(DEV), b.num_atoms, None)
+    assert inc2.E == b.num_hyperedges
+
+
+def test_incidence_out_of_range_flag(monkeypatch):
+    monkeypatch.setenv("EQH_CHECK_INDEX", "1")
+    with pytest.raises(RuntimeError):
+        ops.csr_build(torch.tensor([0, 5, 1], device=DEV), 3)
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_segment_reduce_bit_exact_and_grad(C, reduce):
+    g = torch.Generator().manual_seed(C)
+    Z, n = 3000, 700
+    src = torch.randn(Z, C, generator=g)
+    index = torch.randint(0, n - 20, (Z,), generator=g)     # trailing empty segments
+    index[index == 5] = 6                                     # interior empty segment
+    index[:200] = 9                                           # one long segment (> 32 rows)
+    ref_in = src.clone().requires_grad_(True)
+    ref = R.scatter_rows(ref_in, index, n, reduce)
+    w = torch.randn(n, C, generator=g)
+    (ref * w).sum().backward()
+    s = src.to(DEV).requires_grad_(True)
+    out = ops.scatter(s, index.to(DEV), dim=-2, dim_size=n, reduce=reduce)
+    assert torch.equal(out.cpu(), ref.detach())              # same association as sequential scatter_add_
+    (out * w.to(DEV)).sum().backward()
+    assert rel_err(s.grad, ref_in.grad) < 1e-6
+    assert float(out[5].abs().max()) == 0.0 and float(out[-1].abs().max()) == 0.0
+
+
+def test_scatter_against_reference_golden():
+    fx = load_golden("scatter")
+    src, index = fx["src"], fx["index"]
+    # C = 48 is not a multiple of 32: the kernels do not implement it and must say so
+    with pytest.raises(NotImplementedError):
+        ops.scatter(src.to(DEV), index.to(DEV), dim=-2, dim_size=fx["n"], reduce="sum")
+    src64 = F.pad(src, (0, 16))
+    for red in ("sum", "mean"):
+        out = ops.scatter(src64.to(DEV), index.to(DEV), dim=-2, dim_size=fx["n"], reduce=red)
+        assert torch.equal(out.cpu()[:, :48], fx[f"{red}_dimsize"])
+        out = ops.scatter(src64.to(DEV), index.to(DEV), dim=-2, reduce=red)
+        assert torch.equal(out.cpu()[:, :48], fx[f"{red}_auto"])
+    out3 = ops.scatter(F.pad(fx["src3"], (0, 16)).to(DEV), index.to(DEV), dim=-2, dim_size=fx["n"], reduce="mean")
+    assert torch.equal(out3.cpu()[..., :48], fx["mean3"])
+    with pytest.raises(NotImplementedError):
+        ops.scatter(src64.to(DEV), index.to(DEV), dim=-2, reduce="max")
+
+
+def test_empty_inputs():
+    out = ops.scatter(torch.zeros(0, 64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), dim=-2,
+                      dim_size=7, reduce="mean")
+    assert out.shape == (7, 64) and float(out.abs().max()) == 0.0
+    out = ops.scatter(torch.zeros(0, 64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), dim=-2,
+                      reduce="sum")
+    assert out.shape == (0, 64)
+
+
+@pytest.mark.parametrize("C", [32, 64, 256])
+@pytest.mark.parametrize("reduce", ["mean", "sum"])
+def test_v2e_gather_reduce(C, reduce):
+    b = synthetic.make_batch("qm9", 32, 11)
+    inc = ops.build_incidence(b.edge_index0.to(DEV), b.edge_index1.to(DEV), b.num_atoms, b.num_hyperedges)
+    g = torch.Generator().manual_seed(1)
+    Y = torch.randn(b.num_atoms, C, generator=g)
+    w = torch.randn(b.num_hyperedges, C, generator=g)
+    yr = Y.clone().requires_grad_(True)
+    ref = R.scatter_rows(yr[b.edge_index0], b.edge_index1, b.num_hyperedges, reduce)
+    (ref * w).sum().backward()
+    yd = Y.to(DEV).requires_grad_(True)
+    out = ops.v2e_gather_reduce(yd, inc, reduce)
+    assert torch.equal(out.cpu(), ref.detach())
+    (out * w.to(DEV)).sum().backward()
+    assert rel_err(yd.grad, yr.grad) < TOL
+
+
+def _fused_ref(A, B, gamma, beta, vertex, edges, n_out, group, reduce):
+    t = F.relu(A[vertex] + B[edges])
+    if gamma is not None:
+        t = F.layer_norm(t, (t.shape[-1],), gamma, beta, 1e-5)
+    return R.scatter_rows(t, edges if group == "e" else vertex, n_out, reduce)
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256])
+@pytest.mark.parametrize("group", ["v", "e"])
+@pytest.mark.parametrize("reduce,ln", [("mean", True), ("sum", True), ("mean", False), ("sum", False)])
+def test_fused_message_fwd_bwd(C, group, reduce, ln):
+    b = synthetic.make_batch("pcqm4mv2", 24, 5 + C)
+    N, E = b.num_atoms + 3, b.num_hyperedges + 2              # trailing empty vertex / hyperedge segments
+    inc = ops.build_incidence(b.edge_index0.to(DEV), b.edge_index1.to(DEV), N, E)
+    g = torch.Generator().manual_seed(C)
+    A = torch.randn(N, C, generator=g)
+    B = torch.randn(E, C, generator=g)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)) if ln else None
+    beta = 0.3 * torch.randn(C, generator=g) if ln else None
+    n_out = E if group == "e" else N
+    w = torch.randn(n_out, C, generator=g)
+    leaves = [t.clone().double().requires_grad_(True) if t is not None else None for t in (A, B, gamma, beta)]
+    ref = _fused_ref(*leaves, b.edge_index0, b.edge_index1, n_out, group, reduce)     # fp64 reference
+    (ref * w.double()).sum().backward()
+    dl = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (A, B, gamma, beta)]
+    U = ops.fused_message(dl[0], dl[1], dl[2], dl[3], inc, group, reduce)
+    assert rel_err(U, ref) < TOL
+    (U * w.to(DEV)).sum().backward()
+    for got, want, name in zip(dl, leaves, "A B gamma beta".split()):
+        if got is not None:
+            assert rel_err(got.grad, want.grad) < TOL, name
+    # fp32 CPU oracle of the same composition agrees as well
+    ref32 = _fused_ref(A, B, gamma, beta, b.edge_index0, b.edge_index1, n_out, group, reduce)
+    assert rel_err(U, ref32) < TOL
+    # determinism: bit-identical rerun, forward and backward
+    dl2 = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (A, B, gamma, beta)]
+    U2 = ops.fused_message(dl2[0], dl2[1], dl2[2], dl2[3], inc, group, reduce)
+    (U2 * w.to(DEV)).sum().backward()
+    assert torch.equal(U, U2)
+    for a_, b_ in zip(dl, dl2):
+        if a_ is not None:
+            assert torch.equal(a_.grad, b_.grad)
+
+
+@pytest.mark.parametrize("profile,B", [("qm9", 4), ("qm9", 128), ("molecule3d", 700)])
+def test_knn16_bit_exact(profile, B):
+    b = synthetic.make_batch(profile, B, 17)
+    idx, d2 = ops.knn16(b.pos.to(DEV))
+    ridx, rd2 = R.knn(b.pos, 16)
+    assert torch.equal(idx.cpu().long(), ridx)               # integer output: bit-exact
+    assert torch.equal(d2.cpu(), rd2)                        # same fp32 arithmetic as (rel**2).sum(-1)
+    assert torch.equal(idx[:, 0].cpu().long(), torch.arange(b.num_atoms))   # self first (fact 3)
+
+
+def test_knn16_golden_and_errors():
+    fx = load_golden("egnn_c64_eps0.1")
+    idx, d2 = ops.knn16(fx["pos"].to(DEV))
+    assert torch.equal(idx.cpu().long(), fx["nbhd"]) and torch.equal(d2.cpu(), fx["nbhd_d2"])
+    with pytest.raises(RuntimeError):
+        ops.knn16(torch.randn(15, 3, device=DEV))            # reference: topk raises for k > N
+    # cross-molecule neighbours are the rule, not the exception (fact 2)
+    b = synthetic.make_batch("qm9", 64, 3)
+    idx, _ = ops.knn16(b.pos.to(DEV))
+    cross = (b.batch[idx.cpu().long()] != b.batch[:, None]).float().mean()
+    assert float(cross) > 0.5
+
+
+def test_knn16_ties_are_ordered_by_index():
+    pos = torch.zeros(40, 3)
+    pos[20:] = 1.0
+    idx, d2 = ops.knn16(pos.to(DEV))
+    assert torch.equal(idx[0].cpu(), torch.arange(16, dtype=torch.int32))
+    assert torch.equal(idx[25].cpu(), torch.arange(20, 36, dtype=torch.int32))
+    assert float(d2.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C", [32, 64, 256])
+def test_egnn_edge_fwd_bwd(C):
+    b = synthetic.make_batch("qm9", 12, 23)
+    N = b.num_atoms
+    g = torch.Generator().manual_seed(C)
+    H0 = 2 * (2 * C + 1)
+    Hp = (H0 + 63) // 64 * 64
+    P = 0.5 * torch.randn(N, Hp, generator=g)
+    Q = 0.5 * torch.randn(N, Hp, generator=g)
+    wc = 0.3 * torch.randn(Hp, generator=g)
+    W2 = 0.1 * torch.randn(16, Hp, generator=g)
+    P[:, H0:] = 0
+    Q[:, H0:] = 0
+    wc[H0:] = 0
+    W2[:, H0:] = 0
+    b2 = 0.1 * torch.randn(16, generator=g)
+    graph = ops.build_knn_graph(b.pos.to(DEV))
+    idx = graph.idx.cpu().long()
+    wm = torch.randn(N, 16, generator=g)
+    wij = torch.randn(N, 16, 16, generator=g)
+
+    def ref(Pr, Qr, wcr, W2r, b2r, d2r):
+        pre = Pr[:, None, :] + Qr[idx] + d2r[..., None] * wcr
+        s2 = F.silu(pre) @ W2r.t() + b2r
+        mij = F.silu(s2)
+        return mij.sum(1), mij
+
+    lv = [t.clone().double().requires_grad_(True) for t in (P, Q, wc, W2, b2, graph.d2.cpu())]
+    mi_r, mij_r = ref(*lv)
+    ((mi_r * wm.double()).sum() + (mij_r * wij.double()).sum()).backward()
+    dv = [t.to(DEV).requires_grad_(True) for t in (P, Q, wc, W2, b2)]
+    d2d = graph.d2.clone().requires_grad_(True)
+    mi, mij = ops.egnn_edge(*dv, d2d, graph)
+    assert rel_err(mi, mi_r) < TOL and rel_err(mij, mij_r) < TOL
+    ((mi * wm.to(DEV)).sum() + (mij * wij.to(DEV)).sum()).backward()
+    for got, want, name in zip(dv + [d2d], lv, "P Q wc W2 b2 d2".split()):
+        assert rel_err(got.grad, want.grad) < TOL, name
+    # only m_i used (what egnn_equihnns does): dMij is None
+    dv2 = [t.to(DEV).requires_grad_(True) for t in (P, Q, wc, W2, b2)]
+    mi2, _ = ops.egnn_edge(*dv2, graph.d2, graph)
+    (mi2 * wm.to(DEV)).sum().backward()
+    lv2 = [t.clone().double().requires_grad_(True) for t in (P, Q, wc, W2, b2)]
+    mi_r2, _ = ref(*lv2, graph.d2.cpu().double())
+    (mi_r2 * wm.double()).sum().backward()
+    for got, want, name in zip(dv2, lv2, "P Q wc W2 b2".split()):
+        assert rel_err(got.grad, want.grad) < TOL, name
+
+
+def test_adam_step_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(10001, generator=g)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3, weight_decay=0.01)
+    p = p0.to(DEV)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(10001, generator=g)
+        ref_p.grad = grad.clone()
+        opt.step()
+        ops.adam_step_(p, grad.to(DEV), m, v, step, 1e-3, weight_decay=0.01)
+    assert rel_err(p, ref_p) < 1e-6
