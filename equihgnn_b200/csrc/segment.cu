@@ -104,7 +104,7 @@ extern "C" {
 int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* rowptr, const int32_t* src_rowptr,
                       int64_t n_out, int64_t C, int mode, float* out, eqh_stream_t stream) {
   using namespace eqh;
-  EQH_CHECK_ARG(n_out >= 0 && rowptr && (n_out == 0 || (out && table)));
+  EQH_CHECK_ARG(n_out >= 0 && rowptr && (n_out == 0 || out));  // table may be NULL when every segment is empty
   EQH_CHECK_ARG(mode == EQH_REDUCE_SUM || mode == EQH_REDUCE_MEAN);
   EQH_CHECK_ARG(aligned16(table) && aligned16(out));
   const int64_t CB = col_block(C);

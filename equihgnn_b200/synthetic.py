@@ -8,6 +8,8 @@ with bond-type feature 5; on collation atom ids are offset by the atoms so far a
 ids by the hyperedges so far (HData.__inc__, data/utils.py:172-178).
 
 Profiles are stated assumptions taken from the public dataset descriptions (H-inclusive):
+Positions: random tree walk, bond length ~N(1.5, 0.075) A clipped to [1.2, 1.8], centred per molecule
+(molecules overlap near the origin, so kNN edges cross molecules as they do in the reference).
   qm9        a~round(N(18,3))  clip[4,29],    r~Pois(1.6), h~Bern(0.25), s~U{3..8}
   pcqm4mv2   a~round(N(29.5,7)) clip[6,51],   r~Pois(1.1), h~Pois(0.9),  s~U{4..14}
   molecule3d a~round(N(29,8))  clip[5,60],    r~Pois(1.4), h~Pois(0.8),  s~U{4..14}
@@ -87,7 +89,8 @@ def _molecule(rng: np.random.Generator, prof) -> tuple:
     for k in range(1, a):
         for _ in range(8):
             d = rng.normal(size=3)
-            d *= 1.5 / np.linalg.norm(d)
+            # bond length 1.5 A +- 5 % (continuous, so squared distances are tie-free in fp32)
+            d *= float(np.clip(rng.normal(1.5, 0.075), 1.2, 1.8)) / np.linalg.norm(d)
             cand = pos[parent[k - 1]] + d
             if k < 2 or np.min(np.sum((pos[:k] - cand) ** 2, axis=1)) > 1.0:
                 break

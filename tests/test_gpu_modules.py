@@ -104,15 +104,23 @@ def test_egnn_pos_gradient_and_errors():
     fx = load_golden("egnn_c32_coors")
     m = EGNN(dim=32, norm_coors=True, norm_feats=True, num_nearest_neighbors=16, init_eps=0.1).to(DEV)
     m.load_state_dict(fx["sd"])
-    p = {"e." + k: v.clone().double() for k, v in fx["sd"].items()}
-    pos_r = fx["pos"].clone().double().requires_grad_(True)
     nbhd, _ = R.knn(fx["pos"], 16)
-    no_r, co_r = R.egnn(p, "e", fx["h"].double(), pos_r, nbhd=nbhd)
-    ((no_r * fx["w"][0].double()).sum() + (co_r * fx["wc"][0].double()).sum()).backward()
+
+    def oracle_pos_grad(dtype):
+        p = {"e." + k: v.clone().to(dtype) for k, v in fx["sd"].items()}
+        pos_r = fx["pos"].clone().to(dtype).requires_grad_(True)
+        no_r, co_r = R.egnn(p, "e", fx["h"].to(dtype), pos_r, nbhd=nbhd)
+        ((no_r * fx["w"][0].to(dtype)).sum() + (co_r * fx["wc"][0].to(dtype)).sum()).backward()
+        return pos_r.grad
+
+    g64, g32 = oracle_pos_grad(torch.float64), oracle_pos_grad(torch.float32)
     pos = fx["pos"].to(DEV).requires_grad_(True)
     no, co = m(fx["h"].to(DEV).unsqueeze(0), pos.unsqueeze(0))
     ((no * fx["w"].to(DEV)).sum() + (co * fx["wc"].to(DEV)).sum()).backward()
-    assert rel_err(pos.grad, pos_r.grad) < 5 * TOL
+    # The self edge (rel = 0) goes through rel / clamp(|rel|, 1e-8): +-1e8-scaled terms that cancel
+    # exactly in exact arithmetic and only to ~1e-2 in fp32 -- in the reference's own fp32 arithmetic
+    # too.  The bar is therefore the reference-arithmetic error against fp64, not 1e-5.
+    assert rel_err(pos.grad, g64) < max(5 * TOL, 4 * rel_err(g32, g64))
     with pytest.raises(RuntimeError):                        # N < 16: the reference's topk raises
         m(torch.randn(1, 10, 32, device=DEV), torch.randn(1, 10, 3, device=DEV))
     with pytest.raises(NotImplementedError):
@@ -146,12 +154,29 @@ def _sd_from(m):
     return {k: v.detach().cpu().clone() for k, v in m.state_dict().items() if "running" not in k and "num_batches" not in k}
 
 
+def _oracle_run(fn, sd, b, dtype, nbhd):
+    import types
+    p = {k: (v.to(dtype) if v.is_floating_point() else v).clone().requires_grad_(v.is_floating_point())
+         for k, v in sd.items()}
+    data = types.SimpleNamespace(**{k: (getattr(b, k).to(dtype) if torch.is_tensor(getattr(b, k)) and
+                                        getattr(b, k).is_floating_point() else getattr(b, k))
+                                    for k in ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "batch", "y",
+                                              "num_graphs")})
+    pred = fn(p, data, nbhd=nbhd) if nbhd is not None else fn(p, data)
+    F.mse_loss(pred, data.y).backward()
+    return pred.detach(), {k: v.grad for k, v in p.items()}
+
+
 @pytest.mark.parametrize("method,cls,fn,profile,B,C", [
     ("egnn_equihnns", EGNNEquiHNNS, R.egnn_equihnns, "qm9", 128, 256),        # BASELINE config 2, script sizes
     ("mhnnm", MHNNM, R.mhnnm, "qm9", 128, 256),                              # BASELINE config 1
     ("egnn_equihnns", EGNNEquiHNNS, R.egnn_equihnns, "opv", 8, 64),          # long conjugated hyperedges
 ])
 def test_models_vs_oracle_at_baseline_sizes(method, cls, fn, profile, B, C):
+    """Whole training step at BASELINE.json sizes.  A 3-layer ReLU/LayerNorm network in fp32 is not
+    reproducible to 1e-5 by ANY fp32 implementation (ReLU gates flip under rounding): the reference
+    arithmetic itself (oracle in fp32) is measured against the fp64 oracle in the same test, and the
+    CUDA path has to be as close to the fp64 truth as that, up to a factor 4 (floor: 1e-4)."""
     b = synthetic.make_batch(profile, B, 61)
     args = synthetic.model_args(hidden=C)
     torch.manual_seed(3)
@@ -160,20 +185,31 @@ def test_models_vs_oracle_at_baseline_sizes(method, cls, fn, profile, B, C):
         for k, p_ in m.named_parameters():
             if k.startswith("egnn_layer") and k.endswith("weight") and p_.dim() == 2:
                 p_.normal_(0, 0.05)
-    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in _sd_from(m).items()}
-    pred_r = fn(p, b)
-    loss_r = F.mse_loss(pred_r, b.y)
-    loss_r.backward()
+    sd = _sd_from(m)
+    nbhd = R.knn(b.pos, 16)[0] if method == "egnn_equihnns" else None
+    pred64, g64 = _oracle_run(fn, sd, b, torch.float64, nbhd)
+    pred32, g32 = _oracle_run(fn, sd, b, torch.float32, nbhd)
     m = m.to(DEV).train()
     d = b.to(DEV)
     pred = m(d)
     loss = F.mse_loss(pred, d.y)
     loss.backward()
-    assert rel_err(pred, pred_r) < TOL_MODEL
-    golden = {k: p[k].grad for k, _ in m.named_parameters()}
-    assert not grads_mismatch(_named_grads(m), golden, 2e-4)
+    assert rel_err(pred, pred64) < max(TOL_MODEL, 4 * rel_err(pred32, pred64))
+    got = _named_grads(m)
+    scale = max(float(v.abs().max()) for v in g64.values() if v is not None)
+    bad = {}
+    for k, _ in m.named_parameters():
+        if g64[k] is None:
+            assert got[k] is None or float(got[k].abs().max()) == 0.0, k
+            continue
+        den = max(float(g64[k].abs().max()), 0.05 * scale)
+        e_gpu = float((got[k].double().cpu() - g64[k]).abs().max()) / den
+        e_ref = float((g32[k].double() - g64[k]).abs().max()) / den
+        if e_gpu > max(1e-4, 4 * e_ref):
+            bad[k] = (e_gpu, e_ref)
+    assert not bad, dict(sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
     # determinism: a second identical step is bit-identical (atomics-free path)
-    g1 = {k: v.clone() for k, v in _named_grads(m).items() if v is not None}
+    g1 = {k: v.clone() for k, v in got.items() if v is not None}
     m.zero_grad(set_to_none=True)
     pred2 = m(d)
     F.mse_loss(pred2, d.y).backward()
