@@ -1,0 +1,148 @@
+"""CUDA-graph execution of the training step (B200-first replacement for per-op dispatch).
+
+The reference's step is ~700 ATen dispatches over a few MB of data: launch-bound on any modern
+GPU.  Here forward + loss + backward of a whole batch is captured ONCE per shape
+bucket into a CUDA graph and replayed; the host then does three things per step: copy the
+collated batch into the graph's static input buffers, replay, launch the (all-reduce +) Adam.
+
+Variable batch shapes vs static graphs: a batch is padded on the host to its bucket
+(N_pad, E_pad, Z_pad) with an inert *ghost molecule* --
+  * ghost atoms (ids N..N_pad-1) sit in a compact cluster 1000 A away from everything, so no real
+    atom ever has a ghost among its 16 nearest neighbours (real batches have >= 16 atoms), i.e.
+    the batch-wide kNN of the real atoms is bit-identical to the unpadded one;
+  * ghost hyperedges (ids E..E_pad-1) and ghost incidences only connect ghost atoms to ghost
+    hyperedges, following HData's numbering (data/utils.py:172-178), so every real segment of the
+    incidence CSR is unchanged;
+  * the ghost molecule is graph id B and is excluded from the loss, so every gradient that flows
+    through a ghost row is exactly zero.
+Nothing in the kernels knows about padding.  BatchNorm over atom rows (mhnnm) would see the
+ghost rows, so MHNNM is only graphed with exact (unpadded) shapes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .synthetic import HBatch
+from .train import Trainer
+
+GHOST_OFFSET = 1000.0   # Angstrom
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def bucket_of(b: HBatch, gran: Tuple[int, int, int] = (256, 256, 512)) -> Tuple[int, int, int]:
+    """(N_pad, E_pad, Z_pad): always at least one ghost atom and one ghost hyperedge."""
+    return (_round_up(b.num_atoms + 1, gran[0]), _round_up(b.num_hyperedges + 1, gran[1]),
+            _round_up(b.num_incidences, gran[2]))
+
+
+def pad_batch(b: HBatch, bucket: Tuple[int, int, int]) -> HBatch:
+    """Host-side: append the ghost molecule so the batch has exactly the bucket's shape."""
+    N, E, Z, B = b.num_atoms, b.num_hyperedges, b.num_incidences, b.num_graphs
+    Np, Ep, Zp = bucket
+    ga, ge, gz = Np - N, Ep - E, Zp - Z
+    if ga < 1 or ge < 1 or gz < 0:
+        raise ValueError(f"batch (N={N},E={E},Z={Z}) does not fit bucket {bucket}")
+    # ghost atoms: a 3-D lattice with 1.5 A spacing, far away from every real atom
+    side = int(np.ceil(ga ** (1.0 / 3.0)))
+    g = np.arange(ga)
+    gpos = np.stack([g % side, (g // side) % side, g // (side * side)], 1).astype(np.float32) * 1.5
+    gpos += np.float32(GHOST_OFFSET) + np.abs(b.pos.numpy()).max()
+    zi = torch.arange(gz, dtype=torch.int64)
+    return HBatch(
+        x=torch.cat([b.x, torch.zeros(ga, b.x.shape[1], dtype=b.x.dtype)]),
+        pos=torch.cat([b.pos, torch.from_numpy(gpos)]),
+        edge_index0=torch.cat([b.edge_index0, N + zi % ga]),
+        edge_index1=torch.cat([b.edge_index1, E + zi % ge]),
+        edge_attr=torch.cat([b.edge_attr, torch.full((ge, 1), 5, dtype=b.edge_attr.dtype)]),
+        n_e=torch.cat([b.n_e, torch.tensor([ge], dtype=b.n_e.dtype)]),
+        e_order=torch.cat([b.e_order, torch.bincount(zi % ge, minlength=ge).to(b.e_order.dtype)]),
+        batch=torch.cat([b.batch, torch.full((ga,), B, dtype=b.batch.dtype)]),
+        ptr=torch.cat([b.ptr, torch.tensor([Np], dtype=b.ptr.dtype)]),
+        y=torch.cat([b.y, torch.zeros(1, dtype=b.y.dtype)]),
+        num_graphs=B + 1)
+
+
+_ALL = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "n_e", "e_order", "batch", "ptr", "y")
+_FIELDS = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "batch", "y")   # what the model wrappers read
+
+
+def step_input_bytes(b: HBatch) -> int:
+    """Bytes copied into the graph's static inputs per step."""
+    return sum(getattr(b, f).numel() * getattr(b, f).element_size() for f in _FIELDS)
+
+
+class _Bucket:
+    def __init__(self, static: HBatch, graph: torch.cuda.CUDAGraph, loss: torch.Tensor, launches: int):
+        self.static, self.graph, self.loss, self.launches = static, graph, loss, launches
+
+
+class GraphedTrainer(Trainer):
+    """Trainer whose forward+loss+backward is one CUDA-graph replay per step.
+
+    step(padded_device_batch) / step_from_host(padded_pinned_batch, device): the batch must have
+    been padded with `pad_batch(batch, bucket_of(batch))` (host side, part of collation).
+    """
+
+    def __init__(self, model, real_graphs: int, **kw):
+        super().__init__(model, **kw)
+        self.B = real_graphs
+        self.buckets: Dict[Tuple[int, int, int, int], _Bucket] = {}
+        self.replays = 0
+        self.own_launches = 0
+
+    def _fwd_bwd(self, data) -> torch.Tensor:
+        self.fp.zero_grad()
+        pred = self.model(data)
+        loss = F.mse_loss(pred[:self.B], data.y.view(-1)[:self.B])     # the ghost molecule is not in the loss
+        loss.backward()
+        return loss.detach()
+
+    def _capture(self, like: HBatch) -> _Bucket:
+        dev = self.fp.flat.device
+        static = HBatch(**{f: torch.empty_like(getattr(like, f), device=dev) for f in _ALL},
+                        num_graphs=like.num_graphs)
+        for f in _ALL:
+            getattr(static, f).copy_(getattr(like, f))
+        # warm-up on a side stream (cuBLAS workspaces, autograd buffers), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._fwd_bwd(static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        before = ops.STATS["launches"]
+        with torch.cuda.graph(g):        # private pool per bucket: buckets may replay in any order
+            loss = self._fwd_bwd(static)
+        return _Bucket(static, g, loss, ops.STATS["launches"] - before)
+
+    def _bucket(self, data: HBatch) -> _Bucket:
+        key = (data.num_atoms, data.num_hyperedges, data.num_incidences, data.num_graphs)
+        bk = self.buckets.get(key)
+        if bk is None:
+            bk = self.buckets[key] = self._capture(data)
+        return bk
+
+    def forward_backward(self, data: HBatch) -> torch.Tensor:
+        bk = self._bucket(data)
+        for f in _FIELDS:                                   # D2D (resident batch) or H2D (pinned host batch)
+            getattr(bk.static, f).copy_(getattr(data, f), non_blocking=True)
+        bk.graph.replay()
+        self.replays += 1
+        self.own_launches += bk.launches
+        return bk.loss
+
+    def step_from_host(self, host_batch: HBatch, device=None) -> float:
+        loss = self.forward_backward(host_batch)           # H2D straight into the graph's static inputs
+        self.sync_gradients()
+        self.optimizer_step()
+        return float(loss.item())

@@ -35,13 +35,40 @@ def _f32(t: torch.Tensor, what: str) -> torch.Tensor:
         raise RuntimeError(f"{what}: expected a CUDA tensor (equihgnn_b200 has no CPU path)")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:          # the kernels use 128-bit accesses; views into flat buffers may be misaligned
+        t = t.clone()
+    return t
 
 
 def _i32(t: torch.Tensor, what: str) -> torch.Tensor:
     if not t.is_cuda or t.dtype != torch.int32:
         raise RuntimeError(f"{what}: expected a CUDA int32 tensor")
     return t.contiguous()
+
+
+# Launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the live
+# roofline figure): PROFILE maps a C-ABI entry point name to a list of (start, end) event pairs.
+STATS = {"launches": 0}
+PROFILE = None
+
+
+def _call(name: str, n_kernels: int, *args, nbytes: float = 0.0) -> None:
+    """nbytes: algorithmic (compulsory) HBM bytes of this launch -- each distinct input row once, each
+    output row once, each index array once; only used for the roofline report."""
+    fn = getattr(_lib.load(), name)
+    prof = PROFILE
+    if prof is not None and name in prof and not torch.cuda.is_current_stream_capturing():
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        prof[name].append((s, e, nbytes))
+    else:
+        rc = fn(*args)
+    STATS["launches"] += n_kernels
+    _lib.check(rc, name)
 
 
 def partial_rows() -> int:
@@ -74,10 +101,9 @@ def csr_build(dst: torch.Tensor, n_dst: int, other: Optional[torch.Tensor] = Non
     ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
     check_idx = os.environ.get("EQH_CHECK_INDEX", "0") == "1"
     status = torch.zeros(1, dtype=torch.int32, device=dev) if check_idx else None
-    fn = lib.eqh_incidence_build_i64 if dst.dtype == torch.int64 else lib.eqh_incidence_build_i32
-    rc = fn(_p(dst), _p(other), Z, n_dst, _p(rowptr), _p(perm), _p(dst32), _p(osort), _p(status), _p(ws), nbytes,
-            _stream())
-    _lib.check(rc, "eqh_incidence_build")
+    name = "eqh_incidence_build_i64" if dst.dtype == torch.int64 else "eqh_incidence_build_i32"
+    _call(name, 4 if Z > 0 else 1, _p(dst), _p(other), Z, n_dst, _p(rowptr), _p(perm), _p(dst32), _p(osort),
+          _p(status), _p(ws), nbytes, _stream())
     if check_idx and int(status.item()) != 0:
         raise RuntimeError("index out of range in incidence build (EQH_CHECK_INDEX=1)")
     return rowptr, perm, dst32, osort
@@ -150,6 +176,8 @@ class _IncidenceCache:
         self._slot = None
 
     def get(self, vertex, edges, N, E) -> Incidence:
+        if torch.cuda.is_current_stream_capturing():        # a captured graph must contain its own build
+            return build_incidence(vertex, edges, N, E)
         s = self._slot
         if s is not None:
             v_ref, e_ref, v_ver, e_ver, n, e_req, inc = s
@@ -170,24 +198,26 @@ incidence_cache = _IncidenceCache()
 def gather_reduce_raw(table, idx, rowptr, src_rowptr, n_out: int, mode: int) -> torch.Tensor:
     C = table.shape[-1]
     out = torch.empty((n_out, C), dtype=torch.float32, device=table.device)
-    rc = _lib.load().eqh_gather_reduce(_p(table), _p(idx), _p(rowptr), _p(src_rowptr), n_out, C, mode, _p(out),
-                                       _stream())
-    _lib.check(rc, f"eqh_gather_reduce(C={C})")
+    Z = idx.numel() if idx is not None else table.shape[0]
+    nb = 4.0 * C * (min(Z, table.shape[0]) + n_out) + 4.0 * ((Z if idx is not None else 0) + n_out + 1)
+    _call("eqh_gather_reduce", 1 if n_out > 0 else 0, _p(table), _p(idx), _p(rowptr), _p(src_rowptr), n_out, C, mode,
+          _p(out), _stream(), nbytes=nb)
     return out
 
 
 def gather_rows_raw(table, idx, scale_rowptr, n_rows: int) -> torch.Tensor:
     C = table.shape[-1]
     out = torch.empty((n_rows, C), dtype=torch.float32, device=table.device)
-    rc = _lib.load().eqh_gather_rows(_p(table), _p(idx), _p(scale_rowptr), n_rows, C, _p(out), _stream())
-    _lib.check(rc, f"eqh_gather_rows(C={C})")
+    nb = 4.0 * C * (min(n_rows, table.shape[0]) + n_rows) + 4.0 * n_rows
+    _call("eqh_gather_rows", 1 if n_rows > 0 else 0, _p(table), _p(idx), _p(scale_rowptr), n_rows, C, _p(out),
+          _stream(), nbytes=nb)
     return out
 
 
 def colsum_raw(partial: torch.Tensor) -> torch.Tensor:
     rows, cols = partial.shape
     out = torch.empty(cols, dtype=torch.float32, device=partial.device)
-    _lib.check(_lib.load().eqh_colsum(_p(partial), rows, cols, _p(out), _stream()), "eqh_colsum")
+    _call("eqh_colsum", 1, _p(partial), rows, cols, _p(out), _stream())
     return out
 
 
@@ -270,9 +300,9 @@ class _FusedMsg(torch.autograd.Function):
         else:
             n_out, rowptr, ia, ib = inc.E, inc.rowptr_e, inc.vtx_by_e, None
         U = torch.empty((n_out, C), dtype=torch.float32, device=A.device)
-        rc = lib.eqh_fused_msg_fwd(_p(A), _p(B), _p(ia), _p(ib), _p(rowptr), n_out, C, _p(gamma), _p(beta), eps, mode,
-                                   _p(U), _stream())
-        _lib.check(rc, f"eqh_fused_msg_fwd(C={C})")
+        nb = 4.0 * C * (A.shape[0] + B.shape[0] + n_out) + 4.0 * (inc.Z + n_out + 1)      # figure F, exact index reads
+        _call("eqh_fused_msg_fwd", 1 if n_out > 0 else 0, _p(A), _p(B), _p(ia), _p(ib), _p(rowptr), n_out, C, _p(gamma),
+              _p(beta), eps, mode, _p(U), _stream(), nbytes=nb)
         ctx.save_for_backward(A, B, gamma, beta)
         ctx.inc, ctx.group, ctx.mode, ctx.eps = inc, group, mode, eps
         return U
@@ -289,24 +319,26 @@ class _FusedMsg(torch.autograd.Function):
         dB = torch.empty_like(B)
         part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev) if gamma is not None else None
         st = _stream()
+        rowsAB = A.shape[0] + B.shape[0]
+        nb_v = 4.0 * C * (rowsAB + 2 * inc.N) + 4.0 * (inc.Z + inc.N + 1)       # primary over vertices: dU[N] in, dOp[N] out
+        nb_e = 4.0 * C * (rowsAB + dU.shape[0] + inc.E) + 4.0 * (2 * inc.Z + inc.E + 1)
+        nb_e2 = 4.0 * C * (rowsAB + 2 * inc.E) + 4.0 * (inc.Z + inc.E + 1)
+        nb_v2 = 4.0 * C * (rowsAB + dU.shape[0] + inc.N) + 4.0 * (2 * inc.Z + inc.N + 1)
+        nb_part = 4.0 * 2 * C * partial_rows() if gamma is not None else 0.0
         if group == "v":
             u_rp = inc.rowptr_v if mode == MEAN else None
             # primary grouping (vertices): gradient of the segment-constant operand A + LayerNorm affine partials
-            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), inc.N, C, _p(gamma),
-                                       _p(beta), eps, _p(dU), _p(u_rp), _p(dA), _p(part), st)
-            _lib.check(rc, "eqh_fused_msg_bwd[v/primary]")
+            _call("eqh_fused_msg_bwd", 1, _p(A), _p(B), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), inc.N, C,
+                  _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dA), _p(part), st, nbytes=nb_v + nb_part)
             # secondary grouping (hyperedges): gradient of the gathered operand B
-            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), inc.E, C,
-                                       _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dB), None, st)
-            _lib.check(rc, "eqh_fused_msg_bwd[v/secondary]")
+            _call("eqh_fused_msg_bwd", 1, _p(A), _p(B), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), inc.E,
+                  C, _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dB), None, st, nbytes=nb_e)
         else:
             u_rp = inc.rowptr_e if mode == MEAN else None
-            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), _p(inc.vtx_by_e), None, None, _p(inc.rowptr_e), inc.E, C, _p(gamma),
-                                       _p(beta), eps, _p(dU), _p(u_rp), _p(dB), _p(part), st)
-            _lib.check(rc, "eqh_fused_msg_bwd[e/primary]")
-            rc = lib.eqh_fused_msg_bwd(_p(A), _p(B), None, _p(inc.edge_by_v), _p(inc.edge_by_v), _p(inc.rowptr_v), inc.N, C,
-                                       _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dA), None, st)
-            _lib.check(rc, "eqh_fused_msg_bwd[e/secondary]")
+            _call("eqh_fused_msg_bwd", 1, _p(A), _p(B), _p(inc.vtx_by_e), None, None, _p(inc.rowptr_e), inc.E, C,
+                  _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dB), _p(part), st, nbytes=nb_e2 + nb_part)
+            _call("eqh_fused_msg_bwd", 1, _p(A), _p(B), None, _p(inc.edge_by_v), _p(inc.edge_by_v), _p(inc.rowptr_v), inc.N,
+                  C, _p(gamma), _p(beta), eps, _p(dU), _p(u_rp), _p(dA), None, st, nbytes=nb_v2)
         dgamma = dbeta = None
         if gamma is not None:
             gb = colsum_raw(part)
@@ -325,7 +357,7 @@ def knn16(pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         raise RuntimeError(f"selected index k out of range (k={KNN_K} > n={N})")
     idx = torch.empty((N, KNN_K), dtype=torch.int32, device=pos.device)
     d2 = torch.empty((N, KNN_K), dtype=torch.float32, device=pos.device)
-    _lib.check(_lib.load().eqh_knn16(_p(pos), N, _p(idx), _p(d2), _stream()), "eqh_knn16")
+    _call("eqh_knn16", 1, _p(pos), N, _p(idx), _p(d2), _stream())
     return idx, d2
 
 
@@ -360,9 +392,8 @@ class _EgnnEdge(torch.autograd.Function):
         S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mij = torch.empty((N, KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
-        rc = lib.eqh_egnn_edge_fwd(_p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij),
-                                   _p(Mi), _stream())
-        _lib.check(rc, f"eqh_egnn_edge_fwd(H={H})")
+        _call("eqh_egnn_edge_fwd", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij),
+              _p(Mi), _stream())
         ctx.save_for_backward(P, Q, wc, W2, b2, d2, S2)
         ctx.graph = graph
         ctx.set_materialize_grads(False)
@@ -387,9 +418,8 @@ class _EgnnEdge(torch.autograd.Function):
         dPre = torch.empty((N * KNN_K, H), dtype=torch.float32, device=dev)
         dd2 = torch.empty_like(d2) if ctx.needs_input_grad[5] else None
         part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        rc = lib.eqh_egnn_edge_bwd(_p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi), _p(dMij), N, H,
-                                   _p(dP), _p(dPre), _p(dd2), _p(part), _stream())
-        _lib.check(rc, f"eqh_egnn_edge_bwd(H={H})")
+        _call("eqh_egnn_edge_bwd", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi), _p(dMij), N,
+              H, _p(dP), _p(dPre), _p(dd2), _p(part), _stream())
         red = colsum_raw(part)
         dW2 = red[:M_DIM * H].view(M_DIM, H)
         dwc = red[M_DIM * H:(M_DIM + 1) * H]
@@ -433,6 +463,10 @@ class _IndexCache:
         self._slot = None
 
     def get(self, index: torch.Tensor, n_out: Optional[int]):
+        if torch.cuda.is_current_stream_capturing():
+            if n_out is None:
+                raise RuntimeError("scatter(dim_size=None) needs a host sync and cannot be captured in a CUDA graph")
+            return (n_out,) + csr_build(index, n_out, None)[:3]
         s = self._slot
         if s is not None:
             ref, ver, n_req, val = s
@@ -476,6 +510,10 @@ class _PoolCache:
         self._slot = None
 
     def get(self, batch: torch.Tensor, size: Optional[int]):
+        if torch.cuda.is_current_stream_capturing():
+            if size is None:
+                raise RuntimeError("global_add_pool(size=None) needs a host sync and cannot be captured in a CUDA graph")
+            return (size,) + csr_build(batch, size, None)[:3]
         s = self._slot
         if s is not None:
             ref, ver, n_req, val = s
@@ -505,6 +543,5 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.
     for t in (param, grad, exp_avg, exp_avg_sq):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise RuntimeError("adam_step_: flat contiguous CUDA float32 buffers required")
-    rc = _lib.load().eqh_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, betas[0], betas[1],
-                                   eps, weight_decay, step, grad_scale, _stream())
-    _lib.check(rc, "eqh_adam_step")
+    _call("eqh_adam_step", 1, _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, betas[0], betas[1], eps,
+          weight_decay, step, grad_scale, _stream())
