@@ -101,7 +101,11 @@ class EGNN(nn.Module):
         if type(module) in {nn.Linear}:
             nn.init.normal_(module.weight, std=self.init_eps)
 
-    def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, knn_graph: "ops.KnnGraph | None" = None):
+    def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, knn_graph: "ops.KnnGraph | None" = None,
+                need_coors: bool = True):
+        """Reference signature plus two optional keywords: `knn_graph` (reuse a prebuilt neighbour graph) and
+        `need_coors=False` (callers that discard coors_out -- every wrapper of the reference does,
+        equihnn_egnn.py:77,158,242 -- skip phi_x and get the input coordinates back)."""
         if edges is not None or mask is not None or adj_mat is not None:
             raise NotImplementedError("equihgnn_b200.EGNN: edges / mask / adj_mat are not implemented "
                                       "(egnn_equihnns passes none of them)")
@@ -134,7 +138,7 @@ class EGNN(nn.Module):
         m_i, m_ij = ops.egnn_edge(P, Q, wc, W2, lin3.bias, d2, graph)
 
         # --- coordinate branch phi_x (egnn_layer.py:325-340); callers of egnn_equihnns discard it
-        if self.coors_mlp is not None:
+        if self.coors_mlp is not None and need_coors:
             cw = self.coors_mlp(m_ij).squeeze(-1)                                  # [N,16]
             if idx_long is None:
                 idx_long = graph.idx.long()

@@ -32,7 +32,9 @@ class AtomEncoder(nn.Module):
             self.atom_embedding_list.append(emb)
 
     def forward(self, x):
-        out = self.atom_embedding_list[0](x[:, 0])
+        if x.is_cuda:
+            return ops.atom_encode(x, [emb.weight for emb in self.atom_embedding_list[:x.shape[1]]])
+        out = self.atom_embedding_list[0](x[:, 0])          # host-side construction / inspection only
         for f in range(1, x.shape[1]):
             out = out + self.atom_embedding_list[f](x[:, f])
         return out
@@ -84,7 +86,7 @@ class EGNNEquiHNNS(nn.Module):
         N = data.x.shape[0]
         inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
         x = self.atom_encoder(data.x)
-        x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0))
+        x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)   # coors_out is discarded (:158)
         x = x.squeeze(0)
         x0 = x
         for _ in range(self.nlayer):

@@ -346,6 +346,53 @@ class _FusedMsg(torch.autograd.Function):
         return dA, dB, dgamma, dbeta, None, None, None, None
 
 
+class _AtomEncode(torch.autograd.Function):
+    """h[n] = sum_f tables[f][x[n,f]]  (ogb AtomEncoder) -- one kernel forward, one + colsum backward."""
+
+    @staticmethod
+    def forward(ctx, x, *tables):
+        import ctypes
+        if not x.is_cuda or x.dtype != torch.int64:
+            raise RuntimeError("atom_encode: expected CUDA int64 categorical features [N,F]")
+        x = x.contiguous()
+        tables = [_f32(t, "atom_encode table") for t in tables]
+        N, F = x.shape
+        C = tables[0].shape[1]
+        ptrs = (ctypes.c_void_p * F)(*[t.data_ptr() for t in tables])
+        rows = (ctypes.c_int32 * F)(*[t.shape[0] for t in tables])
+        out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        _call("eqh_atom_encoder_fwd", 1 if N > 0 else 0, x.data_ptr(), ctypes.cast(ptrs, ctypes.c_void_p),
+              ctypes.cast(rows, ctypes.c_void_p), F, N, C, _p(out), None, _stream(), nbytes=4.0 * C * N * (F + 1))
+        ctx.save_for_backward(x)
+        ctx.rows = [t.shape[0] for t in tables]
+        ctx.C = C
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        (x,) = ctx.saved_tensors
+        g = _f32(g, "atom_encode grad")
+        N, F = x.shape
+        C, rows = ctx.C, ctx.rows
+        R = sum(rows)
+        S = _lib.load().eqh_atom_encoder_slices(N)
+        part = torch.empty((S, R * C), dtype=torch.float32, device=g.device)
+        rows_c = (ctypes.c_int32 * F)(*rows)
+        _call("eqh_atom_encoder_bwd", 1, x.data_ptr(), _p(g), ctypes.cast(rows_c, ctypes.c_void_p), F, N, C, _p(part),
+              _stream(), nbytes=4.0 * C * (N * F + S * R))
+        full = colsum_raw(part).view(R, C)
+        grads, off = [], 0
+        for r in rows:
+            grads.append(full[off:off + r])
+            off += r
+        return (None, *grads)
+
+
+def atom_encode(x: torch.Tensor, tables) -> torch.Tensor:
+    return _AtomEncode.apply(x, *tables)
+
+
 def knn16(pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """pos [N,3] float32 -> (idx [N,16] int32, d2 [N,16] float32), ascending, self first.
     Raises RuntimeError when N < 16, as the reference's topk does (egnn_layer.py:281-283)."""

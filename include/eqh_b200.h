@@ -155,6 +155,21 @@ EQH_API int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, c
                       int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * AtomEncoder (third-party ogb==1.3.6; call sites mhnn.py:201, equihnn_egnn.py:157):
+ *     out[n,:] = sum_f tables[f][x[n,f], :]            x [N,F] int64, tables[f] [rows_per_table[f], C]
+ * (tables / rows_per_table are HOST arrays of F device pointers / row counts, F <= 16).
+ * Backward: per-slice partial table gradients, partial [eqh_atom_encoder_slices(N), sum(rows), C],
+ * to be finished with eqh_colsum(partial, slices, sum(rows)*C); table f's gradient is rows
+ * [off_f, off_f + rows_f) of the result.  Deterministic (ascending atom order, no atomics).
+ * status (optional): set to 1 if a feature value is outside its table.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_atom_encoder_slices(int64_t N);
+EQH_API int eqh_atom_encoder_fwd(const int64_t* x, const float* const* tables, const int32_t* rows_per_table, int F, int64_t N,
+                         int64_t C, float* out, int32_t* status, eqh_stream_t stream);
+EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_t* rows_per_table, int F, int64_t N, int64_t C,
+                         float* partial, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Flat fused Adam step over one contiguous fp32 parameter buffer (main.py:137-140:
  * torch.optim.Adam(lr, weight_decay)); grad is multiplied by grad_scale first (1/world after the
  * summed all-reduce).  L2 weight decay as torch.optim.Adam (not AdamW).

@@ -275,3 +275,27 @@ def test_adam_step_matches_torch():
         opt.step()
         ops.adam_step_(p, grad.to(DEV), m, v, step, 1e-3, weight_decay=0.01)
     assert rel_err(p, ref_p) < 1e-6
+
+
+@pytest.mark.parametrize("C,N", [(64, 300), (256, 5000)])
+def test_atom_encoder_fwd_bwd(C, N):
+    from equihgnn_b200.models import AtomEncoder
+    torch.manual_seed(C)
+    enc = AtomEncoder(C)
+    g = torch.Generator().manual_seed(N)
+    x = torch.stack([torch.randint(0, d, (N,), generator=g) for d in synthetic.ATOM_FEATURE_DIMS], 1)
+    w = torch.randn(N, C, generator=g)
+    ref = enc(x)                                             # CPU: nine nn.Embedding lookups summed in order
+    (ref * w).sum().backward()
+    ref_grads = [e.weight.grad.clone() for e in enc.atom_embedding_list]
+    enc.zero_grad(set_to_none=True)
+    enc = enc.to(DEV)
+    out = enc(x.to(DEV))
+    assert torch.equal(out.cpu(), ref.detach())              # same summation order: bit-exact
+    (out * w.to(DEV)).sum().backward()
+    for e, rg in zip(enc.atom_embedding_list, ref_grads):
+        assert rel_err(e.weight.grad, rg) < TOL
+    g1 = [e.weight.grad.clone() for e in enc.atom_embedding_list]
+    enc.zero_grad(set_to_none=True)
+    (enc(x.to(DEV)) * w.to(DEV)).sum().backward()
+    assert all(torch.equal(a, e.weight.grad) for a, e in zip(g1, enc.atom_embedding_list))   # deterministic
