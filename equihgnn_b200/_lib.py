@@ -37,6 +37,9 @@ _SIGNATURES = {
     "eqh_atom_encoder_slices": (c_int, [c_int64]),
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),
+    "eqh_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "eqh_gemm_tf32x3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P,
+                                c_int, _P, _P]),
     "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                               c_float, _P]),
 }

@@ -1,0 +1,420 @@
+// Row GEMMs of the dense layers next to the hot path on the 5th-generation tensor cores:
+//     D[M,N] = act( A[M,K] . B[N,K]^T + bias[N] ) (+ residual[M,N])
+// fp32 in, fp32 out, fp32-faithful: every operand is split a = a_hi + a_lo (a_hi = a with the low
+// 13 mantissa bits cleared, a_lo = a - a_hi, exact) and the product is evaluated as
+//     a_lo.b_hi + a_hi.b_lo + a_hi.b_hi          ("3xTF32", error ~2^-21 relative)
+// with tcgen05.mma.kind::tf32 accumulating in TMEM.  The reference's tolerance for these layers is
+// 1e-5 relative (BASELINE.json), which rules plain TF32 (2^-11) out; cuBLAS SIMT fp32 is what this
+// kernel replaces (35 % of the step in profiles/r01_launches_eager_qm9b128.md).
+//
+// One CTA computes one 128 x BN output tile for one K-split:
+//   warp 0 (1 thread)  TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a 3-stage ring
+//   warps 4-7          split the landed fp32 tiles into hi (in place) / lo (second buffer) in shared
+//                      memory, fence.proxy.async, signal the MMA warp; afterwards they are the epilogue
+//   warp 1 (1 thread)  issues 4 k-steps x 3 tcgen05.mma per 32-wide K block, commits to the ring
+//   epilogue           tcgen05.ld 32x32b -> bias / activation / residual -> padded smem -> coalesced
+//                      128-bit global stores (bounds-checked; TMA zero-fills ragged M/N/K edges)
+// Operands may be K-major (row-major [rows, K]) or MN-major ([K, rows], the natural layout of the
+// backward GEMMs dX = dY.W and dW = dY^T.X), selected by the UMMA descriptor major bits, so no
+// transposed copies are ever made.  Split-K (weight gradients: K = number of rows, tiny M x N) writes
+// per-split partials that eqh_colsum finishes in a fixed order (deterministic).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace eqh {
+namespace gemm {
+
+constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int kThreads = 256;
+constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle, sm_100 (version bit 46).
+//   K-major : rows of 128 B (32 fp32 along K), 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major: K-rows of 128 B (32 fp32 along MN), 4-row swizzle atoms SBO = 512 B apart, 32-element MN atoms
+//             LBO apart (one TMA box of 32 K-rows each).
+//   layout type (bits 61-63): 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks) --
+//   the only layout the tensor core accepts for MN-major tf32 operands (4 K-rows per swizzle atom).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+struct Params {
+  float* D;
+  const float* bias;
+  const float* residual;
+  float* ws;          // split-K partials [splits, M, N] (ldd == N) or nullptr
+  int64_t ldd;
+  int M, N, K;
+  int act;            // 0 none, 1 relu, 2 silu
+  int kb_per_split;   // K blocks of 32 per split
+};
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB, const Params p) {
+  constexpr uint32_t kABytes = kTileBytes;            // 128 x 32
+  constexpr uint32_t kBBytes = BN * BK * 4;
+  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A raw/hi, A lo, B raw/hi, B lo
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_raw[STAGES], full_split[STAGES], empty[STAGES], tmem_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int nkb = max(kb_end - kb_begin, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_raw[s], 1);
+      mbar_init(&full_split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Three fp32 accumulators of BN columns each.  The tensor core adds into its accumulator with
+  // truncation, so the error grows with the number of accumulations: the large hi.hi terms alternate
+  // between two accumulators and the 2^-11-scaled lo terms get their own (summed in the epilogue).
+  constexpr uint32_t kTmemCols = BN * 4;       // power of two >= 3*BN
+  if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  auto stageA = [&](int s) { return smem + (size_t)s * kStageBytes; };
+  auto stageAlo = [&](int s) { return smem + (size_t)s * kStageBytes + kABytes; };
+  auto stageB = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kABytes; };
+  auto stageBlo = [&](int s) { return smem + (size_t)s * kStageBytes + 2 * kABytes + kBBytes; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full_raw[s], kABytes + kBBytes);
+        const int k0 = (kb_begin + i) * BK;
+        if constexpr (A_KMAJOR) {
+          tma_load_2d(stageA(s), &tmA, &full_raw[s], k0, m0);                 // box {32 K, 128 M}
+        } else {
+#pragma unroll
+          for (int a = 0; a < BM / 32; ++a)                                   // 4 boxes {32 M, 32 K}
+            tma_load_2d(stageA(s) + a * (BK * 128), &tmA, &full_raw[s], m0 + a * 32, k0);
+        }
+        if constexpr (B_KMAJOR) {
+          tma_load_2d(stageB(s), &tmB, &full_raw[s], k0, n0);                 // box {32 K, BN}
+        } else {
+#pragma unroll
+          for (int a = 0; a < BN / 32; ++a)
+            tma_load_2d(stageB(s) + a * (BK * 128), &tmB, &full_raw[s], n0 + a * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
+                                 ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t lboA = A_KMAJOR ? 0u : BK * 128u, lboB = B_KMAJOR ? 0u : BK * 128u;
+      constexpr uint32_t kstepA = A_KMAJOR ? 32u : 1024u, kstepB = B_KMAJOR ? 32u : 1024u;  // bytes per UMMA_K = 8
+      constexpr uint32_t sboA = A_KMAJOR ? 1024u : 512u, sboB = B_KMAJOR ? 1024u : 512u;
+      constexpr uint32_t ltA = A_KMAJOR ? 2u : 1u, ltB = B_KMAJOR ? 2u : 1u;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_split[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t aH = smem_u32(stageA(s)), aL = smem_u32(stageAlo(s));
+        const uint32_t bH = smem_u32(stageB(s)), bL = smem_u32(stageBlo(s));
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint64_t dAh = make_desc(aH + ks * kstepA, lboA, sboA, ltA), dAl = make_desc(aL + ks * kstepA, lboA, sboA, ltA);
+          const uint64_t dBh = make_desc(bH + ks * kstepB, lboB, sboB, ltB), dBl = make_desc(bL + ks * kstepB, lboB, sboB, ltB);
+          const uint32_t step = (uint32_t)(i * (BK / 8) + ks);
+          umma_tf32(tmem_base + 2 * BN, dAl, dBh, idesc, step != 0);
+          umma_tf32(tmem_base + 2 * BN, dAh, dBl, idesc, 1);
+          umma_tf32(tmem_base + (step & 1) * BN, dAh, dBh, idesc, step >= 2);
+        }
+        umma_commit(&empty[s]);   // frees the stage when these MMAs have read it
+      }
+      umma_commit(&tmem_full);
+    }
+  } else if (warp >= 4) {
+    // ===================== operand split (hi / lo), then epilogue =====================
+    const int t = threadIdx.x - 128;   // 0..127
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_raw[s], ph);
+      float4* ah = reinterpret_cast<float4*>(stageA(s));
+      float4* al = reinterpret_cast<float4*>(stageAlo(s));
+#pragma unroll
+      for (int j = 0; j < (int)(kABytes / 16 / 128); ++j) {
+        float4 v = ah[j * 128 + t], h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        ah[j * 128 + t] = h;
+        al[j * 128 + t] = l;
+      }
+      float4* bh = reinterpret_cast<float4*>(stageB(s));
+      float4* bl = reinterpret_cast<float4*>(stageBlo(s));
+#pragma unroll
+      for (int j = 0; j < (int)(kBBytes / 16 / 128); ++j) {
+        float4 v = bh[j * 128 + t], h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        bh[j * 128 + t] = h;
+        bl[j * 128 + t] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(&full_split[s]);
+    }
+    // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
+    constexpr int PITCH = BN + 4;
+    float* stage_out = reinterpret_cast<float*>(smem);   // the operand ring is idle once tmem_full fires
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(&tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const bool final_out = (p.ws == nullptr);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (nkb > 0) {
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        float w[32];
+        tmem_ld32(ta + 2 * BN, v);                           // small terms
+        if (nkb * (BK / 8) >= 2) {                           // the odd accumulator exists from the second k-step on
+          tmem_ld32(ta + BN, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+        tmem_ld32(ta, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (final_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          float x = v[j];
+          if (p.bias && n < p.N) x += __ldg(p.bias + n);
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          else if (p.act == 2) x = silu_f(x);
+          v[j] = x;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+    float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
+    const int64_t ld = final_out ? p.ldd : p.N;
+    const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int r = q; r < BM; r += 4) {                    // one warp per row: 32 lanes x float4 = 128 columns
+      const int m = m0 + r;
+      if (m >= p.M) break;
+      for (int c = lane * 4; c < BN; c += 128) {
+        const int n = n0 + c;
+        if (n >= p.N) continue;
+        float4 x = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
+        float* dst = out + (int64_t)m * ld + n;
+        if (final_out && p.residual) {
+          const float* rs = p.residual + (int64_t)m * ld + n;
+          x.x += __ldg(rs);
+          if (n + 1 < p.N) x.y += __ldg(rs + 1);
+          if (n + 2 < p.N) x.z += __ldg(rs + 2);
+          if (n + 3 < p.N) x.w += __ldg(rs + 3);
+        }
+        if (vec_ok && n + 3 < p.N) {
+          *reinterpret_cast<float4*>(dst) = x;
+        } else {
+          dst[0] = x.x;
+          if (n + 1 < p.N) dst[1] = x.y;
+          if (n + 2 < p.N) dst[2] = x.z;
+          if (n + 3 < p.N) dst[3] = x.w;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = []() -> EncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows, cols] matrix with row stride ld (floats); box = {box_cols, box_rows}
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols,
+                    uint32_t box_rows, CUtensorMapSwizzle swz) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return EQH_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EQH_OK : EQH_ERR_ARG;
+}
+
+template <int BN, bool AK, bool BK_>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) + 1024;
+  static_assert(smem >= (size_t)BM * (BN + 4) * 4 + 1024, "epilogue staging must fit in the operand ring");
+  cudaError_t e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_gemm<BN, AK, BK_><<<grid, kThreads, smem, st>>>(a, b, p);
+  EQH_LAUNCH_RC();
+}
+
+}  // namespace gemm
+}  // namespace eqh
+
+extern "C" {
+
+size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
+  return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)M * (size_t)N : 0;
+}
+
+int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* residual,
+                    int splits, float* ws, eqh_stream_t stream) {
+  using namespace eqh;
+  using namespace eqh::gemm;
+  EQH_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0 && splits >= 1 && act >= 0 && act <= 2);
+  EQH_CHECK_ARG(M < (1 << 30) && N < (1 << 30) && K < (1 << 30));
+  EQH_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0);   // TMA: 16-byte rows
+  EQH_CHECK_ARG(splits == 1 || (ws && !bias && act == 0 && !residual));
+  const int BN = N <= 64 ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // A: logical [M,K].  K-major: stored [M, lda] -> box {32 K, 128 M}.  MN-major: stored [K, lda] -> box {32 M, 32 K}.
+  // MN-major tf32 operands must use the 128B swizzle with 32-byte atoms (UMMA layout SWIZZLE_128B_BASE32B).
+  rc = a_kmajor ? make_map(&tmA, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map(&tmA, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = b_kmajor ? make_map(&tmB, B, N, K, ldb, BK, (uint32_t)BN, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map(&tmB, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  Params p;
+  p.D = D; p.bias = bias; p.residual = residual; p.ws = splits > 1 ? ws : nullptr; p.ldd = ldd;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.act = act;
+  const int kb_total = (int)((K + BK - 1) / BK);
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define EQH_GEMM_CASE(BNV)                                                        \
+  if (a_kmajor && b_kmajor) return launch<BNV, true, true>(tmA, tmB, p, grid, st); \
+  if (a_kmajor && !b_kmajor) return launch<BNV, true, false>(tmA, tmB, p, grid, st); \
+  if (!a_kmajor && !b_kmajor) return launch<BNV, false, false>(tmA, tmB, p, grid, st); \
+  return launch<BNV, false, true>(tmA, tmB, p, grid, st);
+  if (BN == 64) { EQH_GEMM_CASE(64) }
+  EQH_GEMM_CASE(128)
+#undef EQH_GEMM_CASE
+}
+
+}  // extern "C"

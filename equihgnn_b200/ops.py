@@ -346,6 +346,108 @@ class _FusedMsg(torch.autograd.Function):
         return dA, dB, dgamma, dbeta, None, None, None, None
 
 
+# ----------------------------------------------------------------------------------------------
+# dense row GEMMs on tcgen05 (3xTF32, fp32-faithful)
+# ----------------------------------------------------------------------------------------------
+_ACT = {None: 0, "none": 0, "relu": 1, "silu": 2}
+SM_COUNT = 148
+
+
+def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
+             splits: int = 1) -> torch.Tensor:
+    """D[M,N] = act(A.B^T + bias) + residual with A logical [M,K], B logical [N,K]; an operand flagged
+    k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3)."""
+    dev = A.device
+    D = torch.empty((M, N), dtype=torch.float32, device=dev)
+    ws = None
+    if splits > 1:
+        ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
+    flops = 2.0 * M * N * K
+    _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0), _p(D), N, M, N, K,
+          _p(bias), _ACT[act], _p(residual), splits, _p(ws), _stream(), nbytes=flops)
+    if splits > 1:
+        _call("eqh_colsum", 1, _p(ws), splits, M * N, _p(D), _stream())
+    return D
+
+
+def _gemm_ok(t: torch.Tensor) -> bool:
+    return (t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+def _as_gemm_operand(t: torch.Tensor) -> torch.Tensor:
+    return t if _gemm_ok(t) else _f32(t if t.stride(-1) == 1 and t.stride(0) % 4 == 0 else t.contiguous(), "gemm operand")
+
+
+def _wgrad_splits(out_rows: int, out_cols: int, red: int) -> int:
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
+    kb = (red + 31) // 32
+    return max(1, min(SM_COUNT // max(tiles, 1), kb // 2, 64))
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b) (+ residual) on the tcgen05 GEMM; act in {None, 'relu'} (ReLU's mask is recovered
+    from the output, so nothing but x, W and y is kept for the backward)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual):
+        x = _as_gemm_operand(x)
+        w = _as_gemm_operand(w)
+        M, K = x.shape
+        N = w.shape[0]
+        if b is not None:
+            b = _f32(b, "linear bias")
+        if residual is not None:
+            residual = _f32(residual, "linear residual")
+        y = gemm_raw(x, True, w, True, M, N, K, bias=b, act=act, residual=residual)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, w, y if act == "relu" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _f32(dy, "linear grad")
+        dres = dy if ctx.has_res else None
+        if ctx.act == "relu":
+            dy = dy * (y > 0)
+        M, K = x.shape
+        N = w.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_raw(dy, True, w, False, M, K, N)                      # dX = dY . W        (W is [N,K]: MN-major B)
+        if ctx.needs_input_grad[1]:
+            dw = gemm_raw(dy, False, x, False, N, K, M, splits=_wgrad_splits(N, K, M))   # dW = dY^T . X
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db, None, dres
+
+
+LINEAR_MIN_ROWS = 64
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, act: Optional[str] = None,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Linear (+ optional fused ReLU / residual) for 2-D fp32 CUDA rows.  Shapes the tensor-core kernel does
+    not take (tiny row counts, K or N not a multiple of 4) go to the library GEMM."""
+    K, N = x.shape[-1], w.shape[0]
+    if x.dim() != 2 or x.shape[0] < LINEAR_MIN_ROWS or K % 4 or N % 4 or not x.is_cuda or x.dtype != torch.float32:
+        y = torch.nn.functional.linear(x, w, b)
+        if act == "relu":
+            y = torch.relu(y)
+        elif act == "silu":
+            y = torch.nn.functional.silu(y)
+        return y if residual is None else y + residual
+    if act == "silu":      # SiLU's derivative needs the pre-activation: keep it as a separate (autograd) op
+        return torch.nn.functional.silu(_Linear.apply(x, w, b, None, None)) if residual is None else \
+            torch.nn.functional.silu(_Linear.apply(x, w, b, None, None)) + residual
+    if act == "relu" and residual is not None:   # the ReLU mask is recovered from the output: keep the residual outside
+        return _Linear.apply(x, w, b, act, None) + residual
+    return _Linear.apply(x, w, b, act, residual)
+
+
 class _AtomEncode(torch.autograd.Function):
     """h[n] = sum_f tables[f][x[n,f]]  (ogb AtomEncoder) -- one kernel forward, one + colsum backward."""
 

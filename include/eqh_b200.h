@@ -170,6 +170,24 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
                          float* partial, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-faithful row GEMM on the tcgen05 tensor cores (3xTF32 operand splitting, fp32 accumulate):
+ *     D[M,N] = act( A . B^T + bias ) + residual          A logical [M,K], B logical [N,K]
+ * Replaces the cuBLAS SIMT sgemm calls behind nn.Linear in mlp.py:91-99, egnn_layer.py:180-208 and
+ * the P/Q GEMMs of the phi_e split, forward (A, B K-major), dX = dY.W (B MN-major) and
+ * dW = dY^T.X (both MN-major; split-K over the rows, finished by eqh_colsum).
+ *   a_kmajor / b_kmajor: 1 = stored row-major [rows, K] (K contiguous), 0 = stored [K, rows].
+ *   lda / ldb: row stride of the STORED matrix in floats (multiple of 4, base 16-byte aligned).
+ *   D row-major [M, ldd]; bias [N] / residual [M, ldd] optional; act: 0 none, 1 ReLU, 2 SiLU.
+ *   splits > 1: partials go to ws [splits, M, N] (eqh_gemm_workspace_bytes), D is not written,
+ *   bias/act/residual must be null/0; finish with eqh_colsum(ws, splits, M*N, D).
+ * Ragged M / N / K are handled (TMA zero fill, bounds-checked stores).
+ * ---------------------------------------------------------------------------------------- */
+EQH_API size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits);
+EQH_API int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* residual,
+                    int splits, float* ws, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Flat fused Adam step over one contiguous fp32 parameter buffer (main.py:137-140:
  * torch.optim.Adam(lr, weight_decay)); grad is multiplied by grad_scale first (1/world after the
  * summed all-reduce).  L2 weight decay as torch.optim.Adam (not AdamW).

@@ -1,0 +1,77 @@
+"""GPU: the tcgen05 3xTF32 row GEMM (eqh_gemm_tf32x3) against fp64 matmul.  fp32-faithful: the bar is
+the same as for cuBLAS SIMT sgemm (1e-6 of max|D|), three orders below plain TF32."""
+import pytest
+import torch
+
+from conftest import rel_err
+from equihgnn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mk(shape, g, scale=1.0):
+    return (scale * torch.randn(*shape, generator=g)).to(DEV)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (2560, 256, 256), (2341, 1088, 256),
+                                   (300, 64, 272), (1000, 512, 272), (129, 256, 512), (2560, 256, 20)])
+def test_gemm_kmajor_fwd(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, bias = _mk((M, K), g), _mk((N, K), g), _mk((N,), g)
+    ref = A.double() @ B.double().t()
+    D = ops.gemm_raw(A, True, B, True, M, N, K)
+    assert rel_err(D, ref) < 2e-6
+    D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu")
+    assert rel_err(D, torch.relu(ref + bias.double())) < 2e-6
+    res = _mk((M, N), g)
+    D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, residual=res)
+    assert rel_err(D, ref + bias.double() + res.double()) < 2e-6
+    # plain TF32 would be ~1e-3 here: make sure the split really happens
+    assert rel_err(D, ref + bias.double() + res.double()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(2560, 256, 256), (2341, 256, 1088), (300, 272, 512), (130, 128, 64)])
+def test_gemm_dgrad_layout(M, N, K):
+    """dX[M,N] = dY[M,K] . W[K,N]: B is stored [K(reduction), N(out)] = MN-major."""
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    dY, W = _mk((M, K), g), _mk((K, N), g)
+    ref = dY.double() @ W.double()
+    D = ops.gemm_raw(dY, True, W, False, M, N, K)
+    assert rel_err(D, ref) < 2e-6
+
+
+@pytest.mark.parametrize("R,N,K,splits", [(2560, 256, 256, 1), (2560, 256, 256, 20), (2341, 1088, 256, 4),
+                                          (5000, 512, 272, 9), (100, 64, 128, 2), (2560, 256, 256, 64)])
+def test_gemm_wgrad_layout_and_splitk(R, N, K, splits):
+    """dW[N,K] = dY[R,N]^T . X[R,K]: both operands stored [reduction, out] = MN-major; split-K over R."""
+    g = torch.Generator().manual_seed(R + N + K + splits)
+    dY, X = _mk((R, N), g), _mk((R, K), g)
+    ref = dY.double().t() @ X.double()
+    D = ops.gemm_raw(dY, False, X, False, N, K, R, splits=splits)
+    # the tensor core truncates when it adds into its fp32 accumulator, so the error grows with the number of
+    # accumulations per split (R/8/2 here); 5e-6 for an unsplit R=2560 is on par with a sequential fp32 sum
+    assert rel_err(D, ref) < 5e-6
+    D2 = ops.gemm_raw(dY, False, X, False, N, K, R, splits=splits)
+    assert torch.equal(D, D2)                                # deterministic split-K
+
+
+def test_linear_autograd_matches_torch():
+    g = torch.Generator().manual_seed(5)
+    for (M, K, N, act) in [(2341, 256, 256, "relu"), (2341, 272, 512, None), (700, 512, 256, None)]:
+        x = _mk((M, K), g).requires_grad_(True)
+        w = _mk((N, K), g, 0.1).requires_grad_(True)
+        b = _mk((N,), g, 0.1).requires_grad_(True)
+        res = _mk((M, N), g).requires_grad_(True)
+        wgt = _mk((M, N), g)
+        y = ops.linear(x, w, b, act=act, residual=res)
+        (y * wgt).sum().backward()
+        xd, wd, bd, rd = [t.detach().double().requires_grad_(True) for t in (x, w, b, res)]
+        yr = torch.nn.functional.linear(xd, wd, bd)
+        if act == "relu":
+            yr = torch.relu(yr)
+        yr = yr + rd
+        (yr * wgt.double()).sum().backward()
+        assert rel_err(y, yr) < 2e-6
+        for got, want in ((x, xd), (w, wd), (b, bd), (res, rd)):
+            assert rel_err(got.grad, want.grad) < 5e-6
