@@ -26,7 +26,8 @@ namespace eqh {
 namespace gemm {
 
 constexpr int BM = 128, BK = 32, STAGES = 3;
-constexpr int kThreads = 256;
+constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 operand split (warps 4-7 also epilogue)
+constexpr int kSplitThreads = 256;
 constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,16 +121,22 @@ struct Params {
   int kb_per_split;   // K blocks of 32 per split
 };
 
-template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+// kWriteHi: store the masked hi part back (true) or let the tensor core drop the low 13 bits of the raw fp32
+// tile itself (false; valid if the hardware truncates tf32 inputs -- checked by tests/test_gpu_gemm.py).
+template <int BN, bool A_KMAJOR, bool B_KMAJOR, bool kWriteHi>
 __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB, const Params p) {
   constexpr uint32_t kABytes = kTileBytes;            // 128 x 32
   constexpr uint32_t kBBytes = BN * BK * 4;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A raw/hi, A lo, B raw/hi, B lo
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_raw[STAGES], full_split[STAGES], empty[STAGES], tmem_full;
-  __shared__ uint32_t tmem_slot;
+  extern __shared__ __align__(1024) uint8_t smem[];     // operand ring (1024-byte aligned: 128B-swizzle atoms), then barriers
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kStageBytes);
+  uint64_t* full_split = full_raw + STAGES;
+  uint64_t* empty = full_split + STAGES;
+  uint64_t* tmem_full_p = empty + STAGES;
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(tmem_full_p + 1);
+#define tmem_full (*tmem_full_p)
+#define tmem_slot (*tmem_slot_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_raw[s], 1);
-      mbar_init(&full_split[s], 128);
+      mbar_init(&full_split[s], kSplitThreads);
       mbar_init(&empty[s], 1);
     }
     mbar_init(&tmem_full, 1);
@@ -216,50 +223,72 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       }
       umma_commit(&tmem_full);
     }
-  } else if (warp >= 4) {
-    // ===================== operand split (hi / lo), then epilogue =====================
-    const int t = threadIdx.x - 128;   // 0..127
+  } else {
+    // ===================== operand split (hi / lo): warps 2-9 =====================
+    const int t = threadIdx.x - 64;    // 0..255
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(&full_raw[s], ph);
-      float4* ah = reinterpret_cast<float4*>(stageA(s));
-      float4* al = reinterpret_cast<float4*>(stageAlo(s));
+      {
+        float4* ah = reinterpret_cast<float4*>(stageA(s));
+        float4* al = reinterpret_cast<float4*>(stageAlo(s));
+        constexpr int NA = kABytes / 16 / kSplitThreads;   // 4
+        float4 v[NA];
 #pragma unroll
-      for (int j = 0; j < (int)(kABytes / 16 / 128); ++j) {
-        float4 v = ah[j * 128 + t], h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-        ah[j * 128 + t] = h;
-        al[j * 128 + t] = l;
+        for (int j = 0; j < NA; ++j) v[j] = ah[j * kSplitThreads + t];      // all loads first (independent)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u); l.x = v[j].x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u); l.y = v[j].y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u); l.z = v[j].z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u); l.w = v[j].w - h.w;
+          if (kWriteHi) ah[j * kSplitThreads + t] = h;
+          al[j * kSplitThreads + t] = l;
+        }
       }
-      float4* bh = reinterpret_cast<float4*>(stageB(s));
-      float4* bl = reinterpret_cast<float4*>(stageBlo(s));
+      {
+        float4* bh = reinterpret_cast<float4*>(stageB(s));
+        float4* bl = reinterpret_cast<float4*>(stageBlo(s));
+        constexpr int NB = kBBytes / 16 / kSplitThreads;   // 4 (BN=128) or 2 (BN=64)
+        float4 v[NB];
 #pragma unroll
-      for (int j = 0; j < (int)(kBBytes / 16 / 128); ++j) {
-        float4 v = bh[j * 128 + t], h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-        bh[j * 128 + t] = h;
-        bl[j * 128 + t] = l;
+        for (int j = 0; j < NB; ++j) v[j] = bh[j * kSplitThreads + t];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u); l.x = v[j].x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u); l.y = v[j].y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u); l.z = v[j].z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u); l.w = v[j].w - h.w;
+          if (kWriteHi) bh[j * kSplitThreads + t] = h;
+          bl[j * kSplitThreads + t] = l;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&full_split[s]);
     }
+  }
+  if (warp >= 4 && warp < 8) {
     // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
     constexpr int PITCH = BN + 4;
     float* stage_out = reinterpret_cast<float*>(smem);   // the operand ring is idle once tmem_full fires
-    const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may read (warps 4-7 -> 0-3)
     const int row = q * 32 + lane;
     if (nkb > 0) {
       mbar_wait(&tmem_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     const bool final_out = (p.ws == nullptr);
+    // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
+    float* sbias = reinterpret_cast<float*>(smem + (size_t)STAGES * kStageBytes + 128);   // [BN] after the barriers
+    {
+      const int tt = threadIdx.x - 128;
+      if (tt < BN) sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int act = final_out ? p.act : 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
@@ -279,16 +308,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (final_out) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          float x = v[j];
-          if (p.bias && n < p.N) x += __ldg(p.bias + n);
-          if (p.act == 1) x = fmaxf(x, 0.f);
-          else if (p.act == 2) x = silu_f(x);
-          v[j] = x;
-        }
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);   // warp-uniform address: broadcast
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -298,28 +328,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
     float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
     const int64_t ld = final_out ? p.ldd : p.N;
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    for (int r = q; r < BM; r += 4) {                    // one warp per row: 32 lanes x float4 = 128 columns
-      const int m = m0 + r;
-      if (m >= p.M) break;
-      for (int c = lane * 4; c < BN; c += 128) {
-        const int n = n0 + c;
-        if (n >= p.N) continue;
-        float4 x = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
-        float* dst = out + (int64_t)m * ld + n;
-        if (final_out && p.residual) {
-          const float* rs = p.residual + (int64_t)m * ld + n;
-          x.x += __ldg(rs);
-          if (n + 1 < p.N) x.y += __ldg(rs + 1);
-          if (n + 2 < p.N) x.z += __ldg(rs + 2);
-          if (n + 3 < p.N) x.w += __ldg(rs + 3);
+    const bool has_res = final_out && p.residual != nullptr;
+    constexpr int CPL = BN / 32;                         // columns per lane (4 for BN=128: one float4; 2 for BN=64)
+    const int c = lane * CPL;
+    const int n = n0 + c;
+    const bool full_vec = vec_ok && (n + CPL <= p.N) && CPL == 4;
+    const int rows_here = min(BM, p.M - m0);
+    for (int r = q; r < rows_here; r += 4) {             // one warp per row, lanes across the BN columns
+      const float* src = stage_out + r * PITCH + c;
+      float* dst = out + (int64_t)(m0 + r) * ld + n;
+      if (full_vec) {
+        float4 x = *reinterpret_cast<const float4*>(src);
+        if (has_res) {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n));
+          x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
         }
-        if (vec_ok && n + 3 < p.N) {
-          *reinterpret_cast<float4*>(dst) = x;
-        } else {
-          dst[0] = x.x;
-          if (n + 1 < p.N) dst[1] = x.y;
-          if (n + 2 < p.N) dst[2] = x.z;
-          if (n + 3 < p.N) dst[3] = x.w;
+        *reinterpret_cast<float4*>(dst) = x;
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          if (n + j < p.N) {
+            float x = src[j];
+            if (has_res) x += __ldg(p.residual + (int64_t)(m0 + r) * ld + n + j);
+            dst[j] = x;
+          }
         }
       }
     }
@@ -327,6 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+#undef tmem_full
+#undef tmem_slot
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -362,12 +396,20 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 }
 
 template <int BN, bool AK, bool BK_>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) + 1024;
-  static_assert(smem >= (size_t)BM * (BN + 4) * 4 + 1024, "epilogue staging must fit in the operand ring");
-  cudaError_t e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_gemm<BN, AK, BK_><<<grid, kThreads, smem, st>>>(a, b, p);
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, bool write_hi) {
+  constexpr size_t smem = (size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) + 128 + BN * 4;   // ring + barriers + bias tile
+  static_assert((size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) >= (size_t)BM * (BN + 4) * 4,
+                "epilogue staging must fit in the operand ring");
+  cudaError_t e;
+  if (write_hi) {
+    e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_gemm<BN, AK, BK_, true><<<grid, kThreads, smem, st>>>(a, b, p);
+  } else {
+    e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_gemm<BN, AK, BK_, false><<<grid, kThreads, smem, st>>>(a, b, p);
+  }
   EQH_LAUNCH_RC();
 }
 
@@ -381,10 +423,11 @@ size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
 }
 
 int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
-                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* residual,
+                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act_flags, const float* residual,
                     int splits, float* ws, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::gemm;
+  const int act = act_flags & 0xff;
   EQH_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0 && splits >= 1 && act >= 0 && act <= 2);
   EQH_CHECK_ARG(M < (1 << 30) && N < (1 << 30) && K < (1 << 30));
   EQH_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0);   // TMA: 16-byte rows
@@ -407,11 +450,12 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   p.kb_per_split = (kb_total + splits - 1) / splits;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool write_hi = (act_flags & 0x100) != 0;   // debug/verification switch, see kWriteHi
 #define EQH_GEMM_CASE(BNV)                                                        \
-  if (a_kmajor && b_kmajor) return launch<BNV, true, true>(tmA, tmB, p, grid, st); \
-  if (a_kmajor && !b_kmajor) return launch<BNV, true, false>(tmA, tmB, p, grid, st); \
-  if (!a_kmajor && !b_kmajor) return launch<BNV, false, false>(tmA, tmB, p, grid, st); \
-  return launch<BNV, false, true>(tmA, tmB, p, grid, st);
+  if (a_kmajor && b_kmajor) return launch<BNV, true, true>(tmA, tmB, p, grid, st, write_hi); \
+  if (a_kmajor && !b_kmajor) return launch<BNV, true, false>(tmA, tmB, p, grid, st, write_hi); \
+  if (!a_kmajor && !b_kmajor) return launch<BNV, false, false>(tmA, tmB, p, grid, st, write_hi); \
+  return launch<BNV, false, true>(tmA, tmB, p, grid, st, write_hi);
   if (BN == 64) { EQH_GEMM_CASE(64) }
   EQH_GEMM_CASE(128)
 #undef EQH_GEMM_CASE

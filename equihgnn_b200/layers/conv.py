@@ -48,12 +48,12 @@ def _pair_scatter(W, a, b, inc: ops.Incidence, group: str, aggr: str):
     C = a.shape[-1]
     if isinstance(W, MLP) and W.fusable():
         w0, b0 = W.lins[0].weight, W.lins[0].bias
-        A = F.linear(a, w0[:, :C])
-        B = F.linear(b, w0[:, C:], b0)
+        A = ops.linear(a, w0[:, :C])
+        B = ops.linear(b, w0[:, C:], b0)
         gamma, beta, eps = W.ln_affine()
         U = ops.fused_message(A, B, gamma, beta, inc, group, aggr, eps)
         scale = inc.nonempty(group) if aggr == "mean" else inc.counts(group)
-        return F.linear(U, W.lins[1].weight) + W.lins[1].bias * scale
+        return ops.linear(U, W.lins[1].weight) + W.lins[1].bias * scale
     # unfused composition of the same primitives
     av = ops.gather_rows(a, inc.vertex32, inc.rowptr_v, inc.perm_v)
     be = ops.gather_rows(b, inc.edges32, inc.rowptr_e, inc.perm_e)

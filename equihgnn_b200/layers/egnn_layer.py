@@ -131,8 +131,8 @@ class EGNN(nn.Module):
         Hp = _round_up(H0, 64)
         W1 = F.pad(lin0.weight, (0, 0, 0, Hp - H0))
         b1 = F.pad(lin0.bias, (0, Hp - H0))
-        P = F.linear(h, W1[:, :C], b1)
-        Q = F.linear(h, W1[:, C:2 * C])
+        P = ops.linear(h, W1[:, :C], b1)
+        Q = ops.linear(h, W1[:, C:2 * C])
         wc = W1[:, 2 * C].contiguous()
         W2 = F.pad(lin3.weight, (0, Hp - H0))
         m_i, m_ij = ops.egnn_edge(P, Q, wc, W2, lin3.bias, d2, graph)
@@ -151,7 +151,8 @@ class EGNN(nn.Module):
         # --- node update (egnn_layer.py:357-362)
         if self.node_mlp is not None:
             node_in = torch.cat((self.node_norm(h), m_i), dim=-1)
-            node_out = self.node_mlp(node_in) + h
+            t = ops.linear(node_in, self.node_mlp[0].weight, self.node_mlp[0].bias, act="silu")
+            node_out = ops.linear(t, self.node_mlp[3].weight, self.node_mlp[3].bias, residual=h)
         else:
             node_out = h
         return node_out.unsqueeze(0), coors_out.unsqueeze(0)

@@ -354,7 +354,7 @@ SM_COUNT = 148
 
 
 def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
-             splits: int = 1) -> torch.Tensor:
+             splits: int = 1, write_hi: bool = False) -> torch.Tensor:
     """D[M,N] = act(A.B^T + bias) + residual with A logical [M,K], B logical [N,K]; an operand flagged
     k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3)."""
     dev = A.device
@@ -364,7 +364,7 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
         ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
     flops = 2.0 * M * N * K
     _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0), _p(D), N, M, N, K,
-          _p(bias), _ACT[act], _p(residual), splits, _p(ws), _stream(), nbytes=flops)
+          _p(bias), _ACT[act] | (0x100 if write_hi else 0), _p(residual), splits, _p(ws), _stream(), nbytes=flops)
     if splits > 1:
         _call("eqh_colsum", 1, _p(ws), splits, M * N, _p(D), _stream())
     return D

@@ -75,3 +75,15 @@ def test_linear_autograd_matches_torch():
         assert rel_err(y, yr) < 2e-6
         for got, want in ((x, xd), (w, wd), (b, bd), (res, rd)):
             assert rel_err(got.grad, want.grad) < 5e-6
+
+
+def test_tensor_core_truncates_tf32_inputs():
+    """The kernel feeds the raw fp32 tile as the 'hi' operand and relies on the tensor core ignoring the low
+    13 mantissa bits (so hi_hw + lo == a exactly).  Writing the masked hi back explicitly must give the same
+    bits; if the hardware rounded instead, the two results would differ at the 1e-4 level."""
+    g = torch.Generator().manual_seed(99)
+    A, B = _mk((1000, 512), g), _mk((384, 512), g)
+    D0 = ops.gemm_raw(A, True, B, True, 1000, 384, 512)
+    D1 = ops.gemm_raw(A, True, B, True, 1000, 384, 512, write_hi=True)
+    assert torch.equal(D0, D1)
+    assert rel_err(D0, A.double() @ B.double().t()) < 2e-6
