@@ -29,6 +29,10 @@ _SIGNATURES = {
     "eqh_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "eqh_fused_msg_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, c_int, _P, _P]),
     "eqh_fused_msg_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, _P, _P, _P]),
+    "eqh_rowln_fwd": (c_int, [_P, _P, _P, c_float, c_int, c_int64, c_int64, _P, _P]),
+    "eqh_rowln_bwd": (c_int, [_P, _P, c_float, c_int, _P, c_int64, c_int64, _P, _P, _P]),
+    "eqh_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "eqh_colsum_tall": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "eqh_colsum": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),

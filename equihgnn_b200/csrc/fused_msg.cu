@@ -163,6 +163,109 @@ __global__ void __launch_bounds__(256) k_fused_bwd(const float* __restrict__ A, 
   }
 }
 
+// Row LayerNorm of the dense MLPs (mlp.py:94-96: relu_ then LayerNorm), optionally with the ReLU folded in:
+//   y = LN(relu?(x)) ; backward dx = relu'(x) * LN_backward(dy), per-CTA partials of dgamma / dbeta.
+template <int V, bool RELU>
+__global__ void __launch_bounds__(256) k_rowln_fwd(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float eps, int64_t rows,
+                                                    float* __restrict__ y) {
+  constexpr int C = 32 * V;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Row<V> g, bt;
+  g.load(gamma, lane);
+  bt.load(beta, lane);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    Row<V> t;
+    t.load(x + r * C, lane);
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) t.v[i] = fmaxf(t.v[i], 0.f);
+    }
+    float mean, rstd;
+    ln_stats<V>(t, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < V; ++i) t.v[i] = (t.v[i] - mean) * rstd * g.v[i] + bt.v[i];
+    t.store(y + r * C, lane);
+  }
+}
+
+template <int V, bool RELU>
+__global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, float eps,
+                                                    const float* __restrict__ dy, int64_t rows, float* __restrict__ dx,
+                                                    float* __restrict__ dgb_partial) {
+  constexpr int C = 32 * V;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Row<V> g, dg, db;
+  g.load(gamma, lane);
+  dg.zero();
+  db.zero();
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    Row<V> pre, t, gy;
+    pre.load(x + r * C, lane);
+    gy.load(dy + r * C, lane);
+#pragma unroll
+    for (int i = 0; i < V; ++i) t.v[i] = RELU ? fmaxf(pre.v[i], 0.f) : pre.v[i];
+    float mean, rstd;
+    ln_stats<V>(t, eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+    Row<V> xh, dxh;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      xh.v[i] = (t.v[i] - mean) * rstd;
+      dxh.v[i] = gy.v[i] * g.v[i];
+      s1 += dxh.v[i];
+      s2 += dxh.v[i] * xh.v[i];
+      dg.v[i] += gy.v[i] * xh.v[i];
+      db.v[i] += gy.v[i];
+    }
+    constexpr float invC = 1.f / C;
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+    Row<V> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float dt = rstd * (dxh.v[i] - s1 - xh.v[i] * s2);
+      o.v[i] = (!RELU || pre.v[i] > 0.f) ? dt : 0.f;
+    }
+    o.store(dx + r * C, lane);
+  }
+  __shared__ __align__(16) float sm[8][2 * C];
+  dg.store(&sm[wib][0], lane);
+  db.store(&sm[wib][C], lane);
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += sm[w][c];
+    dgb_partial[(int64_t)blockIdx.x * 2 * C + c] = v;
+  }
+}
+
+// Column sums of a tall matrix, stage 1: each CTA reduces one chunk of rows for 32 columns
+// (8 interleaved row groups, fixed order); stage 2 is k_colsum over the chunk partials.
+__global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                        int64_t rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float sm[8][32];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int64_t c = blockIdx.x * 32 + cx;
+  const int64_t r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float v = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + rg; r < r1; r += 8) v += __ldg(x + r * cols + c);
+  sm[rg][cx] = v;
+  __syncthreads();
+  if (rg == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][cx];
+    partial[blockIdx.y * cols + c] = t;
+  }
+}
+
 // out[c] = sum_r partial[r,c], r ascending within each of 8 interleaved groups, groups combined in fixed order
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partial, int64_t rows, int64_t cols,
                                                  float* __restrict__ out) {
@@ -241,6 +344,62 @@ int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const i
                                                                      u_rowptr, dOp, nullptr);
     });
   }
+  EQH_LAUNCH_RC();
+}
+
+int eqh_rowln_fwd(const float* x, const float* gamma, const float* beta, float eps, int relu, int64_t rows, int64_t C,
+                  float* y, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(rows >= 0 && gamma && beta && (rows == 0 || (x && y)));
+  EQH_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta));
+  if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
+  if (rows == 0) return EQH_OK;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EQH_DISPATCH_V(C, {
+    if (relu) k_rowln_fwd<V, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, eps, rows, y);
+    else k_rowln_fwd<V, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, eps, rows, y);
+  });
+  EQH_LAUNCH_RC();
+}
+
+int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const float* dy, int64_t rows, int64_t C,
+                  float* dx, float* dgb_partial, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(rows >= 0 && gamma && dgb_partial && (rows == 0 || (x && dy && dx)));
+  EQH_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) && aligned16(dgb_partial));
+  if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EQH_DISPATCH_V(C, {
+    if (relu) k_rowln_bwd<V, true><<<kPartialRows, 256, 0, st>>>(x, gamma, eps, dy, rows, dx, dgb_partial);
+    else k_rowln_bwd<V, false><<<kPartialRows, 256, 0, st>>>(x, gamma, eps, dy, rows, dx, dgb_partial);
+  });
+  EQH_LAUNCH_RC();
+}
+
+size_t eqh_colsum_workspace_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 64) return 0;
+  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64;
+  return sizeof(float) * (size_t)chunks * (size_t)cols;
+}
+
+// Column sums of a tall [rows, cols] matrix (bias gradients): two fixed-order stages through ws.
+int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, float* out, float* ws, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && (cols == 0 || (x && out)));
+  if (cols == 0) return EQH_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows <= 64) {
+    k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(x, rows, cols, out);
+    EQH_LAUNCH_RC();
+  }
+  EQH_CHECK_ARG(ws != nullptr);
+  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64;
+  const int64_t rpc = (rows + chunks - 1) / chunks;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
+  k_colsum_chunks<<<grid, 256, 0, st>>>(x, rows, cols, rpc, ws);
+  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(ws, chunks, cols, out);
   EQH_LAUNCH_RC();
 }
 

@@ -150,7 +150,11 @@ class EGNN(nn.Module):
 
         # --- node update (egnn_layer.py:357-362)
         if self.node_mlp is not None:
-            node_in = torch.cat((self.node_norm(h), m_i), dim=-1)
+            if isinstance(self.node_norm, nn.LayerNorm) and ops.row_ln_supported(h, C):
+                hn = ops.row_layer_norm(h, self.node_norm.weight, self.node_norm.bias, self.node_norm.eps)
+            else:
+                hn = self.node_norm(h)
+            node_in = torch.cat((hn, m_i), dim=-1)
             t = ops.linear(node_in, self.node_mlp[0].weight, self.node_mlp[0].bias, act="silu")
             node_out = ops.linear(t, self.node_mlp[3].weight, self.node_mlp[3].bias, residual=h)
         else:

@@ -49,10 +49,17 @@ class MLP(nn.Module):
         lead = x.shape[:-1]
         x = x.reshape(-1, x.shape[-1])
         for li, lin in enumerate(self.lins):
-            # Linear (+ fused ReLU) on the tcgen05 3xTF32 GEMM for CUDA rows, library GEMM otherwise
-            x = ops.linear(x, lin.weight, lin.bias, act="relu" if li < last else None)
+            norm = self.normalizations[li + 1] if li < last else None
+            if isinstance(norm, nn.LayerNorm) and ops.row_ln_supported(x, lin.out_features):
+                # Linear on the tcgen05 3xTF32 GEMM, then ReLU + LayerNorm as ONE row kernel (fwd and bwd)
+                x = ops.linear(x, lin.weight, lin.bias)
+                x = ops.row_layer_norm(x, norm.weight, norm.bias, norm.eps, relu=True)
+            else:
+                # Linear (+ fused ReLU) on the tcgen05 GEMM for CUDA rows, library GEMM otherwise
+                x = ops.linear(x, lin.weight, lin.bias, act="relu" if li < last else None)
+                if li < last:
+                    x = norm(x)
             if li < last:
-                x = self.normalizations[li + 1](x)
                 x = F.dropout(x, p=self.dropout, training=self.training)
         return x.reshape(*lead, x.shape[-1])
 

@@ -346,6 +346,54 @@ class _FusedMsg(torch.autograd.Function):
         return dA, dB, dgamma, dbeta, None, None, None, None
 
 
+def colsum_tall(x: torch.Tensor) -> torch.Tensor:
+    """x [rows, cols] -> column sums [cols] (deterministic two-stage reduction): nn.Linear bias gradients."""
+    x = _f32(x, "colsum_tall")
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    nb = _lib.load().eqh_colsum_workspace_bytes(rows, cols)
+    ws = torch.empty(nb // 4, dtype=torch.float32, device=x.device) if nb else None
+    _call("eqh_colsum_tall", 2 if nb else 1, _p(x), rows, cols, _p(out), _p(ws), _stream(), nbytes=4.0 * (rows + 1) * cols)
+    return out
+
+
+class _RowLayerNorm(torch.autograd.Function):
+    """y = LayerNorm(relu?(x)) over the last dim of 2-D rows; only x is kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, relu):
+        x = _f32(x, "rowln x")
+        gamma = _f32(gamma, "rowln gamma")
+        beta = _f32(beta, "rowln beta")
+        rows, C = x.shape
+        y = torch.empty_like(x)
+        _call("eqh_rowln_fwd", 1 if rows else 0, _p(x), _p(gamma), _p(beta), eps, int(relu), rows, C, _p(y), _stream(),
+              nbytes=8.0 * rows * C)
+        ctx.save_for_backward(x, gamma)
+        ctx.eps, ctx.relu = eps, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dy = _f32(dy, "rowln grad")
+        rows, C = x.shape
+        dx = torch.empty_like(x)
+        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=x.device)
+        _call("eqh_rowln_bwd", 1, _p(x), _p(gamma), ctx.eps, int(ctx.relu), _p(dy), rows, C, _p(dx), _p(part), _stream(),
+              nbytes=12.0 * rows * C)
+        gb = colsum_raw(part)
+        return dx, gb[:C], gb[C:], None, None
+
+
+def row_layer_norm(x, gamma, beta, eps: float = 1e-5, relu: bool = False) -> torch.Tensor:
+    return _RowLayerNorm.apply(x, gamma, beta, eps, relu)
+
+
+def row_ln_supported(x: torch.Tensor, width: int) -> bool:
+    return x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and width in (32, 64, 128, 256, 512)
+
+
 # ----------------------------------------------------------------------------------------------
 # dense row GEMMs on tcgen05 (3xTF32, fp32-faithful)
 # ----------------------------------------------------------------------------------------------
@@ -421,7 +469,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = gemm_raw(dy, False, x, False, N, K, M, splits=_wgrad_splits(N, K, M))   # dW = dY^T . X
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
+            db = colsum_tall(dy)
         return dx, dw, db, None, dres
 
 

@@ -117,6 +117,17 @@ EQH_API int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia,
                       const int32_t* rowptr, int64_t n_seg, int64_t C, const float* gamma, const float* beta,
                       float eps, const float* dU, const int32_t* u_rowptr, float* dOp, float* dgb_partial,
                       eqh_stream_t stream);
+/* Row LayerNorm of the dense MLP hidden layers (mlp.py:94-96: relu_ followed by LayerNorm), with the
+ * ReLU optionally folded in: y = LN(relu ? max(x,0) : x).  Backward: dx (ReLU mask applied when relu),
+ * dgb_partial [eqh_partial_rows(), 2C] = per-CTA partials of dgamma | dbeta (finish with eqh_colsum). */
+EQH_API int eqh_rowln_fwd(const float* x, const float* gamma, const float* beta, float eps, int relu, int64_t rows, int64_t C,
+                  float* y, eqh_stream_t stream);
+EQH_API int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const float* dy, int64_t rows, int64_t C,
+                  float* dx, float* dgb_partial, eqh_stream_t stream);
+/* Column sums of a tall row-major [rows, cols] matrix (bias gradients of nn.Linear): two fixed-order
+ * stages through ws (eqh_colsum_workspace_bytes).  Deterministic. */
+EQH_API size_t eqh_colsum_workspace_bytes(int64_t rows, int64_t cols);
+EQH_API int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, float* out, float* ws, eqh_stream_t stream);
 /* out[c] = sum_r partial[r,c] for r in [0,rows): fixed-order (deterministic) column sum */
 EQH_API int eqh_colsum(const float* partial, int64_t rows, int64_t cols, float* out, eqh_stream_t stream);
 

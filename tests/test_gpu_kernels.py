@@ -299,3 +299,31 @@ def test_atom_encoder_fwd_bwd(C, N):
     enc.zero_grad(set_to_none=True)
     (enc(x.to(DEV)) * w.to(DEV)).sum().backward()
     assert all(torch.equal(a, e.weight.grad) for a, e in zip(g1, enc.atom_embedding_list))   # deterministic
+
+
+@pytest.mark.parametrize("C", [64, 256])
+@pytest.mark.parametrize("relu", [False, True])
+def test_row_layer_norm_fwd_bwd(C, relu):
+    g = torch.Generator().manual_seed(C + relu)
+    x = torch.randn(1234, C, generator=g)
+    gamma = 1 + 0.2 * torch.randn(C, generator=g)
+    beta = 0.2 * torch.randn(C, generator=g)
+    w = torch.randn(1234, C, generator=g)
+    lv = [t.clone().double().requires_grad_(True) for t in (x, gamma, beta)]
+    ref = F.layer_norm(F.relu(lv[0]) if relu else lv[0], (C,), lv[1], lv[2], 1e-5)
+    (ref * w.double()).sum().backward()
+    dv = [t.to(DEV).requires_grad_(True) for t in (x, gamma, beta)]
+    y = ops.row_layer_norm(dv[0], dv[1], dv[2], 1e-5, relu=relu)
+    assert rel_err(y, ref) < TOL
+    (y * w.to(DEV)).sum().backward()
+    for a_, b_ in zip(dv, lv):
+        assert rel_err(a_.grad, b_.grad) < TOL
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 64), (64, 256), (65, 256), (2560, 256), (30000, 1088), (5000, 17)])
+def test_colsum_tall(rows, cols):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, cols, generator=g)
+    out = ops.colsum_tall(x.to(DEV))
+    assert rel_err(out, x.double().sum(0)) < 2e-6
+    assert torch.equal(out, ops.colsum_tall(x.to(DEV)))
