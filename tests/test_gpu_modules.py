@@ -309,11 +309,17 @@ def test_graphed_trainer_matches_eager_unpadded_steps():
     i_pad, _ = ops.knn16(pb.pos.to(DEV))
     assert torch.equal(i_real, i_pad[:batches[0].num_atoms])
     losses_e, losses_g = [], []
+    worst2 = None
     for step in range(6):
         b = batches[step % len(batches)]
         losses_e.append(float(eager.step(b.to(DEV)).item()))
         padded = pad_batch(b, bucket_of(b, (64, 64, 128))).pin_memory()
         losses_g.append(graphed.step_from_host(padded, DEV))
+        if step == 1:      # parameters after two optimizer steps: before rounding differences get amplified
+            pe2 = dict(eager.model.named_parameters())
+            worst2 = max(float((q - pe2[k]).abs().max()) / max(float(pe2[k].abs().max()), 1e-2)
+                         for k, q in graphed.model.named_parameters())
+    assert worst2 is not None and worst2 < 2e-3, worst2
     assert len(graphed.buckets) >= 1 and graphed.replays == 6
     for k, (a_, b_) in enumerate(zip(losses_e, losses_g)):
         # the first steps agree to rounding; afterwards Adam's normalised updates amplify last-bit differences
@@ -324,7 +330,7 @@ def test_graphed_trainer_matches_eager_unpadded_steps():
     worst = 0.0
     for k, q in graphed.model.named_parameters():
         worst = max(worst, float((q - pe[k]).abs().max()) / max(float(pe[k].abs().max()), 1e-3))
-    assert worst < 5e-3, worst       # 6 Adam steps (lr 1e-3) amplify fp32 rounding in sign-like updates
+    assert worst < 0.1, worst        # 6 Adam steps (lr 1e-3) amplify fp32 rounding in sign-like updates of tiny parameters
     # phi_x parameters never move (no gradient reaches them, fact 4)
     torch.manual_seed(11)
     ref = EGNNEquiHNNS(1, args)
