@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(384) k_edge_bwd(const float* __restrict__ P, c
 #pragma unroll
       for (int c = 0; c < HC; ++c) {
         const float pre = (pi[c] + q[c]) + dd * wcr[c];
-        const float sg = 1.f / (1.f + expf(-pre));
+        float ex, sg;                                   // SFU approximations (~1 ulp each), see egnn_edge_tc.cu
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + ex));
         const float hid = pre * sg;
         const float dsl = sg * (1.f + pre * (1.f - sg));
         float dh = 0.f;

@@ -589,8 +589,10 @@ class _EgnnEdge(torch.autograd.Function):
         S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mij = torch.empty((N, KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_fwd", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij),
-              _p(Mi), _stream())
+        # tensor-core kernel by default; EQH_EDGE_FWD=simt selects the CUDA-core implementation of the same math
+        name = "eqh_egnn_edge_fwd" if os.environ.get("EQH_EDGE_FWD", "tc") == "simt" else "eqh_egnn_edge_fwd_tc"
+        _call(name, 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij), _p(Mi),
+              _stream(), nbytes=2.0 * N * KNN_K * H * M_DIM)
         ctx.save_for_backward(P, Q, wc, W2, b2, d2, S2)
         ctx.graph = graph
         ctx.set_materialize_grads(False)

@@ -155,6 +155,12 @@ EQH_API int eqh_egnn_edge_fwd(const float* P, const float* Q, const float* wc, c
                       const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
                       float* Mi, eqh_stream_t stream);
 EQH_API size_t eqh_egnn_edge_fwd_smem_bytes(int64_t H);
+/* Same contract, tensor-core implementation: the 16-wide contraction runs on tcgen05 (3xTF32, fp32-faithful,
+ * [128 edges x 32] hid tiles produced into 128B-swizzled shared memory by the gather/SiLU warps, accumulators
+ * double-buffered in TMEM).  eqh_egnn_edge_fwd is the CUDA-core version of the same math. */
+EQH_API int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                         const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
+                         float* Mi, eqh_stream_t stream);
 /* Backward.  dMi [N,16] and/or dMij [N*16,16] (either may be NULL).  Outputs:
  *   dP [N,H]; dPre [N*16,H] (per-edge gradient of `pre`: dQ[j] = sum over incoming edges, done by
  *   eqh_gather_reduce over the transposed kNN incidence); dd2 [N,16] (optional);
