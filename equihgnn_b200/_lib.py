@@ -32,8 +32,8 @@ _SIGNATURES = {
     "eqh_rowln_fwd": (c_int, [_P, _P, _P, c_float, c_int, c_int64, c_int64, _P, _P]),
     "eqh_rowln_bwd": (c_int, [_P, _P, c_float, c_int, _P, c_int64, c_int64, _P, _P, _P]),
     "eqh_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "eqh_colsum_tall": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
-    "eqh_colsum": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "eqh_colsum_tall": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int, _P, _P]),
+    "eqh_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_float, c_int, _P]),
     "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
     "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
@@ -43,8 +43,8 @@ _SIGNATURES = {
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),
     "eqh_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "eqh_gemm_tf32x3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P,
-                                c_int, _P, _P]),
+    "eqh_gemm_tf32x3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int,
+                                _P, c_float, c_float, c_int, _P, _P]),
     "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                               c_float, _P]),
 }

@@ -285,15 +285,16 @@ __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, 
 
 // Column sums of a tall matrix, stage 1: each CTA reduces one chunk of rows for 32 columns
 // (8 interleaved row groups, fixed order); stage 2 is k_colsum over the chunk partials.
-__global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__ x, int64_t rows, int64_t cols,
-                                                        int64_t rows_per_chunk, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                                        const float* __restrict__ roww, int64_t rows_per_chunk,
+                                                        float* __restrict__ partial) {
   __shared__ float sm[8][32];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int64_t c = blockIdx.x * 32 + cx;
   const int64_t r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
   float v = 0.f;
   if (c < cols)
-    for (int64_t r = r0 + rg; r < r1; r += 8) v += __ldg(x + r * cols + c);
+    for (int64_t r = r0 + rg; r < r1; r += 8) v += roww ? __ldg(roww + r) * __ldg(x + r * ld + c) : __ldg(x + r * ld + c);
   sm[rg][cx] = v;
   __syncthreads();
   if (rg == 0 && c < cols) {
@@ -305,21 +306,21 @@ __global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__
 }
 
 // out[c] = sum_r partial[r,c], r ascending within each of 8 interleaved groups, groups combined in fixed order
-__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partial, int64_t rows, int64_t cols,
-                                                 float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partial, int64_t rows, int64_t cols, int64_t ld,
+                                                 float* out, float scale, int accumulate) {
   __shared__ float sm[8][32];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int64_t c = blockIdx.x * 32 + cx;
   float v = 0.f;
   if (c < cols)
-    for (int64_t r = rg; r < rows; r += 8) v += __ldg(partial + r * cols + c);
+    for (int64_t r = rg; r < rows; r += 8) v += __ldg(partial + r * ld + c);
   sm[rg][cx] = v;
   __syncthreads();
   if (rg == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += sm[w][cx];
-    out[c] = t;
+    out[c] = accumulate ? out[c] + scale * t : scale * t;
   }
 }
 
@@ -435,35 +436,38 @@ int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const
 }
 
 size_t eqh_colsum_workspace_bytes(int64_t rows, int64_t cols) {
-  if (rows <= 64) return 0;
-  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64;
+  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64 > 0 ? (rows + 63) / 64 : 1;
   return sizeof(float) * (size_t)chunks * (size_t)cols;
 }
 
-// Column sums of a tall [rows, cols] matrix (bias gradients): two fixed-order stages through ws.
-int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, float* out, float* ws, eqh_stream_t stream) {
+// Column sums of a tall [rows, cols] matrix with row stride ld (bias gradients): out (+)= sum_r roww[r] * x[r,:],
+// two fixed-order stages through ws.
+int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, int64_t ld, const float* roww, float* out, int accumulate,
+                    float* ws, eqh_stream_t stream) {
   using namespace eqh;
-  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && (cols == 0 || (x && out)));
+  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && ld >= cols && (cols == 0 || (x && out)));
   if (cols == 0) return EQH_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (rows <= 64) {
-    k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(x, rows, cols, out);
+  if (rows <= 64 && !roww) {
+    k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(x, rows, cols, ld, out, 1.f, accumulate);
     EQH_LAUNCH_RC();
   }
   EQH_CHECK_ARG(ws != nullptr);
-  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64;
+  const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64 > 0 ? (rows + 63) / 64 : 1;
   const int64_t rpc = (rows + chunks - 1) / chunks;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
-  k_colsum_chunks<<<grid, 256, 0, st>>>(x, rows, cols, rpc, ws);
-  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(ws, chunks, cols, out);
+  k_colsum_chunks<<<grid, 256, 0, st>>>(x, rows, cols, ld, roww, rpc, ws);
+  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(ws, chunks, cols, cols, out, 1.f, accumulate);
   EQH_LAUNCH_RC();
 }
 
-int eqh_colsum(const float* partial, int64_t rows, int64_t cols, float* out, eqh_stream_t stream) {
+int eqh_colsum(const float* partial, int64_t rows, int64_t cols, int64_t ld, float* out, float scale, int accumulate,
+               eqh_stream_t stream) {
   using namespace eqh;
-  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && (cols == 0 || (partial && out)));
+  EQH_CHECK_ARG(rows >= 0 && cols >= 0 && ld >= cols && (cols == 0 || (partial && out)));
   if (cols == 0) return EQH_OK;
-  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, cols, out);
+  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, cols, ld, out, scale,
+                                                                                      accumulate);
   EQH_LAUNCH_RC();
 }
 

@@ -32,7 +32,9 @@ constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand 
 struct Params {
   float* D;
   const float* bias;
-  const float* residual;
+  const float* rowscale;   // optional [M]: the bias is multiplied by rowscale[m] (empty-segment mask / segment count)
+  const float* residual;   // optional [M, ldd]; may alias D (in-place accumulation)
+  float out_scale, res_scale;
   float* ws;          // split-K partials [splits, M, N] (ldd == N) or nullptr
   int64_t ldd;
   int M, N, K;
@@ -208,6 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int act = final_out ? p.act : 0;
+    const float rs = (final_out && p.rowscale && m0 + row < p.M) ? __ldg(p.rowscale + m0 + row) : 1.f;
+    const float osc = final_out ? p.out_scale : 1.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);   // warp-uniform address: broadcast
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        v[j] += b4.x * rs; v[j + 1] += b4.y * rs; v[j + 2] += b4.z * rs; v[j + 3] += b4.w * rs;
       }
       if (act == 1) {
 #pragma unroll
@@ -241,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) =
+            make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
     float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
@@ -258,9 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       float* dst = out + (int64_t)(m0 + r) * ld + n;
       if (full_vec) {
         float4 x = *reinterpret_cast<const float4*>(src);
-        if (has_res) {
-          const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n));
-          x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+        if (has_res) {   // plain (coherent) load: the residual may be D itself
+          const float4 rr = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
+          x.x += p.res_scale * rr.x; x.y += p.res_scale * rr.y; x.z += p.res_scale * rr.z; x.w += p.res_scale * rr.w;
         }
         *reinterpret_cast<float4*>(dst) = x;
       } else {
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
         for (int j = 0; j < CPL; ++j) {
           if (n + j < p.N) {
             float x = src[j];
-            if (has_res) x += __ldg(p.residual + (int64_t)(m0 + r) * ld + n + j);
+            if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
             dst[j] = x;
           }
         }
@@ -280,6 +285,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 #undef tmem_full
 #undef tmem_slot
+}
+
+// Split-K finish: D[m,n] = out_scale * sum_z ws[z,m,n] + res_scale * R[m,n], partials added in split order
+// (deterministic); R may alias D.
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ ws, int splits, int M, int N, float* D,
+                                                        int64_t ldd, const float* R, float out_scale, float res_scale) {
+  const int64_t total = (int64_t)M * N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += __ldg(ws + (int64_t)z * total + i);
+    const int64_t m = i / N, n = i - m * N;
+    float x = out_scale * acc;
+    if (R) x += res_scale * R[m * ldd + n];
+    D[m * ldd + n] = x;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -342,15 +363,16 @@ size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
 }
 
 int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
-                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act_flags, const float* residual,
-                    int splits, float* ws, eqh_stream_t stream) {
+                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act_flags,
+                    const float* residual, float out_scale, float res_scale, int splits, float* ws, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::gemm;
   const int act = act_flags & 0xff;
   EQH_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0 && splits >= 1 && act >= 0 && act <= 2);
   EQH_CHECK_ARG(M < (1 << 30) && N < (1 << 30) && K < (1 << 30));
   EQH_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0);   // TMA: 16-byte rows
-  EQH_CHECK_ARG(splits == 1 || (ws && !bias && act == 0 && !residual));
+  EQH_CHECK_ARG(splits == 1 || (ws && !bias && act == 0));
+  EQH_CHECK_ARG(ldd >= N);
   const int BN = N <= 64 ? 64 : 128;
   CUtensorMap tmA, tmB;
   int rc;
@@ -363,20 +385,31 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
                 : make_map(&tmB, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   Params p;
-  p.D = D; p.bias = bias; p.residual = residual; p.ws = splits > 1 ? ws : nullptr; p.ldd = ldd;
+  p.D = D; p.bias = bias; p.rowscale = rowscale; p.residual = residual; p.ws = splits > 1 ? ws : nullptr; p.ldd = ldd;
+  p.out_scale = out_scale; p.res_scale = res_scale;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.act = act;
   const int kb_total = (int)((K + BK - 1) / BK);
   p.kb_per_split = (kb_total + splits - 1) / splits;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool write_hi = (act_flags & 0x100) != 0;   // debug/verification switch, see kWriteHi
+  auto dispatch = [&]() -> int {
 #define EQH_GEMM_CASE(BNV)                                                        \
   if (a_kmajor && b_kmajor) return launch<BNV, true, true>(tmA, tmB, p, grid, st, write_hi); \
   if (a_kmajor && !b_kmajor) return launch<BNV, true, false>(tmA, tmB, p, grid, st, write_hi); \
   if (!a_kmajor && !b_kmajor) return launch<BNV, false, false>(tmA, tmB, p, grid, st, write_hi); \
   return launch<BNV, false, true>(tmA, tmB, p, grid, st, write_hi);
-  if (BN == 64) { EQH_GEMM_CASE(64) }
-  EQH_GEMM_CASE(128)
+    if (BN == 64) { EQH_GEMM_CASE(64) }
+    EQH_GEMM_CASE(128)
+  };
+  rc = dispatch();
+  if (rc || splits == 1) return rc;
+  {
+    int64_t blocks = (M * N + 255) / 256;
+    if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
+    k_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>(ws, splits, (int)M, (int)N, D, ldd, residual, out_scale, res_scale);
+  }
+  EQH_LAUNCH_RC();
 #undef EQH_GEMM_CASE
 }
 

@@ -214,10 +214,15 @@ def gather_rows_raw(table, idx, scale_rowptr, n_rows: int) -> torch.Tensor:
     return out
 
 
-def colsum_raw(partial: torch.Tensor) -> torch.Tensor:
-    rows, cols = partial.shape
-    out = torch.empty(cols, dtype=torch.float32, device=partial.device)
-    _call("eqh_colsum", 1, _p(partial), rows, cols, _p(out), _stream())
+def colsum_raw(partial: torch.Tensor, col0: int = 0, cols: Optional[int] = None, out: Optional[torch.Tensor] = None,
+               scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out (+)= scale * column sums of partial[:, col0:col0+cols] (fixed order, deterministic)."""
+    rows, ld = partial.shape
+    cols = ld - col0 if cols is None else cols
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=partial.device)
+        accumulate = False
+    _call("eqh_colsum", 1, partial.data_ptr() + 4 * col0, rows, cols, ld, _p(out), scale, int(accumulate), _stream())
     return out
 
 
@@ -346,14 +351,19 @@ class _FusedMsg(torch.autograd.Function):
         return dA, dB, dgamma, dbeta, None, None, None, None
 
 
-def colsum_tall(x: torch.Tensor) -> torch.Tensor:
-    """x [rows, cols] -> column sums [cols] (deterministic two-stage reduction): nn.Linear bias gradients."""
+def colsum_tall(x: torch.Tensor, roww: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                accumulate: bool = False) -> torch.Tensor:
+    """out (+)= sum_r roww[r] * x[r, :] for a tall [rows, cols] matrix (deterministic two-stage reduction):
+    nn.Linear bias gradients."""
     x = _f32(x, "colsum_tall")
     rows, cols = x.shape
-    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
+        accumulate = False
     nb = _lib.load().eqh_colsum_workspace_bytes(rows, cols)
-    ws = torch.empty(nb // 4, dtype=torch.float32, device=x.device) if nb else None
-    _call("eqh_colsum_tall", 2 if nb else 1, _p(x), rows, cols, _p(out), _p(ws), _stream(), nbytes=4.0 * (rows + 1) * cols)
+    ws = torch.empty(max(nb // 4, 1), dtype=torch.float32, device=x.device)
+    _call("eqh_colsum_tall", 2, _p(x), rows, cols, x.stride(0), _p(roww), _p(out), int(accumulate), _p(ws), _stream(),
+          nbytes=4.0 * (rows + 1) * cols)
     return out
 
 
@@ -402,19 +412,21 @@ SM_COUNT = 148
 
 
 def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
-             splits: int = 1, write_hi: bool = False) -> torch.Tensor:
-    """D[M,N] = act(A.B^T + bias) + residual with A logical [M,K], B logical [N,K]; an operand flagged
-    k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3)."""
+             splits: int = 1, write_hi: bool = False, rowscale=None, out: Optional[torch.Tensor] = None,
+             out_scale: float = 1.0, res_scale: float = 1.0) -> torch.Tensor:
+    """D = out_scale * act(A.B^T + bias * rowscale) + res_scale * residual with A logical [M,K], B logical [N,K]; an
+    operand flagged k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3).  `out` may be a row-strided
+    view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation)."""
     dev = A.device
-    D = torch.empty((M, N), dtype=torch.float32, device=dev)
-    ws = None
-    if splits > 1:
-        ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
+    D = torch.empty((M, N), dtype=torch.float32, device=dev) if out is None else out
+    ldd = D.stride(0)
+    if residual is not None and residual.stride(0) != ldd:
+        raise RuntimeError("gemm_raw: residual must have the row stride of the output")
+    ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev) if splits > 1 else None
     flops = 2.0 * M * N * K
-    _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0), _p(D), N, M, N, K,
-          _p(bias), _ACT[act] | (0x100 if write_hi else 0), _p(residual), splits, _p(ws), _stream(), nbytes=flops)
-    if splits > 1:
-        _call("eqh_colsum", 1, _p(ws), splits, M * N, _p(D), _stream())
+    _call("eqh_gemm_tf32x3", 2 if splits > 1 else 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
+          _p(D), ldd, M, N, K, _p(bias), _p(rowscale), _ACT[act] | (0x100 if write_hi else 0), _p(residual), out_scale,
+          res_scale, splits, _p(ws), _stream(), nbytes=flops)
     return D
 
 

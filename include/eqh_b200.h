@@ -124,12 +124,15 @@ EQH_API int eqh_rowln_fwd(const float* x, const float* gamma, const float* beta,
                   float* y, eqh_stream_t stream);
 EQH_API int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const float* dy, int64_t rows, int64_t C,
                   float* dx, float* dgb_partial, eqh_stream_t stream);
-/* Column sums of a tall row-major [rows, cols] matrix (bias gradients of nn.Linear): two fixed-order
- * stages through ws (eqh_colsum_workspace_bytes).  Deterministic. */
+/* Column sums of a tall row-major [rows, cols] matrix with row stride ld (bias gradients of nn.Linear), optionally
+ * row-weighted: out (+)= sum_r roww[r] * x[r,:]; two fixed-order stages through ws (eqh_colsum_workspace_bytes,
+ * always required when roww != NULL or rows > 64).  Deterministic. */
 EQH_API size_t eqh_colsum_workspace_bytes(int64_t rows, int64_t cols);
-EQH_API int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, float* out, float* ws, eqh_stream_t stream);
-/* out[c] = sum_r partial[r,c] for r in [0,rows): fixed-order (deterministic) column sum */
-EQH_API int eqh_colsum(const float* partial, int64_t rows, int64_t cols, float* out, eqh_stream_t stream);
+EQH_API int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, int64_t ld, const float* roww /* optional [rows] */,
+                    float* out, int accumulate, float* ws, eqh_stream_t stream);
+/* out[c] (+)= scale * sum_r partial[r*ld + c] for r in [0,rows): fixed-order (deterministic) column sum */
+EQH_API int eqh_colsum(const float* partial, int64_t rows, int64_t cols, int64_t ld, float* out, float scale, int accumulate,
+               eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batch-wide 16-nearest-neighbour search on squared distance.
@@ -194,15 +197,17 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
  * dW = dY^T.X (both MN-major; split-K over the rows, finished by eqh_colsum).
  *   a_kmajor / b_kmajor: 1 = stored row-major [rows, K] (K contiguous), 0 = stored [K, rows].
  *   lda / ldb: row stride of the STORED matrix in floats (multiple of 4, base 16-byte aligned).
- *   D row-major [M, ldd]; bias [N] / residual [M, ldd] optional; act: 0 none, 1 ReLU, 2 SiLU.
- *   splits > 1: partials go to ws [splits, M, N] (eqh_gemm_workspace_bytes), D is not written,
- *   bias/act/residual must be null/0; finish with eqh_colsum(ws, splits, M*N, D).
+ *   Full epilogue: D = out_scale * act(A.B^T + bias[n] * rowscale[m]) + res_scale * residual
+ *   D row-major [M, ldd]; bias [N], rowscale [M], residual [M, ldd] optional (residual may alias D: in-place
+ *   accumulation); act: 0 none, 1 ReLU, 2 SiLU.
+ *   splits > 1 (split-K over the reduction, bias/act must be null/0): partials go to ws [splits, M, N]
+ *   (eqh_gemm_workspace_bytes) and a second launch adds them in split order (deterministic) into D.
  * Ragged M / N / K are handled (TMA zero fill, bounds-checked stores).
  * ---------------------------------------------------------------------------------------- */
 EQH_API size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits);
 EQH_API int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
-                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* residual,
-                    int splits, float* ws, eqh_stream_t stream);
+                    int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
+                    const float* residual, float out_scale, float res_scale, int splits, float* ws, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flat fused Adam step over one contiguous fp32 parameter buffer (main.py:137-140:
