@@ -26,6 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from .fused_conv import MHNNSConvFused
 from .mlp import MLP
 
 
@@ -124,6 +125,23 @@ class MHNNSConv(nn.Module):
         self.aggr = aggr
         self.alpha = alpha
         self.dropout = dropout
+        # set by equihgnn_b200.train.Trainer: parameter gradients are accumulated straight into p.grad by the
+        # kernels' epilogues instead of being returned to autograd (see layers/fused_conv.py)
+        self.direct_param_grad = False
+
+    def _layer_fusable(self, x) -> bool:
+        ws = [getattr(self, f"W{k}", None) for k in (1, 2, 3)]
+        return (all(isinstance(w, MLP) and w.fusable() and w.normalization == "ln" for w in ws)
+                and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and self.hid_dim in (32, 64, 128, 256, 512)
+                and self.aggr in ("mean", "sum"))
+
+    def _fused_params(self):
+        out = []
+        for k in (1, 2, 3):
+            w = getattr(self, f"W{k}")
+            n = w.normalizations[1]
+            out += [w.lins[0].weight, w.lins[0].bias, n.weight, n.bias, w.lins[1].weight, w.lins[1].bias]
+        return out
 
     def reset_parameters(self):
         for k in (1, 2, 3):
@@ -136,6 +154,10 @@ class MHNNSConv(nn.Module):
         inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, N, num_hyperedges)
 
         def layer(x, x0):
+            if self._layer_fusable(x):
+                eps = tuple(getattr(self, f"W{k}").normalizations[1].eps for k in (1, 2, 3))
+                direct = self.direct_param_grad and torch.is_grad_enabled()
+                return MHNNSConvFused.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, *self._fused_params())
             Xe = ops.v2e_gather_reduce(self.W1(x), inc, self.aggr)        # conv.py:172-173
             Xv = _pair_scatter(self.W2, x, Xe, inc, "v", self.aggr)       # conv.py:175-177
             x = (1 - self.alpha) * Xv + self.alpha * x0                   # conv.py:179

@@ -1,0 +1,166 @@
+"""Layer-level autograd Function for MHNNSConv in its shipped configuration (2-layer MLPs with LayerNorm,
+dropout 0): the whole forward and the whole backward are hand-scheduled sequences of this package's kernels --
+tcgen05 GEMMs with fused bias / row-scale / residual-mix / in-place-accumulate epilogues, the fused
+ReLU+LayerNorm row kernels and the fused gather-reduce kernels -- with no autograd-generated elementwise,
+accumulation or reduction launches in between (reference: conv.py:169-182, mlp.py:91-99).
+
+Two gradient modes:
+  * default: parameter gradients are returned to autograd (drop-in semantics);
+  * `direct=True` (set by the Trainer): they are accumulated straight into the parameters' `.grad` storage (the
+    flat gradient buffer) by the producing kernels' epilogues and None is returned, which removes one
+    accumulation launch per parameter and layer.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..ops import MEAN, SUM, _MODES, _call, _p, _stream, colsum_raw, colsum_tall, gather_reduce_raw, gemm_raw, partial_rows
+
+
+def _rowln_fwd(x, g, b, eps):
+    y = torch.empty_like(x)
+    _call("eqh_rowln_fwd", 1, _p(x), _p(g), _p(b), eps, 1, x.shape[0], x.shape[1], _p(y), _stream())
+    return y
+
+
+def _rowln_bwd(x, g, eps, dy):
+    dx = torch.empty_like(x)
+    part = torch.empty((partial_rows(), 2 * x.shape[1]), dtype=torch.float32, device=x.device)
+    _call("eqh_rowln_bwd", 1, _p(x), _p(g), eps, 1, _p(dy), x.shape[0], x.shape[1], _p(dx), _p(part), _stream())
+    return dx, part
+
+
+class _GradSink:
+    """Where a parameter gradient goes: into p.grad (direct mode, accumulate) or into a fresh tensor (returned)."""
+
+    def __init__(self, params, direct):
+        self.direct = direct
+        self.out = {}
+        for p in params:
+            if direct:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                self.out[id(p)] = p.grad
+            else:
+                self.out[id(p)] = None
+        self.params = params
+
+    def weight(self, p, dy, x, cols=None):
+        """p.grad[:, cols] (+)= dy^T x   (dy [M, out], x [M, in])"""
+        M, n_out = dy.shape
+        n_in = x.shape[1]
+        tgt = self.out[id(p)]
+        fresh = tgt is None
+        if fresh:
+            tgt = self.out[id(p)] = torch.empty_like(p)
+            self._fresh_cols = getattr(self, "_fresh_cols", {})
+        view = tgt if cols is None else tgt[:, cols]
+        acc = self.direct or (not fresh and cols is None)
+        gemm_raw(dy, False, x, False, n_out, n_in, M, splits=ops._wgrad_splits(n_out, n_in, M), out=view,
+                 residual=view if acc else None)
+
+    def bias(self, p, dy, roww=None):
+        tgt = self.out[id(p)]
+        if tgt is None:
+            self.out[id(p)] = colsum_tall(dy, roww)
+        else:
+            colsum_tall(dy, roww, out=tgt, accumulate=True)
+
+    def affine(self, g, b, part):
+        C = g.shape[0]
+        for p, c0 in ((g, 0), (b, C)):
+            tgt = self.out[id(p)]
+            if tgt is None:
+                self.out[id(p)] = colsum_raw(part, c0, C)
+            else:
+                colsum_raw(part, c0, C, out=tgt, accumulate=True)
+
+    def results(self):
+        return tuple(None if self.direct else self.out[id(p)] for p in self.params)
+
+
+class MHNNSConvFused(torch.autograd.Function):
+    """(X, X0) -> W3((1-alpha) * mean_v(W2(cat(X[v], mean_e(W1(X)[v])[e]))) + alpha * X0)   (conv.py:169-182)."""
+
+    @staticmethod
+    def forward(ctx, X, X0, inc, aggr, alpha, direct, eps, *params):
+        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+        X = ops._f32(X, "MHNNSConv X")
+        X0 = ops._f32(X0, "MHNNSConv X0")
+        N, C = X.shape
+        mode = _MODES[aggr]
+        h1 = gemm_raw(X, True, w10, True, N, C, C, bias=b10)
+        y1 = _rowln_fwd(h1, g1, t1, eps[0])
+        Y = gemm_raw(y1, True, w11, True, N, C, C, bias=b11)
+        Xe = gather_reduce_raw(Y, inc.vtx_by_e, inc.rowptr_e, None, inc.E, mode)                    # conv.py:172-173
+        A = gemm_raw(X, True, w20[:, :C], True, N, C, C)
+        Bm = gemm_raw(Xe, True, w20[:, C:], True, inc.E, C, C, bias=b20)
+        U = torch.empty((N, C), dtype=torch.float32, device=X.device)
+        _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
+              mode, _p(U), _stream())                                                                # conv.py:175-177
+        rowscale = inc.nonempty("v") if mode == MEAN else inc.counts("v")
+        # last Linear of W2 commuted with the reduction, and the residual mix (conv.py:179) in the same epilogue
+        Xm = gemm_raw(U, True, w21, True, N, C, C, bias=b21, rowscale=rowscale, out_scale=1.0 - alpha, residual=X0,
+                      res_scale=alpha)
+        h3 = gemm_raw(Xm, True, w30, True, N, C, C, bias=b30)
+        y3 = _rowln_fwd(h3, g3, t3, eps[2])
+        out = gemm_raw(y3, True, w31, True, N, C, C, bias=b31)                                      # conv.py:180
+        ctx.save_for_backward(X, h1, y1, Xe, A, Bm, U, Xm, h3, y3, rowscale, *params)
+        ctx.inc, ctx.mode, ctx.alpha, ctx.direct, ctx.eps = inc, mode, alpha, direct, eps
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        saved = ctx.saved_tensors
+        X, h1, y1, Xe, A, Bm, U, Xm, h3, y3, rowscale = saved[:11]
+        params = saved[11:]
+        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+        inc, mode, alpha, eps = ctx.inc, ctx.mode, ctx.alpha, ctx.eps
+        sink = _GradSink(params, ctx.direct)
+        dOut = ops._f32(dOut, "MHNNSConv grad")
+        N, C = X.shape
+        E = inc.E
+        # ---- W3
+        dy3 = gemm_raw(dOut, True, w31, False, N, C, C)
+        sink.weight(w31, dOut, y3)
+        sink.bias(b31, dOut)
+        dh3, part = _rowln_bwd(h3, g3, eps[2], dy3)
+        sink.affine(g3, t3, part)
+        dXm = gemm_raw(dh3, True, w30, False, N, C, C)
+        sink.weight(w30, dh3, Xm)
+        sink.bias(b30, dh3)
+        # ---- residual mix
+        if alpha == 0.5:
+            dXv = dX0 = dXm * 0.5
+        else:
+            dXv, dX0 = dXm * (1.0 - alpha), dXm * alpha
+        # ---- W2: last Linear (commuted), fused message, split first Linear
+        dU = gemm_raw(dXv, True, w21, False, N, C, C)
+        sink.weight(w21, dXv, U)
+        sink.bias(b21, dXv, roww=rowscale)
+        dA = torch.empty_like(A)
+        dBm = torch.empty_like(Bm)
+        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=X.device)
+        u_rp = inc.rowptr_v if mode == MEAN else None
+        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), N, C, _p(g2), _p(t2),
+              eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream())
+        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), E, C,
+              _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream())
+        sink.affine(g2, t2, part)
+        dX = gemm_raw(dA, True, w20[:, :C], False, N, C, C)
+        dXe = gemm_raw(dBm, True, w20[:, C:], False, E, C, C)
+        sink.weight(w20, dA, X, cols=slice(0, C))
+        sink.weight(w20, dBm, Xe, cols=slice(C, 2 * C))
+        sink.bias(b20, dBm)
+        # ---- V2E gather-mean backward, W1
+        dY = gather_reduce_raw(dXe, inc.edge_by_v, inc.rowptr_v, inc.rowptr_e if mode == MEAN else None, N, SUM)
+        dy1 = gemm_raw(dY, True, w11, False, N, C, C)
+        sink.weight(w11, dY, y1)
+        sink.bias(b11, dY)
+        dh1, part = _rowln_bwd(h1, g1, eps[0], dy1)
+        sink.affine(g1, t1, part)
+        gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX)          # dX += dh1 . W1_0 (in-place epilogue)
+        sink.weight(w10, dh1, X)
+        sink.bias(b10, dh1)
+        return (dX, dX0, None, None, None, None, None) + sink.results()

@@ -56,6 +56,9 @@ class Trainer:
                  distributed: Optional[bool] = None):
         self.model = model
         self.fp = FlatParams(model)
+        for m in model.modules():       # kernels accumulate parameter gradients straight into the flat buffer
+            if hasattr(m, "direct_param_grad"):
+                m.direct_param_grad = True
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
