@@ -34,6 +34,9 @@ _SIGNATURES = {
     "eqh_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "eqh_colsum_tall": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int, _P, _P]),
     "eqh_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_float, c_int, _P]),
+    "eqh_colsum_batch_workspace_bytes": (c_size_t, [_P, c_int]),
+    "eqh_colsum_batch_counters": (c_int64, [_P, c_int]),
+    "eqh_colsum_batch": (c_int, [_P, c_int, _P, _P, _P]),
     "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
     "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
@@ -43,12 +46,22 @@ _SIGNATURES = {
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),
     "eqh_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "eqh_gemm_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
     "eqh_gemm_tf32x3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int,
-                                _P, c_float, c_float, c_int, _P, _P]),
+                                _P, c_float, c_float, c_int, _P, _P, _P]),
     "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                               c_float, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
+
+
+class ColsumJob(ctypes.Structure):
+    """struct eqh_colsum_job (include/eqh_b200.h)"""
+    _fields_ = [("x", c_void_p), ("roww", c_void_p), ("out", c_void_p), ("rows", c_int64), ("cols", c_int64),
+                ("ld", c_int64), ("scale", c_float), ("accumulate", ctypes.c_int32)]
+
+
+COLSUM_MAX_JOBS = 32
 
 _lib = None
 

@@ -58,7 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = pair
         if not force and not _stale(obj, [src] + headers):
             return None
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("EQH_NVCC_EXTRA", "").split()          # e.g. -DEQH_TRACE for the phase-timing experiments
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

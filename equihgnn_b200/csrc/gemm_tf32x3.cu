@@ -17,14 +17,29 @@
 // Operands may be K-major (row-major [rows, K]) or MN-major ([K, rows], the natural layout of the
 // backward GEMMs dX = dY.W and dW = dY^T.X), selected by the UMMA descriptor major bits, so no
 // transposed copies are ever made.  Split-K (weight gradients: K = number of rows, tiny M x N) writes
-// per-split partials that eqh_colsum finishes in a fixed order (deterministic).
+// per-split partials; the CTA arriving last at a tile's counter adds them in split order (deterministic)
+// and applies the output transform -- one launch.  The tile width (32/64/128) and the split count are
+// chosen per problem so that small GEMMs still occupy every SM (plan()).
 #include "tc_common.cuh"
 
 namespace eqh {
 namespace gemm {
 using namespace eqh::tc;
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32;
+
+#ifdef EQH_TRACE
+// phase timestamps (ns, globaltimer) of CTA (0,0,0) of the most recent launch: scratch/trace_gemm.py
+__device__ unsigned long long g_trace[16];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define EQH_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[i] = gtime(); } while (0)
+#else
+#define EQH_STAMP(i) do { } while (0)
+#endif
 constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 operand split (warps 4-7 also epilogue)
 constexpr int kSplitThreads = 256;
 constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
@@ -36,6 +51,8 @@ struct Params {
   const float* residual;   // optional [M, ldd]; may alias D (in-place accumulation)
   float out_scale, res_scale;
   float* ws;          // split-K partials [splits, M, N] (ldd == N) or nullptr
+  int32_t* counters;  // split-K: one arrival counter per output tile (zero on entry, left zero)
+  int splits;
   int64_t ldd;
   int M, N, K;
   int act;            // 0 none, 1 relu, 2 silu
@@ -44,8 +61,8 @@ struct Params {
 
 // kWriteHi: store the masked hi part back (true) or let the tensor core drop the low 13 bits of the raw fp32
 // tile itself (false; valid if the hardware truncates tf32 inputs -- checked by tests/test_gpu_gemm.py).
-template <int BN, bool A_KMAJOR, bool B_KMAJOR, bool kWriteHi>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_KMAJOR, bool B_KMAJOR, bool kWriteHi, int STAGES, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB, const Params p) {
   constexpr uint32_t kABytes = kTileBytes;            // 128 x 32
   constexpr uint32_t kBBytes = BN * BK * 4;
@@ -56,11 +73,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   uint64_t* empty = full_split + STAGES;
   uint64_t* tmem_full_p = empty + STAGES;
   uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(tmem_full_p + 1);
+  __shared__ int s_last;
 #define tmem_full (*tmem_full_p)
 #define tmem_slot (*tmem_slot_p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  if (threadIdx.x == 0) EQH_STAMP(0);
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
@@ -69,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_raw[s], 1);
-      mbar_init(&full_split[s], kSplitThreads);
+      mbar_init(&full_split[s], kSplitThreads / 32);     // one elected arrival per split warp
       mbar_init(&empty[s], 1);
     }
     mbar_init(&tmem_full, 1);
@@ -78,12 +97,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
   // Three fp32 accumulators of BN columns each.  The tensor core adds into its accumulator with
   // truncation, so the error grows with the number of accumulations: the large hi.hi terms alternate
   // between two accumulators and the 2^-11-scaled lo terms get their own (summed in the epilogue).
-  constexpr uint32_t kTmemCols = BN * 4;       // power of two >= 3*BN
+  constexpr uint32_t kTmemCols = BN * 4;       // power of two >= 3*BN (>= 32)
+  static_assert(kTmemCols * MINB <= 512, "co-resident CTAs must fit in TMEM");
   if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) EQH_STAMP(1);
 
   auto stageA = [&](int s) { return smem + (size_t)s * kStageBytes; };
   auto stageAlo = [&](int s) { return smem + (size_t)s * kStageBytes + kABytes; };
@@ -128,6 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_split[s], ph);
+        if (i == 0) EQH_STAMP(3);
+        if (i == nkb - 1) EQH_STAMP(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t aH = smem_u32(stageA(s)), aL = smem_u32(stageAlo(s));
         const uint32_t bH = smem_u32(stageB(s)), bL = smem_u32(stageBlo(s));
@@ -151,6 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(&full_raw[s], ph);
+      if (t == 0 && i == 0) EQH_STAMP(2);
+      if (t == 0 && i == nkb - 1) EQH_STAMP(4);
       {
         float4* ah = reinterpret_cast<float4*>(stageA(s));
         float4* al = reinterpret_cast<float4*>(stageAlo(s));
@@ -172,7 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       {
         float4* bh = reinterpret_cast<float4*>(stageB(s));
         float4* bl = reinterpret_cast<float4*>(stageBlo(s));
-        constexpr int NB = kBBytes / 16 / kSplitThreads;   // 4 (BN=128) or 2 (BN=64)
+        constexpr int NB = kBBytes / 16 / kSplitThreads;   // 4 (BN=128), 2 (BN=64), 1 (BN=32)
+        static_assert(NB >= 1, "BN >= 32");
         float4 v[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) v[j] = bh[j * kSplitThreads + t];
@@ -188,7 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&full_split[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_split[s]);
     }
   }
   if (warp >= 4 && warp < 8) {
@@ -201,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       mbar_wait(&tmem_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    if (threadIdx.x == 128) EQH_STAMP(6);
     const bool final_out = (p.ws == nullptr);
     // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
     float* sbias = reinterpret_cast<float*>(smem + (size_t)STAGES * kStageBytes + 128);   // [BN] after the barriers
@@ -217,14 +245,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
       float v[32];
       if (nkb > 0) {
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        float w[32];
-        tmem_ld32(ta + 2 * BN, v);                           // small terms
-        if (nkb * (BK / 8) >= 2) {                           // the odd accumulator exists from the second k-step on
-          tmem_ld32(ta + BN, w);
+        float w[32], u[32];
+        const bool odd = nkb * (BK / 8) >= 2;                // the odd accumulator exists from the second k-step on
+        tmem_ld32_nowait(ta + 2 * BN, v);                    // small terms
+        tmem_ld32_nowait(ta, w);
+        if (odd) tmem_ld32_nowait(ta + BN, u);
+        tmem_ld_wait();
+        if (odd) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
         }
-        tmem_ld32(ta, w);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += w[j];
       } else {
@@ -249,58 +279,120 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm(const __grid_constant__ CU
             make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+    if (threadIdx.x == 128) EQH_STAMP(7);
     float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
     const int64_t ld = final_out ? p.ldd : p.N;
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool has_res = final_out && p.residual != nullptr;
-    constexpr int CPL = BN / 32;                         // columns per lane (4 for BN=128: one float4; 2 for BN=64)
-    const int c = lane * CPL;
+    // a warp instruction covers 128 / BN rows of the tile as float4s; four such groups in flight per warp
+    constexpr int LPR = BN / 4;                          // lanes per row
+    constexpr int RPI = 32 / LPR;                        // rows per warp instruction
+    const int c = (lane % LPR) * 4, rsub = lane / LPR;
     const int n = n0 + c;
-    const bool full_vec = vec_ok && (n + CPL <= p.N) && CPL == 4;
+    const bool full_vec = vec_ok && (n + 4 <= p.N);
     const int rows_here = min(BM, p.M - m0);
-    for (int r = q; r < rows_here; r += 4) {             // one warp per row, lanes across the BN columns
-      const float* src = stage_out + r * PITCH + c;
-      float* dst = out + (int64_t)(m0 + r) * ld + n;
+    for (int rb = q * RPI; rb < rows_here; rb += 16 * RPI) {
       if (full_vec) {
-        float4 x = *reinterpret_cast<const float4*>(src);
-        if (has_res) {   // plain (coherent) load: the residual may be D itself
-          const float4 rr = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
-          x.x += p.res_scale * rr.x; x.y += p.res_scale * rr.y; x.z += p.res_scale * rr.z; x.w += p.res_scale * rr.w;
+        float4 x[4], rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r < rows_here) {
+            x[u] = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
+            // plain (coherent) load: the residual may be D itself
+            if (has_res) rr[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
+          }
         }
-        *reinterpret_cast<float4*>(dst) = x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r < rows_here) {
+            if (has_res) {
+              x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
+              x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
+            }
+            *reinterpret_cast<float4*>(out + (int64_t)(m0 + r) * ld + n) = x[u];
+          }
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          if (n + j < p.N) {
-            float x = src[j];
-            if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
-            dst[j] = x;
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r >= rows_here) continue;
+          const float* src = stage_out + r * PITCH + c;
+          float* dst = out + (int64_t)(m0 + r) * ld + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < p.N) {
+              float x = src[j];
+              if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
+              dst[j] = x;
+            }
           }
         }
       }
     }
   }
+  if (threadIdx.x == 128) EQH_STAMP(8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (p.ws != nullptr) __threadfence();       // this split's partial tile is visible device-wide before the arrival
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (p.ws != nullptr) {
+    // ---- split-K finish: the CTA that arrives last at this tile's counter adds the partials in split order
+    // (the order never depends on which CTA is last: deterministic) and applies the output transform
+    if (threadIdx.x == 0) {
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      const int prev = atomicAdd(p.counters + tile, 1);
+      s_last = (prev == (int)gridDim.z - 1);
+      if (s_last) p.counters[tile] = 0;         // left zero for the next launch
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int64_t MN = (int64_t)p.M * p.N;
+      const int rows_here = min(BM, p.M - m0);
+      const int nz = (int)gridDim.z;
+      const bool vec = ((p.N & 3) == 0) && ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
+                       (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      if (vec) {
+        constexpr int C4 = BN / 4;
+        for (int e = threadIdx.x; e < rows_here * C4; e += kThreads) {
+          const int r = e / C4, c = (e - r * C4) * 4;
+          if (n0 + c >= p.N) continue;
+          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+          for (int z = 0; z < nz; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * MN));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
+          float4 x = make_float4(p.out_scale * acc.x, p.out_scale * acc.y, p.out_scale * acc.z, p.out_scale * acc.w);
+          if (p.residual) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + o);
+            x.x += p.res_scale * rr.x; x.y += p.res_scale * rr.y; x.z += p.res_scale * rr.z; x.w += p.res_scale * rr.w;
+          }
+          *reinterpret_cast<float4*>(p.D + o) = x;
+        }
+      } else {
+        for (int e = threadIdx.x; e < rows_here * BN; e += kThreads) {
+          const int r = e / BN, c = e - r * BN;
+          if (n0 + c >= p.N) continue;
+          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int z = 0; z < nz; ++z) acc += __ldcg(src + (int64_t)z * MN);
+          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
+          float x = p.out_scale * acc;
+          if (p.residual) x += p.res_scale * p.residual[o];
+          p.D[o] = x;
+        }
+      }
+    }
+  }
 #undef tmem_full
 #undef tmem_slot
-}
-
-// Split-K finish: D[m,n] = out_scale * sum_z ws[z,m,n] + res_scale * R[m,n], partials added in split order
-// (deterministic); R may alias D.
-__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ ws, int splits, int M, int N, float* D,
-                                                        int64_t ldd, const float* R, float out_scale, float res_scale) {
-  const int64_t total = (int64_t)M * N;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += __ldg(ws + (int64_t)z * total + i);
-    const int64_t m = i / N, n = i - m * N;
-    float x = out_scale * acc;
-    if (R) x += res_scale * R[m * ldd + n];
-    D[m * ldd + n] = x;
-  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -335,22 +427,40 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
   return r == CUDA_SUCCESS ? EQH_OK : EQH_ERR_ARG;
 }
 
-template <int BN, bool AK, bool BK_>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, bool write_hi) {
+template <int BN, bool AK, bool BK_, bool WH, int STAGES, int MINB>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) + 128 + BN * 4;   // ring + barriers + bias tile
   static_assert((size_t)STAGES * (2 * kTileBytes + 2 * BN * BK * 4) >= (size_t)BM * (BN + 4) * 4,
                 "epilogue staging must fit in the operand ring");
-  cudaError_t e;
-  if (write_hi) {
-    e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    k_gemm<BN, AK, BK_, true><<<grid, kThreads, smem, st>>>(a, b, p);
-  } else {
-    e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    k_gemm<BN, AK, BK_, false><<<grid, kThreads, smem, st>>>(a, b, p);
-  }
+  static_assert(smem * MINB <= 227 * 1024, "shared memory budget");
+  cudaError_t e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, WH, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_gemm<BN, AK, BK_, WH, STAGES, MINB><<<grid, kThreads, smem, st>>>(a, b, p);
   EQH_LAUNCH_RC();
+}
+
+// Tile width and split count.  Cost model (clocks per CTA): a 32-deep K block costs ~300 (operand split of the
+// 128-row A tile) + 6.4*BN (12 MMAs); the split-K finish costs ~4*BN per split in the last CTA.
+static void plan(int64_t M, int64_t N, int64_t K, int splits_req, int bn_req, int* bn_out, int* splits_out) {
+  const int64_t tiles_m = (M + BM - 1) / BM, kb = (K + BK - 1) / BK;
+  double best = 1e300;
+  int best_bn = 128, best_s = 1;
+  for (int bn = 128; bn >= 32; bn >>= 1) {
+    if (bn_req && bn != bn_req) continue;
+    if (!bn_req && bn > 32 && bn / 2 >= N) continue;               // do not pad N by more than 2x
+    const int64_t t = tiles_m * ((N + bn - 1) / bn);
+    const int s_max = splits_req == 0 ? (int)(kb / 2 < 1 ? 1 : (kb / 2 > 32 ? 32 : kb / 2)) : splits_req;
+    for (int s = splits_req == 0 ? 1 : splits_req; s <= s_max; ++s) {
+      const int64_t kbps = (kb + s - 1) / s;
+      const int64_t s_eff = (kb + kbps - 1) / kbps;
+      const int64_t waves = (t * s_eff + kSMs - 1) / kSMs;
+      const double cost = (double)waves * ((double)kbps * (300.0 + 6.4 * bn) + 1500.0) + (s_eff > 1 ? 4.0 * bn * s_eff : 0.0);
+      if (cost < best - 1e-9) { best = cost; best_bn = bn; best_s = (int)s_eff; }
+    }
+  }
+  *bn_out = best_bn;
+  *splits_out = best_s;
 }
 
 }  // namespace gemm
@@ -358,22 +468,45 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
 
 extern "C" {
 
+#ifdef EQH_TRACE
+EQH_API int eqh_debug_gemm_trace(unsigned long long* host16) {
+  return (int)cudaMemcpyFromSymbol(host16, eqh::gemm::g_trace, sizeof(unsigned long long) * 16);
+}
+#endif
+
+int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits, int flags, int* bn, int* splits_out, int64_t* tiles) {
+  using namespace eqh;
+  EQH_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits >= 0 && bn && splits_out && tiles);
+  const int code = (flags >> 9) & 3;
+  gemm::plan(M, N, K, splits, (flags & 0x100) ? 128 : (code ? (16 << code) : 0), bn, splits_out);
+  *tiles = ((M + gemm::BM - 1) / gemm::BM) * ((N + *bn - 1) / *bn);
+  return EQH_OK;
+}
+
 size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
   return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)M * (size_t)N : 0;
 }
 
 int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
                     int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act_flags,
-                    const float* residual, float out_scale, float res_scale, int splits, float* ws, eqh_stream_t stream) {
+                    const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                    eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::gemm;
   const int act = act_flags & 0xff;
   EQH_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0 && splits >= 1 && act >= 0 && act <= 2);
   EQH_CHECK_ARG(M < (1 << 30) && N < (1 << 30) && K < (1 << 30));
   EQH_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0);   // TMA: 16-byte rows
-  EQH_CHECK_ARG(splits == 1 || (ws && !bias && act == 0));
+  EQH_CHECK_ARG(splits == 1 || (ws && counters && !bias && act == 0));
   EQH_CHECK_ARG(ldd >= N);
-  const int BN = N <= 64 ? 64 : 128;
+  const int bn_code = (act_flags >> 9) & 3;             // 0 auto, 1..3 = 32 / 64 / 128 (tuning / tests)
+  const bool write_hi = (act_flags & 0x100) != 0;       // debug/verification switch, see kWriteHi
+  const bool pair = (act_flags & 0x800) != 0;           // two co-resident CTAs per SM (BN <= 64, 2-stage ring)
+  int BN, s_plan;
+  plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
+  const int kb_total = (int)((K + BK - 1) / BK);
+  const int kbps = (kb_total + splits - 1) / splits;
+  EQH_CHECK_ARG((kb_total + kbps - 1) / kbps == splits);          // every split owns at least one K block
   CUtensorMap tmA, tmB;
   int rc;
   // A: logical [M,K].  K-major: stored [M, lda] -> box {32 K, 128 M}.  MN-major: stored [K, lda] -> box {32 M, 32 K}.
@@ -386,31 +519,32 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   if (rc) return rc;
   Params p;
   p.D = D; p.bias = bias; p.rowscale = rowscale; p.residual = residual; p.ws = splits > 1 ? ws : nullptr; p.ldd = ldd;
+  p.counters = counters; p.splits = splits;
   p.out_scale = out_scale; p.res_scale = res_scale;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.act = act;
-  const int kb_total = (int)((K + BK - 1) / BK);
-  p.kb_per_split = (kb_total + splits - 1) / splits;
+  p.kb_per_split = kbps;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool write_hi = (act_flags & 0x100) != 0;   // debug/verification switch, see kWriteHi
-  auto dispatch = [&]() -> int {
-#define EQH_GEMM_CASE(BNV)                                                        \
-  if (a_kmajor && b_kmajor) return launch<BNV, true, true>(tmA, tmB, p, grid, st, write_hi); \
-  if (a_kmajor && !b_kmajor) return launch<BNV, true, false>(tmA, tmB, p, grid, st, write_hi); \
-  if (!a_kmajor && !b_kmajor) return launch<BNV, false, false>(tmA, tmB, p, grid, st, write_hi); \
-  return launch<BNV, false, true>(tmA, tmB, p, grid, st, write_hi);
-    if (BN == 64) { EQH_GEMM_CASE(64) }
-    EQH_GEMM_CASE(128)
-  };
-  rc = dispatch();
-  if (rc || splits == 1) return rc;
-  {
-    int64_t blocks = (M * N + 255) / 256;
-    if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
-    k_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>(ws, splits, (int)M, (int)N, D, ldd, residual, out_scale, res_scale);
+#define EQH_GEMM_MAJORS(BNV, WHV, STG, MB)                                                            \
+  do {                                                                                                \
+    if (a_kmajor && b_kmajor) return launch<BNV, true, true, WHV, STG, MB>(tmA, tmB, p, grid, st);    \
+    if (a_kmajor && !b_kmajor) return launch<BNV, true, false, WHV, STG, MB>(tmA, tmB, p, grid, st);  \
+    if (!a_kmajor && !b_kmajor) return launch<BNV, false, false, WHV, STG, MB>(tmA, tmB, p, grid, st);\
+    return launch<BNV, false, true, WHV, STG, MB>(tmA, tmB, p, grid, st);                             \
+  } while (0)
+  if (write_hi) {
+    if (BN != 128) return EQH_ERR_UNSUPPORTED;
+    EQH_GEMM_MAJORS(128, true, 3, 1);
   }
-  EQH_LAUNCH_RC();
-#undef EQH_GEMM_CASE
+  if (pair) {
+    if (BN == 32) EQH_GEMM_MAJORS(32, false, 2, 2);
+    if (BN == 64) EQH_GEMM_MAJORS(64, false, 2, 2);
+    return EQH_ERR_UNSUPPORTED;
+  }
+  if (BN == 32) EQH_GEMM_MAJORS(32, false, 4, 1);
+  if (BN == 64) EQH_GEMM_MAJORS(64, false, 4, 1);
+  EQH_GEMM_MAJORS(128, false, 3, 1);
+#undef EQH_GEMM_MAJORS
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 from .. import ops
-from ..ops import MEAN, SUM, _MODES, _call, _p, _stream, colsum_raw, colsum_tall, gather_reduce_raw, gemm_raw, partial_rows
+from ..ops import MEAN, SUM, _MODES, _call, _p, _stream, gather_reduce_raw, gemm_raw, partial_rows
 
 
 def _rowln_fwd(x, g, b, eps):
@@ -45,6 +45,7 @@ class _GradSink:
             else:
                 self.out[id(p)] = None
         self.params = params
+        self.batch = ops.ColsumBatch(params[0].device)
 
     def weight(self, p, dy, x, cols=None):
         """p.grad[:, cols] (+)= dy^T x   (dy [M, out], x [M, in])"""
@@ -61,20 +62,26 @@ class _GradSink:
                  residual=view if acc else None)
 
     def bias(self, p, dy, roww=None):
+        """p.grad (+)= sum_r roww[r] * dy[r, :]  (queued; finished by flush())"""
         tgt = self.out[id(p)]
         if tgt is None:
-            self.out[id(p)] = colsum_tall(dy, roww)
+            tgt = self.out[id(p)] = torch.empty_like(p)
+            self.batch.add(dy, tgt, roww)
         else:
-            colsum_tall(dy, roww, out=tgt, accumulate=True)
+            self.batch.add(dy, tgt, roww, accumulate=True)
 
     def affine(self, g, b, part):
         C = g.shape[0]
         for p, c0 in ((g, 0), (b, C)):
             tgt = self.out[id(p)]
             if tgt is None:
-                self.out[id(p)] = colsum_raw(part, c0, C)
+                tgt = self.out[id(p)] = torch.empty_like(p)
+                self.batch.add(part, tgt, col0=c0, cols=C)
             else:
-                colsum_raw(part, c0, C, out=tgt, accumulate=True)
+                self.batch.add(part, tgt, col0=c0, cols=C, accumulate=True)
+
+    def flush(self):
+        self.batch.run()
 
     def results(self):
         return tuple(None if self.direct else self.out[id(p)] for p in self.params)
@@ -163,4 +170,5 @@ class MHNNSConvFused(torch.autograd.Function):
         gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX)          # dX += dh1 . W1_0 (in-place epilogue)
         sink.weight(w10, dh1, X)
         sink.bias(b10, dh1)
+        sink.flush()      # all bias / LayerNorm-affine gradients of the layer: one launch
         return (dX, dX0, None, None, None, None, None) + sink.results()

@@ -226,6 +226,59 @@ def colsum_raw(partial: torch.Tensor, col0: int = 0, cols: Optional[int] = None,
     return out
 
 
+_COUNTERS = {}
+_COUNTER_SLOTS = 1 << 20
+
+
+def counters(n: int, device) -> torch.Tensor:
+    """n zeroed int32 slots for the kernels that finish a reduction in their last-arriving block (they reset
+    the slots themselves).  Slices of one persistent per-device buffer handed out round-robin, so launches that
+    may overlap (side streams, parallel graph branches) never share a slot."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _COUNTERS.get(key)
+    if st is None:
+        st = _COUNTERS[key] = [torch.zeros(_COUNTER_SLOTS, dtype=torch.int32, device=device), 0]
+    buf, off = st
+    if n > _COUNTER_SLOTS:
+        raise RuntimeError("counters: request too large")
+    if off + n > _COUNTER_SLOTS:
+        off = 0
+    st[1] = off + n
+    return buf[off:off + n]
+
+
+class ColsumBatch:
+    """Collects column-sum jobs (bias gradients, per-CTA partial buffers) and finishes them in one launch."""
+
+    def __init__(self, device):
+        self.device = device
+        self.jobs = []
+        self.keep = []
+
+    def add(self, x: torch.Tensor, out: torch.Tensor, roww: Optional[torch.Tensor] = None, accumulate: bool = False,
+            scale: float = 1.0, col0: int = 0, cols: Optional[int] = None) -> None:
+        """out (+)= scale * sum_r roww[r] * x[r, col0:col0+cols]"""
+        rows, width = x.shape
+        cols = width - col0 if cols is None else cols
+        if out.numel() != cols or not out.is_contiguous() or x.stride(1) != 1:
+            raise RuntimeError("ColsumBatch.add: bad shapes")
+        self.jobs.append(_lib.ColsumJob(x.data_ptr() + 4 * col0, _p(roww), out.data_ptr(), rows, cols, x.stride(0),
+                                        scale, int(accumulate)))
+        self.keep += [x, out, roww]
+
+    def run(self) -> None:
+        lib = _lib.load()
+        for i in range(0, len(self.jobs), _lib.COLSUM_MAX_JOBS):
+            chunk = self.jobs[i:i + _lib.COLSUM_MAX_JOBS]
+            arr = (_lib.ColsumJob * len(chunk))(*chunk)
+            nb = lib.eqh_colsum_batch_workspace_bytes(arr, len(chunk))
+            nc = lib.eqh_colsum_batch_counters(arr, len(chunk))
+            ws = torch.empty(max(nb // 4, 1), dtype=torch.float32, device=self.device)
+            cnt = counters(int(nc), self.device)
+            _call("eqh_colsum_batch", 1, arr, len(chunk), _p(ws), _p(cnt), _stream())
+        self.jobs, self.keep = [], []
+
+
 # ----------------------------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------------------------
@@ -411,22 +464,41 @@ _ACT = {None: 0, "none": 0, "relu": 1, "silu": 2}
 SM_COUNT = 148
 
 
+GEMM_FLAGS = int(os.environ.get("EQH_GEMM_FLAGS", "0"), 0)     # tuning: forced tile width / co-resident CTAs
+
+
+def gemm_plan(M: int, N: int, K: int, splits: int = 1, flags: int = 0):
+    """(tile width, effective splits, output tiles) the kernel will use; splits 1 = none, 0 = choose."""
+    import ctypes
+    bn, s, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    _lib.check(_lib.load().eqh_gemm_plan(M, N, K, splits, flags, ctypes.byref(bn), ctypes.byref(s), ctypes.byref(t)),
+               "eqh_gemm_plan")
+    return bn.value, s.value, t.value
+
+
 def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
              splits: int = 1, write_hi: bool = False, rowscale=None, out: Optional[torch.Tensor] = None,
-             out_scale: float = 1.0, res_scale: float = 1.0) -> torch.Tensor:
+             out_scale: float = 1.0, res_scale: float = 1.0, flags: Optional[int] = None) -> torch.Tensor:
     """D = out_scale * act(A.B^T + bias * rowscale) + res_scale * residual with A logical [M,K], B logical [N,K]; an
     operand flagged k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3).  `out` may be a row-strided
-    view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation)."""
+    view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation).
+    splits: 1 = no split-K, 0 = let the kernel's planner choose (weight gradients), >1 = at most that many."""
     dev = A.device
     D = torch.empty((M, N), dtype=torch.float32, device=dev) if out is None else out
     ldd = D.stride(0)
     if residual is not None and residual.stride(0) != ldd:
         raise RuntimeError("gemm_raw: residual must have the row stride of the output")
-    ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev) if splits > 1 else None
+    fl = (GEMM_FLAGS if flags is None else flags) | _ACT[act] | (0x100 if write_hi else 0)
+    ws = cnt = None
+    if splits != 1:
+        _, splits, tiles = gemm_plan(M, N, K, splits, fl)
+        if splits > 1:
+            ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
+            cnt = counters(tiles, dev)
     flops = 2.0 * M * N * K
-    _call("eqh_gemm_tf32x3", 2 if splits > 1 else 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
-          _p(D), ldd, M, N, K, _p(bias), _p(rowscale), _ACT[act] | (0x100 if write_hi else 0), _p(residual), out_scale,
-          res_scale, splits, _p(ws), _stream(), nbytes=flops)
+    _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
+          _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
+          _stream(), nbytes=flops)
     return D
 
 
@@ -440,9 +512,8 @@ def _as_gemm_operand(t: torch.Tensor) -> torch.Tensor:
 
 
 def _wgrad_splits(out_rows: int, out_cols: int, red: int) -> int:
-    tiles = ((out_rows + 127) // 128) * ((out_cols + 127) // 128)
-    kb = (red + 31) // 32
-    return max(1, min(SM_COUNT // max(tiles, 1), kb // 2, 64))
+    """Weight gradients reduce over the rows: split-K chosen by the kernel's planner."""
+    return 0
 
 
 class _Linear(torch.autograd.Function):

@@ -134,6 +134,26 @@ EQH_API int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, int64_t 
 EQH_API int eqh_colsum(const float* partial, int64_t rows, int64_t cols, int64_t ld, float* out, float scale, int accumulate,
                eqh_stream_t stream);
 
+/* Batched form: every bias gradient and per-CTA partial buffer of one layer's backward in ONE launch.
+ *     out_j[c] (+)= scale_j * sum_r roww_j[r] * x_j[r*ld_j + c]      (roww_j optional)
+ * Row chunks are reduced by separate blocks into ws; the block arriving last at a column tile's counter adds the
+ * chunk partials in ascending chunk order (deterministic) and resets the counter: `counters`
+ * (eqh_colsum_batch_counters() int32) must be zero on first use and is left zero.  Two launches may share
+ * counters / ws only if they are ordered on one stream. */
+#define EQH_COLSUM_MAX_JOBS 32
+typedef struct eqh_colsum_job {
+  const float* x;      /* [rows, ld] row-major */
+  const float* roww;   /* optional [rows] */
+  float* out;          /* [cols] */
+  int64_t rows, cols, ld;
+  float scale;
+  int32_t accumulate;  /* 0: out = ..., 1: out += ... */
+} eqh_colsum_job;
+EQH_API size_t eqh_colsum_batch_workspace_bytes(const eqh_colsum_job* jobs, int n_jobs);
+EQH_API int64_t eqh_colsum_batch_counters(const eqh_colsum_job* jobs, int n_jobs);
+EQH_API int eqh_colsum_batch(const eqh_colsum_job* jobs /* host array */, int n_jobs, float* ws, int32_t* counters,
+                     eqh_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batch-wide 16-nearest-neighbour search on squared distance.
  * Replaces egnn_layer.py:253-259,281-283: the [1,N,N,3] rel_coors, [1,N,N] ranking and topk(16,
@@ -194,20 +214,28 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
  *     D[M,N] = act( A . B^T + bias ) + residual          A logical [M,K], B logical [N,K]
  * Replaces the cuBLAS SIMT sgemm calls behind nn.Linear in mlp.py:91-99, egnn_layer.py:180-208 and
  * the P/Q GEMMs of the phi_e split, forward (A, B K-major), dX = dY.W (B MN-major) and
- * dW = dY^T.X (both MN-major; split-K over the rows, finished by eqh_colsum).
+ * dW = dY^T.X (both MN-major; split-K over the rows).
  *   a_kmajor / b_kmajor: 1 = stored row-major [rows, K] (K contiguous), 0 = stored [K, rows].
  *   lda / ldb: row stride of the STORED matrix in floats (multiple of 4, base 16-byte aligned).
  *   Full epilogue: D = out_scale * act(A.B^T + bias[n] * rowscale[m]) + res_scale * residual
  *   D row-major [M, ldd]; bias [N], rowscale [M], residual [M, ldd] optional (residual may alias D: in-place
  *   accumulation); act: 0 none, 1 ReLU, 2 SiLU.
  *   splits > 1 (split-K over the reduction, bias/act must be null/0): partials go to ws [splits, M, N]
- *   (eqh_gemm_workspace_bytes) and a second launch adds them in split order (deterministic) into D.
+ *   (eqh_gemm_workspace_bytes); the CTA arriving last at an output tile's counter adds them in split order
+ *   (deterministic) and applies out_scale / residual.  `counters`: one zeroed int32 per output tile (count from
+ *   eqh_gemm_plan), left zero.  `splits` must be a value returned by eqh_gemm_plan.
+ *   eqh_gemm_plan(M,N,K, splits_req, flags): splits_req 1 = no split, 0 = choose, >1 = at most that many;
+ *   returns the tile width the kernel will use, the effective split count and the number of output tiles.
+ *   act flags: bits 0-7 activation; 0x100 store the masked hi part (verification); bits 9-10 force the tile
+ *   width (1/2/3 = 32/64/128); 0x800 two co-resident CTAs per SM (tile width <= 64).
  * Ragged M / N / K are handled (TMA zero fill, bounds-checked stores).
  * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits_req, int flags, int* bn, int* splits, int64_t* tiles);
 EQH_API size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits);
 EQH_API int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
                     int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
-                    const float* residual, float out_scale, float res_scale, int splits, float* ws, eqh_stream_t stream);
+                    const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                    eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flat fused Adam step over one contiguous fp32 parameter buffer (main.py:137-140:

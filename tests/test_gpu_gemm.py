@@ -41,8 +41,41 @@ def test_gemm_dgrad_layout(M, N, K):
     assert rel_err(D, ref) < 2e-6
 
 
+@pytest.mark.parametrize("flags", [1 << 9, 2 << 9, 3 << 9, (1 << 9) | 0x800, (2 << 9) | 0x800])
+@pytest.mark.parametrize("M,N,K", [(2341, 256, 256), (300, 72, 272), (129, 1088, 64)])
+def test_gemm_every_tile_width(M, N, K, flags):
+    """Forced tile widths 32 / 64 / 128 and the two-CTAs-per-SM variant give the same result as the planner's choice
+    (bit-identical: the K order per output element does not depend on the tile width)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, bias, W = _mk((M, K), g), _mk((N, K), g), _mk((N,), g), _mk((K, N), g)
+    ref = torch.relu(A.double() @ B.double().t() + bias.double())
+    D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu", flags=flags)
+    assert rel_err(D, ref) < 2e-6
+    assert torch.equal(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu"))
+    D = ops.gemm_raw(A, True, W, False, M, N, K, flags=flags)                   # MN-major B (dgrad layout)
+    assert rel_err(D, A.double() @ W.double()) < 2e-6
+    X = _mk((M, N), g)
+    D = ops.gemm_raw(A, False, X, False, K, N, M, splits=0, flags=flags)        # wgrad layout, planner-chosen split-K
+    assert rel_err(D, A.double().t() @ X.double()) < 5e-6
+
+
+def test_gemm_splitk_epilogue_in_place_and_strided():
+    """Split-K finish in the last-arriving CTA: out_scale, accumulation into a strided view of a wider matrix."""
+    g = torch.Generator().manual_seed(11)
+    R, N, K = 3000, 256, 256
+    dY, X = _mk((R, N), g), _mk((R, K), g)
+    W = _mk((N, 2 * K), g)
+    ref = W.double().clone()
+    ref[:, K:] = 0.5 * ref[:, K:] + 2.0 * (dY.double().t() @ X.double())
+    view = W[:, K:]
+    ops.gemm_raw(dY, False, X, False, N, K, R, splits=0, out=view, residual=view, out_scale=2.0, res_scale=0.5)
+    assert rel_err(W, ref) < 5e-6
+    assert ops.gemm_plan(N, K, R, 0)[1] > 1
+
+
 @pytest.mark.parametrize("R,N,K,splits", [(2560, 256, 256, 1), (2560, 256, 256, 20), (2341, 1088, 256, 4),
-                                          (5000, 512, 272, 9), (100, 64, 128, 2), (2560, 256, 256, 64)])
+                                          (5000, 512, 272, 9), (100, 64, 128, 2), (2560, 256, 256, 64), (2560, 256, 256, 0),
+                                          (30000, 256, 272, 0), (40, 1088, 256, 0)])
 def test_gemm_wgrad_layout_and_splitk(R, N, K, splits):
     """dW[N,K] = dY[R,N]^T . X[R,K]: both operands stored [reduction, out] = MN-major; split-K over R."""
     g = torch.Generator().manual_seed(R + N + K + splits)
@@ -83,7 +116,7 @@ def test_tensor_core_truncates_tf32_inputs():
     bits; if the hardware rounded instead, the two results would differ at the 1e-4 level."""
     g = torch.Generator().manual_seed(99)
     A, B = _mk((1000, 512), g), _mk((384, 512), g)
-    D0 = ops.gemm_raw(A, True, B, True, 1000, 384, 512)
+    D0 = ops.gemm_raw(A, True, B, True, 1000, 384, 512, flags=3 << 9)      # same 128-wide tiles as the write_hi variant
     D1 = ops.gemm_raw(A, True, B, True, 1000, 384, 512, write_hi=True)
     assert torch.equal(D0, D1)
     assert rel_err(D0, A.double() @ B.double().t()) < 2e-6

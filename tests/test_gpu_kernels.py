@@ -327,3 +327,36 @@ def test_colsum_tall(rows, cols):
     out = ops.colsum_tall(x.to(DEV))
     assert rel_err(out, x.double().sum(0)) < 2e-6
     assert torch.equal(out, ops.colsum_tall(x.to(DEV)))
+
+
+def test_colsum_batch_many_jobs_one_launch():
+    """Bias / partial-buffer column sums of a whole layer in one launch: row-weighted, accumulating, strided and
+    sub-range jobs of different heights; deterministic (last-arriving block adds the chunks in fixed order)."""
+    g = torch.Generator().manual_seed(7)
+    shapes = [(1, 64), (64, 256), (65, 256), (2560, 256), (30000, 96), (5000, 17), (296, 512), (20000, 33)]
+    xs = [torch.randn(r, c, generator=g) for r, c in shapes]
+    ww = [torch.rand(r, generator=g) if i % 3 == 1 else None for i, (r, c) in enumerate(shapes)]
+    init = [torch.randn(c, generator=g) for r, c in shapes]
+
+    def run():
+        outs = [t.clone().to(DEV) for t in init]
+        batch = ops.ColsumBatch(DEV)
+        for i, x in enumerate(xs):
+            batch.add(x.to(DEV), outs[i], None if ww[i] is None else ww[i].to(DEV), accumulate=(i % 2 == 0),
+                      scale=1.0 if i != 3 else 0.5)
+        part = xs[6].to(DEV)
+        sub = torch.empty(256, device=DEV)
+        batch.add(part, sub, col0=256, cols=256)          # second half of a [296, 2C] partial buffer
+        before = ops.STATS["launches"]
+        batch.run()
+        assert ops.STATS["launches"] - before == 1
+        return outs, sub
+
+    outs, sub = run()
+    for i, x in enumerate(xs):
+        xd = x.double() if ww[i] is None else x.double() * ww[i].double()[:, None]
+        ref = (0.5 if i == 3 else 1.0) * xd.sum(0) + (init[i].double() if i % 2 == 0 else 0)
+        assert rel_err(outs[i], ref) < 2e-6, i
+    assert rel_err(sub, xs[6][:, 256:].double().sum(0)) < 2e-6
+    outs2, sub2 = run()
+    assert all(torch.equal(a, b) for a, b in zip(outs, outs2)) and torch.equal(sub, sub2)
