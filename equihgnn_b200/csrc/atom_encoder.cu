@@ -20,6 +20,7 @@ struct FeatMeta { int32_t rows[kMaxFeat]; int32_t off[kMaxFeat]; };   // rows pe
 template <int V>
 __global__ void __launch_bounds__(256) k_atom_fwd(const int64_t* __restrict__ x, TablePtrs tabs, FeatMeta meta, int F,
                                                    int64_t N, float* __restrict__ out, int32_t* __restrict__ status) {
+  pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) k_atom_fwd(const int64_t* __restrict__ x,
 __global__ void __launch_bounds__(32) k_atom_bwd(const int64_t* __restrict__ x, const float* __restrict__ dh, FeatMeta meta,
                                                   int F, int64_t N, int C, int64_t slice, int total_rows,
                                                   float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float acc[];   // [rows_f][32]
   const int lane = threadIdx.x;
   const int f = blockIdx.z, cb = blockIdx.y;
@@ -108,7 +110,7 @@ int eqh_atom_encoder_fwd(const int64_t* x, const float* const* tables, const int
   int64_t blocks = (N + 7) / 8;
   if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  EQH_DISPATCH_V(C, { k_atom_fwd<V><<<(unsigned)blocks, 256, 0, st>>>(x, tp, meta, F, N, out, status); });
+  EQH_DISPATCH_V(C, { launch_kernel(k_atom_fwd<V>, dim3((unsigned)blocks), dim3(256), 0, st, x, tp, meta, F, N, out, status); });
   EQH_LAUNCH_RC();
 }
 
@@ -131,7 +133,7 @@ int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_t* rows_
   const int S = eqh_atom_encoder_slices(N);
   const int64_t slice = (N + S - 1) / S > 0 ? (N + S - 1) / S : 1;
   dim3 grid((unsigned)S, (unsigned)(C / 32), (unsigned)F);
-  k_atom_bwd<<<grid, 32, smem, static_cast<cudaStream_t>(stream)>>>(x, dh, meta, F, N, (int)C, slice, off, partial);
+  launch_kernel(k_atom_bwd, dim3(grid), dim3(32), smem, static_cast<cudaStream_t>(stream), x, dh, meta, F, N, (int)C, slice, off, partial);
   EQH_LAUNCH_RC();
 }
 

@@ -31,6 +31,7 @@ static inline int64_t chunks_for(int64_t rows) {
 
 __global__ void __launch_bounds__(256) k_colsum_batch(const __grid_constant__ JobPack p, float* __restrict__ ws,
                                                        int32_t* __restrict__ counters) {
+  pdl_prologue();
   __shared__ float sm[8][32];
   __shared__ int s_last;
   int j = 0;
@@ -132,7 +133,7 @@ int eqh_colsum_batch(const eqh_colsum_job* jobs, int n_jobs, float* ws, int32_t*
   if (n == 0) return EQH_OK;
   p.block0[n] = (int32_t)blocks;
   p.n = n;
-  k_colsum_batch<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, ws, counters);
+  launch_kernel(k_colsum_batch, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), p, ws, counters);
   EQH_LAUNCH_RC();
 }
 

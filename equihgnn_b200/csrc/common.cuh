@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "eqh_b200.h"
 
@@ -25,6 +26,47 @@ constexpr unsigned kFull = 0xffffffffu;
     cudaError_t e__ = cudaGetLastError();                \
     return e__ == cudaSuccess ? EQH_OK : (int)e__;       \
   } while (0)
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// The step is ~150 small kernels back to back: the launch latency and the prologue of kernel N+1 are overlapped with
+// the tail of kernel N.  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_prologue(): it first lets ITS dependents be scheduled (their CTAs then park in
+// their own griddepcontrol.wait) and then waits until the grid it depends on has completed and flushed its
+// memory.  Nothing touches global memory before the wait, so ordering is exactly that of a plain stream; the
+// instructions are no-ops when a kernel is launched without the attribute (EQH_PDL=0, or a foreign predecessor).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+#ifndef __CUDA_ARCH__
+static inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("EQH_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+#ifndef __CUDA_ARCH__
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+#endif
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through cudaGetLastError()
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

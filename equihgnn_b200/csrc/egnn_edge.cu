@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(const float* __restrict__ P, c
                                                    const float* __restrict__ b2, const int32_t* __restrict__ idx,
                                                    const float* __restrict__ d2, int64_t N, int H,
                                                    float* __restrict__ S2, float* __restrict__ Mij, float* __restrict__ Mi) {
+  pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   float* w2t = smem;                 // [H][kPitch]
   float* wcs = smem + (size_t)H * kPitch;  // [H]
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(384) k_edge_bwd(const float* __restrict__ P, c
                                                    const float* __restrict__ dMij, int64_t N, int H,
                                                    float* __restrict__ dP, float* __restrict__ dPre,
                                                    float* __restrict__ dd2, float* __restrict__ part) {
+  pdl_prologue();
   __shared__ __align__(16) float ds2s[kNbr][kM];
   __shared__ float dd2s[12][kNbr];
   __shared__ int32_t js[kNbr];
@@ -272,7 +274,7 @@ int eqh_egnn_edge_fwd(const float* P, const float* Q, const float* wc, const flo
   int64_t blocks = (N + 7) / 8;
   const int64_t cap = smem > 110 * 1024 ? kSMs : 2 * kSMs;  // persistent: W2^T staging is amortised over many atoms
   if (blocks > cap) blocks = cap;
-  k_edge_fwd<<<(unsigned)blocks, 256, smem, st>>>(P, Q, wc, W2, b2, idx, d2, N, (int)H, S2, Mij, Mi);
+  launch_kernel(k_edge_fwd, dim3((unsigned)blocks), dim3(256), smem, st, P, Q, wc, W2, b2, idx, d2, N, (int)H, S2, Mij, Mi);
   EQH_LAUNCH_RC();
 }
 
@@ -290,7 +292,7 @@ int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, const flo
   T = (T + 31) / 32 * 32;
   const unsigned grid = kPartialRows;  // every CTA writes its partial row (zeros when it owns no atom)
 #define EQH_BWD(HCV)                                                                                              \
-  k_edge_bwd<HCV><<<grid, T, 0, st>>>(P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, dd2, part)
+  launch_kernel(k_edge_bwd<HCV>, dim3(grid), dim3(T), 0, st, P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, dd2, part)
   switch (HC) {
     case 1: EQH_BWD(1); break;
     case 2: EQH_BWD(2); break;

@@ -46,6 +46,7 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
               const float* __restrict__ W2, const float* __restrict__ b2, const int32_t* __restrict__ idx,
               const float* __restrict__ d2, int64_t N, int H, int64_t ldpq, float* __restrict__ S2,
               float* __restrict__ Mij, float* __restrict__ Mi) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kStageBytes);
   uint64_t* empty = full + STAGES;
@@ -256,7 +257,7 @@ extern "C" int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float*
   if (e != cudaSuccess) return (int)e;
   const int64_t tiles = (N * kNbr + BM - 1) / BM;
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
-  k_edge_fwd_tc<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(P, Q, wc, W2, b2, idx, d2, N, (int)H, H, S2,
+  launch_kernel(k_edge_fwd_tc, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), P, Q, wc, W2, b2, idx, d2, N, (int)H, H, S2,
                                                                            Mij, Mi);
   EQH_LAUNCH_RC();
 }

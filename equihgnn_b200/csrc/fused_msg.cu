@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256, 4) k_fused_fwd(const float* __restrict__ 
                                                        const int32_t* __restrict__ rowptr, int64_t n_out,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int mode, float* __restrict__ U) {
+  pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256, DGB ? 2 : 4) k_fused_bwd(
     const int32_t* __restrict__ ib, const int32_t* __restrict__ iu, const int32_t* __restrict__ rowptr, int64_t n_seg,
     const float* __restrict__ gamma, float eps, const float* __restrict__ dU, const int32_t* __restrict__ u_rowptr,
     float* __restrict__ dOp, float* __restrict__ dgb_partial) {
+  pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -207,6 +209,7 @@ template <int V, bool RELU>
 __global__ void __launch_bounds__(256) k_rowln_fwd(const float* __restrict__ x, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float eps, int64_t rows,
                                                     float* __restrict__ y) {
+  pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -233,6 +236,7 @@ template <int V, bool RELU>
 __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, float eps,
                                                     const float* __restrict__ dy, int64_t rows, float* __restrict__ dx,
                                                     float* __restrict__ dgb_partial) {
+  pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, 
 __global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
                                                         const float* __restrict__ roww, int64_t rows_per_chunk,
                                                         float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float sm[8][32];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int64_t c = blockIdx.x * 32 + cx;
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(256) k_colsum_chunks(const float* __restrict__
 // out[c] = sum_r partial[r,c], r ascending within each of 8 interleaved groups, groups combined in fixed order
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partial, int64_t rows, int64_t cols, int64_t ld,
                                                  float* out, float scale, int accumulate) {
+  pdl_prologue();
   __shared__ float sm[8][32];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int64_t c = blockIdx.x * 32 + cx;
@@ -345,7 +351,7 @@ int eqh_fused_msg_fwd(const float* A, const float* B, const int32_t* ia, const i
   if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
   const unsigned gb = (unsigned)blocks;
 #define EQH_FWD(LNV, GAV, GBV) \
-  k_fused_fwd<V, LNV, GAV, GBV><<<gb, 256, 0, st>>>(A, B, ia, ib, rowptr, n_out, gamma, beta, eps, mode, U)
+  launch_kernel(k_fused_fwd<V, LNV, GAV, GBV>, dim3(gb), dim3(256), 0, st, A, B, ia, ib, rowptr, n_out, gamma, beta, eps, mode, U)
   EQH_DISPATCH_V(C, {
     if (gamma) {
       if (ia && ib) EQH_FWD(true, true, true);
@@ -385,7 +391,7 @@ int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const i
   const unsigned grid = dgb_partial ? (unsigned)kPartialRows : (unsigned)blocks;   // partial rows: fixed, all written
   if (!dgb_partial && n_seg == 0) return EQH_OK;
 #define EQH_BWD(LNV, DGBV, GAV, GBV, GUV)                                                                       \
-  k_fused_bwd<V, LNV, DGBV, GAV, GBV, GUV><<<grid, 256, 0, st>>>(A, B, ia, ib, iu, rowptr, n_seg, gamma, eps, dU, \
+  launch_kernel(k_fused_bwd<V, LNV, DGBV, GAV, GBV, GUV>, dim3(grid), dim3(256), 0, st, A, B, ia, ib, iu, rowptr, n_seg, gamma, eps, dU, \
                                                                  u_rowptr, dOp, dgb_partial)
 #define EQH_BWD_G(LNV, DGBV)                                   \
   do {                                                         \
@@ -415,8 +421,8 @@ int eqh_rowln_fwd(const float* x, const float* gamma, const float* beta, float e
   if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EQH_DISPATCH_V(C, {
-    if (relu) k_rowln_fwd<V, true><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, eps, rows, y);
-    else k_rowln_fwd<V, false><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, eps, rows, y);
+    if (relu) launch_kernel(k_rowln_fwd<V, true>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y);
+    else launch_kernel(k_rowln_fwd<V, false>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y);
   });
   EQH_LAUNCH_RC();
 }
@@ -429,8 +435,8 @@ int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const
   if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EQH_DISPATCH_V(C, {
-    if (relu) k_rowln_bwd<V, true><<<kPartialRows, 256, 0, st>>>(x, gamma, eps, dy, rows, dx, dgb_partial);
-    else k_rowln_bwd<V, false><<<kPartialRows, 256, 0, st>>>(x, gamma, eps, dy, rows, dx, dgb_partial);
+    if (relu) launch_kernel(k_rowln_bwd<V, true>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial);
+    else launch_kernel(k_rowln_bwd<V, false>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial);
   });
   EQH_LAUNCH_RC();
 }
@@ -449,15 +455,15 @@ int eqh_colsum_tall(const float* x, int64_t rows, int64_t cols, int64_t ld, cons
   if (cols == 0) return EQH_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rows <= 64 && !roww) {
-    k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(x, rows, cols, ld, out, 1.f, accumulate);
+    launch_kernel(k_colsum, dim3((unsigned)((cols + 31) / 32)), dim3(256), 0, st, x, rows, cols, ld, out, 1.f, accumulate);
     EQH_LAUNCH_RC();
   }
   EQH_CHECK_ARG(ws != nullptr);
   const int64_t chunks = rows > 64 * 64 ? 64 : (rows + 63) / 64 > 0 ? (rows + 63) / 64 : 1;
   const int64_t rpc = (rows + chunks - 1) / chunks;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
-  k_colsum_chunks<<<grid, 256, 0, st>>>(x, rows, cols, ld, roww, rpc, ws);
-  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(ws, chunks, cols, cols, out, 1.f, accumulate);
+  launch_kernel(k_colsum_chunks, dim3(grid), dim3(256), 0, st, x, rows, cols, ld, roww, rpc, ws);
+  launch_kernel(k_colsum, dim3((unsigned)((cols + 31) / 32)), dim3(256), 0, st, ws, chunks, cols, cols, out, 1.f, accumulate);
   EQH_LAUNCH_RC();
 }
 
@@ -466,7 +472,7 @@ int eqh_colsum(const float* partial, int64_t rows, int64_t cols, int64_t ld, flo
   using namespace eqh;
   EQH_CHECK_ARG(rows >= 0 && cols >= 0 && ld >= cols && (cols == 0 || (partial && out)));
   if (cols == 0) return EQH_OK;
-  k_colsum<<<(unsigned)((cols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, cols, ld, out, scale,
+  launch_kernel(k_colsum, dim3((unsigned)((cols + 31) / 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), partial, rows, cols, ld, out, scale,
                                                                                       accumulate);
   EQH_LAUNCH_RC();
 }

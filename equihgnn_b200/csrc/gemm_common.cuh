@@ -1,0 +1,224 @@
+// Shared by the two tcgen05 3xTF32 GEMM kernels (gemm_tf32x3.cu: both operands from shared memory;
+// gemm_ts.cu: A operand through registers into tensor memory): parameters, the epilogue and the split-K finish.
+#pragma once
+#include "tc_common.cuh"
+
+namespace eqh {
+namespace gemm {
+using namespace eqh::tc;
+
+
+constexpr int BM = 128, BK = 32;
+
+#ifdef EQH_TRACE
+// phase timestamps (ns, globaltimer) of CTA (0,0,0) of the most recent launch: scratch/trace_gemm.py
+static __device__ unsigned long long g_trace[16];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define EQH_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[i] = gtime(); } while (0)
+#else
+#define EQH_STAMP(i) do { } while (0)
+#endif
+constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 operand split (warps 4-7 also epilogue)
+constexpr int kSplitThreads = 256;
+constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
+
+struct Params {
+  float* D;
+  const float* bias;
+  const float* rowscale;   // optional [M]: the bias is multiplied by rowscale[m] (empty-segment mask / segment count)
+  const float* residual;   // optional [M, ldd]; may alias D (in-place accumulation)
+  float out_scale, res_scale;
+  float* ws;          // split-K partials [splits, M, N] (ldd == N) or nullptr
+  int32_t* counters;  // split-K: one arrival counter per output tile (zero on entry, left zero)
+  int splits;
+  int64_t ldd;
+  int M, N, K;
+  int act;            // 0 none, 1 relu, 2 silu
+  int kb_per_split;   // K blocks of 32 per split
+};
+
+
+// Epilogue of one 128 x BN tile, executed by warps 4-7 (TMEM lane quadrant = warp & 3):
+// TMEM -> registers -> (bias, act, scales) -> padded smem (`smem`, the idle operand ring) -> coalesced stores
+// (+ residual).  Three accumulators of BN columns at tmem_base: hi.hi even / odd k-steps, small terms.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint32_t tmem_base, uint64_t* tmem_full, int warp,
+                                              int lane, int nkb, const Params& p, int m0, int n0) {
+    // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
+    constexpr int PITCH = BN + 4;
+    float* stage_out = reinterpret_cast<float*>(smem);   // the operand ring is idle once tmem_full fires
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may read (warps 4-7 -> 0-3)
+    const int row = q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (threadIdx.x == 128) EQH_STAMP(6);
+    const bool final_out = (p.ws == nullptr);
+    // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
+    {
+      const int tt = threadIdx.x - 128;
+      if (tt < BN) sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int act = final_out ? p.act : 0;
+    const float rs = (final_out && p.rowscale && m0 + row < p.M) ? __ldg(p.rowscale + m0 + row) : 1.f;
+    const float osc = final_out ? p.out_scale : 1.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (nkb > 0) {
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        float w[32], u[32];
+        const bool odd = nkb * (BK / 8) >= 2;                // the odd accumulator exists from the second k-step on
+        tmem_ld32_nowait(ta + 2 * BN, v);                    // small terms
+        tmem_ld32_nowait(ta, w);
+        if (odd) tmem_ld32_nowait(ta + BN, u);
+        tmem_ld_wait();
+        if (odd) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);   // warp-uniform address: broadcast
+        v[j] += b4.x * rs; v[j + 1] += b4.y * rs; v[j + 2] += b4.z * rs; v[j + 3] += b4.w * rs;
+      }
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) =
+            make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+    if (threadIdx.x == 128) EQH_STAMP(7);
+    float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
+    const int64_t ld = final_out ? p.ldd : p.N;
+    const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool has_res = final_out && p.residual != nullptr;
+    // a warp instruction covers 128 / BN rows of the tile as float4s; four such groups in flight per warp
+    constexpr int LPR = BN / 4;                          // lanes per row
+    constexpr int RPI = 32 / LPR;                        // rows per warp instruction
+    const int c = (lane % LPR) * 4, rsub = lane / LPR;
+    const int n = n0 + c;
+    const bool full_vec = vec_ok && (n + 4 <= p.N);
+    const int rows_here = min(BM, p.M - m0);
+    for (int rb = q * RPI; rb < rows_here; rb += 16 * RPI) {
+      if (full_vec) {
+        float4 x[4], rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r < rows_here) {
+            x[u] = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
+            // plain (coherent) load: the residual may be D itself
+            if (has_res) rr[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r < rows_here) {
+            if (has_res) {
+              x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
+              x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
+            }
+            *reinterpret_cast<float4*>(out + (int64_t)(m0 + r) * ld + n) = x[u];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + rsub + 4 * RPI * u;
+          if (r >= rows_here) continue;
+          const float* src = stage_out + r * PITCH + c;
+          float* dst = out + (int64_t)(m0 + r) * ld + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < p.N) {
+              float x = src[j];
+              if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
+              dst[j] = x;
+            }
+          }
+        }
+      }
+    }
+}
+
+// Split-K finish, executed by the whole CTA after its partial tile is written (includes the block barriers).
+template <int BN>
+__device__ __forceinline__ void splitk_finish(const Params& p, int m0, int n0, int* s_last) {
+  {
+    // ---- split-K finish: the CTA that arrives last at this tile's counter adds the partials in split order
+    // (the order never depends on which CTA is last: deterministic) and applies the output transform
+    if (threadIdx.x == 0) {
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      const int prev = atomicAdd(p.counters + tile, 1);
+      *s_last = (prev == (int)gridDim.z - 1);
+      if (*s_last) p.counters[tile] = 0;         // left zero for the next launch
+    }
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      const int64_t MN = (int64_t)p.M * p.N;
+      const int rows_here = min(BM, p.M - m0);
+      const int nz = (int)gridDim.z;
+      const bool vec = ((p.N & 3) == 0) && ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
+                       (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      if (vec) {
+        constexpr int C4 = BN / 4;
+        for (int e = threadIdx.x; e < rows_here * C4; e += kThreads) {
+          const int r = e / C4, c = (e - r * C4) * 4;
+          if (n0 + c >= p.N) continue;
+          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+          for (int z = 0; z < nz; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * MN));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
+          float4 x = make_float4(p.out_scale * acc.x, p.out_scale * acc.y, p.out_scale * acc.z, p.out_scale * acc.w);
+          if (p.residual) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.residual + o);
+            x.x += p.res_scale * rr.x; x.y += p.res_scale * rr.y; x.z += p.res_scale * rr.z; x.w += p.res_scale * rr.w;
+          }
+          *reinterpret_cast<float4*>(p.D + o) = x;
+        }
+      } else {
+        for (int e = threadIdx.x; e < rows_here * BN; e += kThreads) {
+          const int r = e / BN, c = e - r * BN;
+          if (n0 + c >= p.N) continue;
+          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int z = 0; z < nz; ++z) acc += __ldcg(src + (int64_t)z * MN);
+          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
+          float x = p.out_scale * acc;
+          if (p.residual) x += p.res_scale * p.residual[o];
+          p.D[o] = x;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace gemm
+}  // namespace eqh

@@ -20,44 +20,10 @@
 // per-split partials; the CTA arriving last at a tile's counter adds them in split order (deterministic)
 // and applies the output transform -- one launch.  The tile width (32/64/128) and the split count are
 // chosen per problem so that small GEMMs still occupy every SM (plan()).
-#include "tc_common.cuh"
+#include "gemm_common.cuh"
 
 namespace eqh {
 namespace gemm {
-using namespace eqh::tc;
-
-constexpr int BM = 128, BK = 32;
-
-#ifdef EQH_TRACE
-// phase timestamps (ns, globaltimer) of CTA (0,0,0) of the most recent launch: scratch/trace_gemm.py
-__device__ unsigned long long g_trace[16];
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define EQH_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[i] = gtime(); } while (0)
-#else
-#define EQH_STAMP(i) do { } while (0)
-#endif
-constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 operand split (warps 4-7 also epilogue)
-constexpr int kSplitThreads = 256;
-constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
-
-struct Params {
-  float* D;
-  const float* bias;
-  const float* rowscale;   // optional [M]: the bias is multiplied by rowscale[m] (empty-segment mask / segment count)
-  const float* residual;   // optional [M, ldd]; may alias D (in-place accumulation)
-  float out_scale, res_scale;
-  float* ws;          // split-K partials [splits, M, N] (ldd == N) or nullptr
-  int32_t* counters;  // split-K: one arrival counter per output tile (zero on entry, left zero)
-  int splits;
-  int64_t ldd;
-  int M, N, K;
-  int act;            // 0 none, 1 relu, 2 silu
-  int kb_per_split;   // K blocks of 32 per split
-};
 
 // kWriteHi: store the masked hi part back (true) or let the tensor core drop the low 13 bits of the raw fp32
 // tile itself (false; valid if the hardware truncates tf32 inputs -- checked by tests/test_gpu_gemm.py).
@@ -77,6 +43,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
 #define tmem_full (*tmem_full_p)
 #define tmem_slot (*tmem_slot_p)
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   if (threadIdx.x == 0) EQH_STAMP(0);
@@ -103,6 +70,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();        // everything above (barriers, tensor memory) overlapped the previous kernel's tail
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) EQH_STAMP(1);
 
@@ -219,178 +187,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
     }
   }
   if (warp >= 4 && warp < 8) {
-    // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
-    constexpr int PITCH = BN + 4;
-    float* stage_out = reinterpret_cast<float*>(smem);   // the operand ring is idle once tmem_full fires
-    const int q = warp & 3;                              // TMEM lane quadrant this warp may read (warps 4-7 -> 0-3)
-    const int row = q * 32 + lane;
-    if (nkb > 0) {
-      mbar_wait(&tmem_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    if (threadIdx.x == 128) EQH_STAMP(6);
-    const bool final_out = (p.ws == nullptr);
-    // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
     float* sbias = reinterpret_cast<float*>(smem + (size_t)STAGES * kStageBytes + 128);   // [BN] after the barriers
-    {
-      const int tt = threadIdx.x - 128;
-      if (tt < BN) sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int act = final_out ? p.act : 0;
-    const float rs = (final_out && p.rowscale && m0 + row < p.M) ? __ldg(p.rowscale + m0 + row) : 1.f;
-    const float osc = final_out ? p.out_scale : 1.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      if (nkb > 0) {
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        float w[32], u[32];
-        const bool odd = nkb * (BK / 8) >= 2;                // the odd accumulator exists from the second k-step on
-        tmem_ld32_nowait(ta + 2 * BN, v);                    // small terms
-        tmem_ld32_nowait(ta, w);
-        if (odd) tmem_ld32_nowait(ta + BN, u);
-        tmem_ld_wait();
-        if (odd) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += u[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);   // warp-uniform address: broadcast
-        v[j] += b4.x * rs; v[j + 1] += b4.y * rs; v[j + 2] += b4.z * rs; v[j + 3] += b4.w * rs;
-      }
-      if (act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (act == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) =
-            make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
-    if (threadIdx.x == 128) EQH_STAMP(7);
-    float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
-    const int64_t ld = final_out ? p.ldd : p.N;
-    const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const bool has_res = final_out && p.residual != nullptr;
-    // a warp instruction covers 128 / BN rows of the tile as float4s; four such groups in flight per warp
-    constexpr int LPR = BN / 4;                          // lanes per row
-    constexpr int RPI = 32 / LPR;                        // rows per warp instruction
-    const int c = (lane % LPR) * 4, rsub = lane / LPR;
-    const int n = n0 + c;
-    const bool full_vec = vec_ok && (n + 4 <= p.N);
-    const int rows_here = min(BM, p.M - m0);
-    for (int rb = q * RPI; rb < rows_here; rb += 16 * RPI) {
-      if (full_vec) {
-        float4 x[4], rr[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = rb + rsub + 4 * RPI * u;
-          if (r < rows_here) {
-            x[u] = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
-            // plain (coherent) load: the residual may be D itself
-            if (has_res) rr[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = rb + rsub + 4 * RPI * u;
-          if (r < rows_here) {
-            if (has_res) {
-              x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
-              x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
-            }
-            *reinterpret_cast<float4*>(out + (int64_t)(m0 + r) * ld + n) = x[u];
-          }
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = rb + rsub + 4 * RPI * u;
-          if (r >= rows_here) continue;
-          const float* src = stage_out + r * PITCH + c;
-          float* dst = out + (int64_t)(m0 + r) * ld + n;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j < p.N) {
-              float x = src[j];
-              if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
-              dst[j] = x;
-            }
-          }
-        }
-      }
-    }
+    epilogue_tile<BN>(smem, sbias, tmem_base, &tmem_full, warp, lane, nkb, p, m0, n0);
   }
   if (threadIdx.x == 128) EQH_STAMP(8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (p.ws != nullptr) __threadfence();       // this split's partial tile is visible device-wide before the arrival
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
-  if (p.ws != nullptr) {
-    // ---- split-K finish: the CTA that arrives last at this tile's counter adds the partials in split order
-    // (the order never depends on which CTA is last: deterministic) and applies the output transform
-    if (threadIdx.x == 0) {
-      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-      const int prev = atomicAdd(p.counters + tile, 1);
-      s_last = (prev == (int)gridDim.z - 1);
-      if (s_last) p.counters[tile] = 0;         // left zero for the next launch
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const int64_t MN = (int64_t)p.M * p.N;
-      const int rows_here = min(BM, p.M - m0);
-      const int nz = (int)gridDim.z;
-      const bool vec = ((p.N & 3) == 0) && ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
-                       (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-      if (vec) {
-        constexpr int C4 = BN / 4;
-        for (int e = threadIdx.x; e < rows_here * C4; e += kThreads) {
-          const int r = e / C4, c = (e - r * C4) * 4;
-          if (n0 + c >= p.N) continue;
-          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-          for (int z = 0; z < nz; ++z) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * MN));
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-          }
-          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
-          float4 x = make_float4(p.out_scale * acc.x, p.out_scale * acc.y, p.out_scale * acc.z, p.out_scale * acc.w);
-          if (p.residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(p.residual + o);
-            x.x += p.res_scale * rr.x; x.y += p.res_scale * rr.y; x.z += p.res_scale * rr.z; x.w += p.res_scale * rr.w;
-          }
-          *reinterpret_cast<float4*>(p.D + o) = x;
-        }
-      } else {
-        for (int e = threadIdx.x; e < rows_here * BN; e += kThreads) {
-          const int r = e / BN, c = e - r * BN;
-          if (n0 + c >= p.N) continue;
-          const float* src = p.ws + (int64_t)(m0 + r) * p.N + n0 + c;
-          float acc = 0.f;
-#pragma unroll 8
-          for (int z = 0; z < nz; ++z) acc += __ldcg(src + (int64_t)z * MN);
-          const int64_t o = (int64_t)(m0 + r) * p.ldd + n0 + c;
-          float x = p.out_scale * acc;
-          if (p.residual) x += p.res_scale * p.residual[o];
-          p.D[o] = x;
-        }
-      }
-    }
-  }
+  if (p.ws != nullptr) splitk_finish<BN>(p, m0, n0, &s_last);
 #undef tmem_full
 #undef tmem_slot
 }
@@ -436,9 +241,13 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
   cudaError_t e = cudaFuncSetAttribute(k_gemm<BN, AK, BK_, WH, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_gemm<BN, AK, BK_, WH, STAGES, MINB><<<grid, kThreads, smem, st>>>(a, b, p);
+  launch_kernel(k_gemm<BN, AK, BK_, WH, STAGES, MINB>, dim3(grid), dim3(kThreads), smem, st, a, b, p);
   EQH_LAUNCH_RC();
 }
+
+// gemm_ts.cu: the kernel that feeds A through registers into tensor memory (flag 0x2000)
+int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const float* A, int64_t lda, const CUtensorMap& tmB, const Params& p,
+              dim3 grid, cudaStream_t st);
 
 // Tile width and split count.  Cost model (clocks per CTA): a 32-deep K block costs ~300 (operand split of the
 // 128-row A tile) + 6.4*BN (12 MMAs); the split-K finish costs ~4*BN per split in the last CTA.
@@ -502,6 +311,7 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   const int bn_code = (act_flags >> 9) & 3;             // 0 auto, 1..3 = 32 / 64 / 128 (tuning / tests)
   const bool write_hi = (act_flags & 0x100) != 0;       // debug/verification switch, see kWriteHi
   const bool pair = (act_flags & 0x800) != 0;           // two co-resident CTAs per SM (BN <= 64, 2-stage ring)
+  const bool smem_a = (act_flags & 0x2000) == 0 || write_hi || pair;   // default kernel: both operands via shared memory
   int BN, s_plan;
   plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
   const int kb_total = (int)((K + BK - 1) / BK);
@@ -511,9 +321,11 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   int rc;
   // A: logical [M,K].  K-major: stored [M, lda] -> box {32 K, 128 M}.  MN-major: stored [K, lda] -> box {32 M, 32 K}.
   // MN-major tf32 operands must use the 128B swizzle with 32-byte atoms (UMMA layout SWIZZLE_128B_BASE32B).
-  rc = a_kmajor ? make_map(&tmA, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
-                : make_map(&tmA, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  if (rc) return rc;
+  if (smem_a) {
+    rc = a_kmajor ? make_map(&tmA, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_map(&tmA, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
   rc = b_kmajor ? make_map(&tmB, B, N, K, ldb, BK, (uint32_t)BN, CU_TENSOR_MAP_SWIZZLE_128B)
                 : make_map(&tmB, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
@@ -525,6 +337,7 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   p.kb_per_split = kbps;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!smem_a) return launch_ts(BN, a_kmajor != 0, b_kmajor != 0, A, lda, tmB, p, grid, st);
 #define EQH_GEMM_MAJORS(BNV, WHV, STG, MB)                                                            \
   do {                                                                                                \
     if (a_kmajor && b_kmajor) return launch<BNV, true, true, WHV, STG, MB>(tmA, tmB, p, grid, st);    \

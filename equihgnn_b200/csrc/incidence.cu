@@ -10,6 +10,7 @@ namespace eqh {
 template <typename IdxT>
 __global__ void k_hist(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, int32_t* __restrict__ cnt,
                        int32_t* __restrict__ dst32, int32_t* __restrict__ status) {
+  pdl_prologue();
   int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (z >= Z) return;
   int64_t d = (int64_t)dst[z];
@@ -24,6 +25,7 @@ __global__ void k_hist(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, i
 
 // exclusive scan of cnt[0..n) -> rowptr[0..n], cursor[0..n) ; one CTA of 1024 threads
 __global__ void __launch_bounds__(1024) k_scan(const int32_t* cnt, int64_t n, int32_t* rowptr, int32_t* cursor /* may alias cnt */) {
+  pdl_prologue();
   __shared__ int32_t part[1024];
   const int t = threadIdx.x;
   const int64_t per = (n + 1023) / 1024;
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(1024) k_scan(const int32_t* cnt, int64_t n, in
 template <typename IdxT>
 __global__ void k_place(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, int32_t* __restrict__ cursor,
                         int32_t* __restrict__ slot_z) {
+  pdl_prologue();
   int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (z >= Z) return;
   int64_t d = (int64_t)dst[z];
@@ -64,6 +67,7 @@ __global__ void k_place(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, 
 template <typename IdxT>
 __global__ void k_order(const int32_t* __restrict__ rowptr, int64_t n_dst, const int32_t* __restrict__ slot_z,
                         const IdxT* __restrict__ other, int32_t* __restrict__ perm, int32_t* __restrict__ other_sorted) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -104,16 +108,16 @@ static int build(const IdxT* dst, const IdxT* other, int64_t Z, int64_t n_dst, i
   cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)(n_dst + 1), st);
   if (e != cudaSuccess) return (int)e;
   const int T = 256;
-  if (Z > 0) k_hist<IdxT><<<(unsigned)((Z + T - 1) / T), T, 0, st>>>(dst, Z, n_dst, cnt, dst32, status);
+  if (Z > 0) launch_kernel(k_hist<IdxT>, dim3((unsigned)((Z + T - 1) / T)), dim3(T), 0, st, dst, Z, n_dst, cnt, dst32, status);
   // in-place: the scan reads cnt[i] before overwriting cursor[i] (same thread, same i)
-  k_scan<<<1, 1024, 0, st>>>(cnt, n_dst, rowptr, cnt);
+  launch_kernel(k_scan, dim3(1), dim3(1024), 0, st, cnt, n_dst, rowptr, cnt);
   if (Z > 0) {
-    k_place<IdxT><<<(unsigned)((Z + T - 1) / T), T, 0, st>>>(dst, Z, n_dst, cnt, slot_z);
+    launch_kernel(k_place<IdxT>, dim3((unsigned)((Z + T - 1) / T)), dim3(T), 0, st, dst, Z, n_dst, cnt, slot_z);
     int64_t warps = n_dst;
     int64_t blocks = (warps * 32 + T - 1) / T;
     if (blocks > kSMs * 16) blocks = kSMs * 16;
     if (blocks < 1) blocks = 1;
-    k_order<IdxT><<<(unsigned)blocks, T, 0, st>>>(rowptr, n_dst, slot_z, other, perm, other_sorted);
+    launch_kernel(k_order<IdxT>, dim3((unsigned)blocks), dim3(T), 0, st, rowptr, n_dst, slot_z, other, perm, other_sorted);
   }
   EQH_LAUNCH_RC();
 }

@@ -46,6 +46,7 @@ struct TopK {
 template <int S>  // lanes per query (8 or 32); 256/S queries per CTA
 __global__ void __launch_bounds__(256) k_knn16(const float* __restrict__ pos, int64_t N, int32_t* __restrict__ idx,
                                                 float* __restrict__ d2out) {
+  pdl_prologue();
   __shared__ float sp[kTile * 3];
   constexpr int QPB = 256 / S;
   const int sub = threadIdx.x % S;
@@ -94,9 +95,9 @@ extern "C" int eqh_knn16(const float* pos, int64_t N, int32_t* idx, float* d2, e
   EQH_CHECK_ARG(N >= kK && N < ((int64_t)1 << 31));  // the reference's topk raises for k > N
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N >= 16384) {
-    k_knn16<8><<<(unsigned)((N + 31) / 32), 256, 0, st>>>(pos, N, idx, d2);
+    launch_kernel(k_knn16<8>, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, st, pos, N, idx, d2);
   } else {
-    k_knn16<32><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(pos, N, idx, d2);
+    launch_kernel(k_knn16<32>, dim3((unsigned)((N + 7) / 8)), dim3(256), 0, st, pos, N, idx, d2);
   }
   EQH_LAUNCH_RC();
 }

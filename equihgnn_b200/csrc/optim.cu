@@ -7,6 +7,7 @@ namespace eqh {
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                                float wd, float bc1, float bc2_sqrt, float gscale) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
     float pi = p[i];
@@ -47,7 +48,7 @@ int eqh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   const float bc2 = 1.f - powf(beta2, (float)step);
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
-  k_adam<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+  launch_kernel(k_adam, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                          beta2, eps, weight_decay, bc1, sqrtf(bc2),
                                                                          grad_scale);
   EQH_LAUNCH_RC();

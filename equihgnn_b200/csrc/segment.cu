@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__
                                                         const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ src_rowptr, int64_t n_out, int mode,
                                                         float* __restrict__ out, int64_t ld) {
+  pdl_prologue();
   table += (int64_t)blockIdx.y * (32 * V);  // column block of a wider row (row stride ld)
   out += (int64_t)blockIdx.y * (32 * V);
   const int lane = threadIdx.x & 31;
@@ -61,6 +62,7 @@ template <int V>
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ table, const int32_t* __restrict__ idx,
                                                       const int32_t* __restrict__ scale_rowptr, int64_t n_rows,
                                                       float* __restrict__ out, int64_t ld) {
+  pdl_prologue();
   table += (int64_t)blockIdx.y * (32 * V);
   out += (int64_t)blockIdx.y * (32 * V);
   const int lane = threadIdx.x & 31;
@@ -114,9 +116,9 @@ int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* row
   const dim3 grid(grid_for_warps(n_out, 256), (unsigned)(C / CB));
   EQH_DISPATCH_V(CB, {
     if (src_rowptr)
-      k_gather_reduce<V, true><<<grid, 256, 0, st>>>(table, idx, rowptr, src_rowptr, n_out, mode, out, C);
+      launch_kernel(k_gather_reduce<V, true>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, src_rowptr, n_out, mode, out, C);
     else
-      k_gather_reduce<V, false><<<grid, 256, 0, st>>>(table, idx, rowptr, nullptr, n_out, mode, out, C);
+      launch_kernel(k_gather_reduce<V, false>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, nullptr, n_out, mode, out, C);
   });
   EQH_LAUNCH_RC();
 }
@@ -131,7 +133,7 @@ int eqh_gather_rows(const float* table, const int32_t* idx, const int32_t* scale
   if (n_rows == 0) return EQH_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(grid_for_warps((n_rows + 1) / 2, 256), (unsigned)(C / CB));
-  EQH_DISPATCH_V(CB, { k_gather_rows<V><<<grid, 256, 0, st>>>(table, idx, scale_rowptr, n_rows, out, C); });
+  EQH_DISPATCH_V(CB, { launch_kernel(k_gather_rows<V>, dim3(grid), dim3(256), 0, st, table, idx, scale_rowptr, n_rows, out, C); });
   EQH_LAUNCH_RC();
 }
 

@@ -103,6 +103,7 @@ class GraphedTrainer(Trainer):
         pred = self.model(data)
         loss = F.mse_loss(pred[:self.B], data.y.view(-1)[:self.B])     # the ghost molecule is not in the loss
         loss.backward()
+        ops.side_work.join()        # the side-stream branch rejoins before the capture ends
         return loss.detach()
 
     def _capture(self, like: HBatch) -> _Bucket:

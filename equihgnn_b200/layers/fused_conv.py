@@ -36,6 +36,9 @@ class _GradSink:
 
     def __init__(self, params, direct):
         self.direct = direct
+        # direct mode: nobody reads the gradients before the optimizer, so they are produced on the side stream
+        # (a parallel branch of the captured graph) and joined by the Trainer
+        self.side = direct and ops.side_work.enabled
         self.out = {}
         for p in params:
             if direct:
@@ -58,8 +61,11 @@ class _GradSink:
             self._fresh_cols = getattr(self, "_fresh_cols", {})
         view = tgt if cols is None else tgt[:, cols]
         acc = self.direct or (not fresh and cols is None)
-        gemm_raw(dy, False, x, False, n_out, n_in, M, splits=ops._wgrad_splits(n_out, n_in, M), out=view,
-                 residual=view if acc else None)
+        if self.side:
+            with ops.side_work.fork(dy.device, keep=(dy, x)):
+                gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view)
+        else:
+            gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None)
 
     def bias(self, p, dy, roww=None):
         """p.grad (+)= sum_r roww[r] * dy[r, :]  (queued; finished by flush())"""
@@ -81,7 +87,11 @@ class _GradSink:
                 self.batch.add(part, tgt, col0=c0, cols=C, accumulate=True)
 
     def flush(self):
-        self.batch.run()
+        if self.side:
+            with ops.side_work.fork(self.batch.device, keep=tuple(self.batch.keep)):
+                self.batch.run()
+        else:
+            self.batch.run()
 
     def results(self):
         return tuple(None if self.direct else self.out[id(p)] for p in self.params)

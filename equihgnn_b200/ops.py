@@ -247,6 +247,51 @@ def counters(n: int, device) -> torch.Tensor:
     return buf[off:off + n]
 
 
+class _SideWork:
+    """Off-critical-path work (weight / bias gradients that are accumulated straight into the flat gradient buffer)
+    runs on a second stream, forked from and joined back into the step's stream with events, so that inside the
+    captured CUDA graph it becomes a parallel branch next to the dX chain.  Tensors handed to the side stream are
+    kept alive until the join (the caching allocator only orders reuse on the allocating stream)."""
+
+    def __init__(self):
+        self.streams = {}
+        self.pending = {}
+        self.enabled = os.environ.get("EQH_SIDE_STREAM", "1") != "0"
+
+    def stream(self, device) -> torch.cuda.Stream:
+        key = torch.device(device).index
+        if key is None:
+            key = torch.cuda.current_device()
+        st = self.streams.get(key)
+        if st is None:
+            st = self.streams[key] = torch.cuda.Stream(device=key)
+        return st
+
+    def fork(self, device, keep=()):
+        """Context manager: work issued inside runs on the side stream after everything issued so far on the
+        current stream."""
+        side = self.stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        key = side.device.index
+        self.pending.setdefault(key, []).extend(keep)
+        if not self.pending[key]:
+            self.pending[key].append(None)
+        return torch.cuda.stream(side)
+
+    def join(self, device=None) -> None:
+        """Make the current stream wait for all side work issued so far (no-op when there is none)."""
+        keys = list(self.pending) if device is None else [torch.device(device).index
+                                                          if torch.device(device).index is not None
+                                                          else torch.cuda.current_device()]
+        for key in keys:
+            if self.pending.get(key):
+                torch.cuda.current_stream(key).wait_stream(self.streams[key])
+                self.pending[key] = []
+
+
+side_work = _SideWork()
+
+
 class ColsumBatch:
     """Collects column-sum jobs (bias gradients, per-CTA partial buffers) and finishes them in one launch."""
 
@@ -264,7 +309,7 @@ class ColsumBatch:
             raise RuntimeError("ColsumBatch.add: bad shapes")
         self.jobs.append(_lib.ColsumJob(x.data_ptr() + 4 * col0, _p(roww), out.data_ptr(), rows, cols, x.stride(0),
                                         scale, int(accumulate)))
-        self.keep += [x, out, roww]
+        self.keep += [t for t in (x, out, roww) if t is not None]
 
     def run(self) -> None:
         lib = _lib.load()

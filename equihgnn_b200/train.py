@@ -75,9 +75,11 @@ class Trainer:
         pred = self.model(data)
         loss = F.mse_loss(pred, data.y.view(-1))
         loss.backward()
+        ops.side_work.join()
         return loss.detach()
 
     def sync_gradients(self):
+        ops.side_work.join()        # weight-gradient work issued on the side stream
         if self.distributed:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
 

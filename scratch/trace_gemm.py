@@ -7,7 +7,7 @@ dev = "cuda:0"
 lib = _lib.load()
 names = ["start", "setup done", "first tile landed", "first split done", "last tile landed", "last split done",
          "accumulator ready", "epilogue staged", "stores done"]
-for (M, N, K, fl) in [(2560, 256, 256, 0), (2560, 256, 256, 3 << 9), (2560, 256, 256, 1 << 9), (30000, 256, 256, 0)]:
+for (M, N, K, fl) in [(2560, 256, 256, 0), (2560, 256, 256, 3 << 9), (2560, 256, 256, 1 << 9), (30000, 256, 256, 0), (2560, 256, 256, 0x2000)]:
     A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
     for rep in range(3):
         torch.cuda.synchronize()
@@ -15,7 +15,7 @@ for (M, N, K, fl) in [(2560, 256, 256, 0), (2560, 256, 256, 3 << 9), (2560, 256,
         e0.record(); ops.gemm_raw(A, True, B, True, M, N, K, flags=fl); e1.record()
         torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
-    lib.eqh_debug_gemm_trace(buf)
+    (lib.eqh_debug_gemm_ts_trace if fl & 0x2000 else lib.eqh_debug_gemm_trace)(buf)
     t0 = buf[0]
     print(f"M={M} N={N} K={K} flags={fl:#x} plan={ops.gemm_plan(M,N,K,1,fl)} event time {e0.elapsed_time(e1)*1e3:.1f} us")
     for i, n in enumerate(names):

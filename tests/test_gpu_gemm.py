@@ -41,7 +41,8 @@ def test_gemm_dgrad_layout(M, N, K):
     assert rel_err(D, ref) < 2e-6
 
 
-@pytest.mark.parametrize("flags", [1 << 9, 2 << 9, 3 << 9, (1 << 9) | 0x800, (2 << 9) | 0x800])
+@pytest.mark.parametrize("flags", [1 << 9, 2 << 9, 3 << 9, (1 << 9) | 0x2000, (2 << 9) | 0x2000, (3 << 9) | 0x2000,
+                                   (1 << 9) | 0x800, (2 << 9) | 0x800])
 @pytest.mark.parametrize("M,N,K", [(2341, 256, 256), (300, 72, 272), (129, 1088, 64)])
 def test_gemm_every_tile_width(M, N, K, flags):
     """Forced tile widths 32 / 64 / 128 and the two-CTAs-per-SM variant give the same result as the planner's choice
