@@ -433,10 +433,17 @@ def _breakdown(step_fn, resident, ops):
 
 def main():
     a = parse()
+    # stdout carries exactly ONE JSON line: libraries that print banners on fd 1 (NCCL's version line, torchrun's
+    # OMP notice) are redirected to stderr for the whole run and the result is written to the saved descriptor.
+    real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
