@@ -92,7 +92,13 @@ def _worker(rank, world, port, out_dir):
 
 def test_flat_gradient_allreduce_and_adam_world2(tmp_path):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for attempt in range(3):          # the probed port can be taken between the probe and the rendezvous
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+            break
+        except Exception:
+            if attempt == 2:
+                raise
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
 
