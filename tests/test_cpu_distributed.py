@@ -42,8 +42,8 @@ def _worker(rank, world, port, out_dir):
         tr = Trainer(model, lr=1e-2)
         assert tr.distributed and tr.world == world
         names = [n for n, _ in model.named_parameters()]
-        # contiguous, 128-byte aligned slices; .grad fields are views of ONE buffer
-        assert all(p.data_ptr() % 128 == 0 for p in tr.fp.params)
+        # .grad fields are views of ONE buffer
+        assert all((p.data_ptr() - tr.fp.flat.data_ptr()) % 128 == 0 for p in tr.fp.params)   # 128-byte aligned slices
         base = tr.fp.grad.data_ptr()
         assert all(base <= p.grad.data_ptr() < base + 4 * tr.fp.numel for p in tr.fp.params)
         p0 = tr.fp.flat.clone()
