@@ -12,7 +12,7 @@ constexpr int BM = 128, BK = 32;
 
 #ifdef EQH_TRACE
 // phase timestamps (ns, globaltimer) of CTA (0,0,0) of the most recent launch: scratch/trace_gemm.py
-static __device__ unsigned long long g_trace[16];
+static __device__ unsigned long long g_trace[80];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -25,6 +25,23 @@ __device__ __forceinline__ unsigned long long gtime() {
 constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 operand split (warps 4-7 also epilogue)
 constexpr int kSplitThreads = 256;
 constexpr uint32_t kTileBytes = BM * BK * 4;  // 16 KB: a 128 x 32 fp32 operand tile (any major)
+
+// Accumulator assignment: three [128 x BN] fp32 tiles in tensor memory.  The tensor core truncates when it adds into
+// its accumulator, so the error grows with the number of accumulations per tile: the big hi.hi products alternate
+// between two tiles (even / odd k-steps) and the 2^-11-scaled lo.hi and hi.lo products share a third; the epilogue
+// adds the three.  (Spreading the 12 products of a K block over 6 or 12 tiles was measured: the main loop is not
+// limited by accumulator dependencies, and every extra tile costs 128*BN*4 bytes of TMEM reads -- 64 B/cycle -- in
+// the epilogue.)
+template <int BN>
+struct AccMap {
+  static constexpr int NA = 3;
+  __device__ static __forceinline__ int hh(int ks) { return ks & 1; }
+  __device__ static __forceinline__ int lh(int ks) { return 2; }
+  __device__ static __forceinline__ int hl(int ks) { return 2; }
+  __device__ static __forceinline__ bool first_big(int kb, int ks) { return kb == 0 && ks < 2; }
+  __device__ static __forceinline__ bool first_lh(int kb, int ks) { return kb == 0 && ks == 0; }
+  __device__ static __forceinline__ bool first_hl(int kb, int ks) { return false; }
+};
 
 struct Params {
   float* D;
@@ -44,8 +61,8 @@ struct Params {
 
 // Epilogue of one 128 x BN tile, executed by warps 4-7 (TMEM lane quadrant = warp & 3):
 // TMEM -> registers -> (bias, act, scales) -> padded smem (`smem`, the idle operand ring) -> coalesced stores
-// (+ residual).  Three accumulators of BN columns at tmem_base: hi.hi even / odd k-steps, small terms.
-template <int BN>
+// (+ residual).  AM::NA accumulators of BN columns at tmem_base (see AccMap): big hi.hi tiles first, small ones after.
+template <int BN, class AM>
 __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint32_t tmem_base, uint64_t* tmem_full, int warp,
                                               int lane, int nkb, const Params& p, int m0, int n0) {
     // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
@@ -73,15 +90,24 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
       float v[32];
       if (nkb > 0) {
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        // small terms first (highest tile index), the big hi.hi tiles last; two loads in flight
         float w[32], u[32];
-        const bool odd = nkb * (BK / 8) >= 2;                // the odd accumulator exists from the second k-step on
-        tmem_ld32_nowait(ta + 2 * BN, v);                    // small terms
-        tmem_ld32_nowait(ta, w);
-        if (odd) tmem_ld32_nowait(ta + BN, u);
+        tmem_ld32_nowait(ta + (AM::NA - 1) * BN, v);
+        tmem_ld32_nowait(ta + (AM::NA - 2) * BN, w);
         tmem_ld_wait();
-        if (odd) {
+#pragma unroll
+        for (int a = AM::NA - 3; a >= 0; a -= 2) {
+          if (a >= 0) tmem_ld32_nowait(ta + a * BN, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          if (a >= 1) tmem_ld32_nowait(ta + (a - 1) * BN, w);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += u[j];
+          if (a < 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = 0.f;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += w[j];

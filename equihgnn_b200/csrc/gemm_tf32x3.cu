@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
   // Three fp32 accumulators of BN columns each.  The tensor core adds into its accumulator with
   // truncation, so the error grows with the number of accumulations: the large hi.hi terms alternate
   // between two accumulators and the 2^-11-scaled lo terms get their own (summed in the epilogue).
-  constexpr uint32_t kTmemCols = BN * 4;       // power of two >= 3*BN (>= 32)
-  static_assert(kTmemCols * MINB <= 512, "co-resident CTAs must fit in TMEM");
+  using AM = AccMap<BN>;
+  constexpr uint32_t kTmemCols = AM::NA * BN <= 128 ? 128 : (AM::NA * BN <= 256 ? 256 : 512);
+  static_assert(AM::NA * BN <= 512 && kTmemCols * MINB <= 512, "co-resident CTAs must fit in TMEM");
   if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
                                  ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       constexpr uint32_t lboA = A_KMAJOR ? 0u : BK * 128u, lboB = B_KMAJOR ? 0u : BK * 128u;
@@ -117,23 +118,25 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_split[s], ph);
-        if (i == 0) EQH_STAMP(3);
-        if (i == nkb - 1) EQH_STAMP(5);
+        if (lane == 0 && i == 0) EQH_STAMP(3);
+        if (lane == 0 && i == nkb - 1) EQH_STAMP(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t aH = smem_u32(stageA(s)), aL = smem_u32(stageAlo(s));
         const uint32_t bH = smem_u32(stageB(s)), bL = smem_u32(stageBlo(s));
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t dAh = make_desc(aH + ks * kstepA, lboA, sboA, ltA), dAl = make_desc(aL + ks * kstepA, lboA, sboA, ltA);
-          const uint64_t dBh = make_desc(bH + ks * kstepB, lboB, sboB, ltB), dBl = make_desc(bL + ks * kstepB, lboB, sboB, ltB);
-          const uint32_t step = (uint32_t)(i * (BK / 8) + ks);
-          umma_tf32(tmem_base + 2 * BN, dAl, dBh, idesc, step != 0);
-          umma_tf32(tmem_base + 2 * BN, dAh, dBl, idesc, 1);
-          umma_tf32(tmem_base + (step & 1) * BN, dAh, dBh, idesc, step >= 2);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t dAh = make_desc(aH + ks * kstepA, lboA, sboA, ltA), dAl = make_desc(aL + ks * kstepA, lboA, sboA, ltA);
+            const uint64_t dBh = make_desc(bH + ks * kstepB, lboB, sboB, ltB), dBl = make_desc(bL + ks * kstepB, lboB, sboB, ltB);
+            umma_tf32(tmem_base + AM::lh(ks) * BN, dAl, dBh, idesc, !AM::first_lh(i, ks));
+            umma_tf32(tmem_base + AM::hh(ks) * BN, dAh, dBh, idesc, !AM::first_big(i, ks));
+            umma_tf32(tmem_base + AM::hl(ks) * BN, dAh, dBl, idesc, !AM::first_hl(i, ks));
+          }
+          umma_commit(&empty[s]);   // frees the stage when these MMAs have read it
         }
-        umma_commit(&empty[s]);   // frees the stage when these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(&tmem_full);
+      if (elect_one()) umma_commit(&tmem_full);
     }
   } else {
     // ===================== operand split (hi / lo): warps 2-9 =====================
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gemm(const __grid_constant__
   }
   if (warp >= 4 && warp < 8) {
     float* sbias = reinterpret_cast<float*>(smem + (size_t)STAGES * kStageBytes + 128);   // [BN] after the barriers
-    epilogue_tile<BN>(smem, sbias, tmem_base, &tmem_full, warp, lane, nkb, p, m0, n0);
+    epilogue_tile<BN, AM>(smem, sbias, tmem_base, &tmem_full, warp, lane, nkb, p, m0, n0);
   }
   if (threadIdx.x == 128) EQH_STAMP(8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -245,8 +248,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
   EQH_LAUNCH_RC();
 }
 
-// gemm_ts.cu: the kernel that feeds A through registers into tensor memory (flag 0x2000)
-int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const float* A, int64_t lda, const CUtensorMap& tmB, const Params& p,
+// gemm_ts.cu: the kernel that feeds A through registers into tensor memory (default)
+int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
               dim3 grid, cudaStream_t st);
 
 // Tile width and split count.  Cost model (clocks per CTA): a 32-deep K block costs ~300 (operand split of the
@@ -310,8 +313,7 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   EQH_CHECK_ARG(ldd >= N);
   const int bn_code = (act_flags >> 9) & 3;             // 0 auto, 1..3 = 32 / 64 / 128 (tuning / tests)
   const bool write_hi = (act_flags & 0x100) != 0;       // debug/verification switch, see kWriteHi
-  const bool pair = (act_flags & 0x800) != 0;           // two co-resident CTAs per SM (BN <= 64, 2-stage ring)
-  const bool smem_a = (act_flags & 0x2000) == 0 || write_hi || pair;   // default kernel: both operands via shared memory
+  const bool smem_a = (act_flags & 0x1000) != 0 || write_hi;   // first kernel: both operands staged and split in shared memory
   int BN, s_plan;
   plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
   const int kb_total = (int)((K + BK - 1) / BK);
@@ -321,11 +323,11 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   int rc;
   // A: logical [M,K].  K-major: stored [M, lda] -> box {32 K, 128 M}.  MN-major: stored [K, lda] -> box {32 M, 32 K}.
   // MN-major tf32 operands must use the 128B swizzle with 32-byte atoms (UMMA layout SWIZZLE_128B_BASE32B).
-  if (smem_a) {
-    rc = a_kmajor ? make_map(&tmA, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
-                  : make_map(&tmA, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
-  }
+  // (the TMEM-A kernel reads an MN-major A tile row by row itself: one plain box {128 M, 32 K})
+  rc = a_kmajor ? make_map(&tmA, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                : (smem_a ? make_map(&tmA, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                          : make_map(&tmA, A, K, M, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE));
+  if (rc) return rc;
   rc = b_kmajor ? make_map(&tmB, B, N, K, ldb, BK, (uint32_t)BN, CU_TENSOR_MAP_SWIZZLE_128B)
                 : make_map(&tmB, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
@@ -337,7 +339,7 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   p.kb_per_split = kbps;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!smem_a) return launch_ts(BN, a_kmajor != 0, b_kmajor != 0, A, lda, tmB, p, grid, st);
+  if (!smem_a) return launch_ts(BN, a_kmajor != 0, b_kmajor != 0, tmA, tmB, p, grid, st);
 #define EQH_GEMM_MAJORS(BNV, WHV, STG, MB)                                                            \
   do {                                                                                                \
     if (a_kmajor && b_kmajor) return launch<BNV, true, true, WHV, STG, MB>(tmA, tmB, p, grid, st);    \
@@ -348,11 +350,6 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   if (write_hi) {
     if (BN != 128) return EQH_ERR_UNSUPPORTED;
     EQH_GEMM_MAJORS(128, true, 3, 1);
-  }
-  if (pair) {
-    if (BN == 32) EQH_GEMM_MAJORS(32, false, 2, 2);
-    if (BN == 64) EQH_GEMM_MAJORS(64, false, 2, 2);
-    return EQH_ERR_UNSUPPORTED;
   }
   if (BN == 32) EQH_GEMM_MAJORS(32, false, 4, 1);
   if (BN == 64) EQH_GEMM_MAJORS(64, false, 4, 1);

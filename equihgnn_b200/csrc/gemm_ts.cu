@@ -1,18 +1,19 @@
-// 3xTF32 row GEMM, second kernel: the A operand never touches shared memory.
+// 3xTF32 row GEMM, second kernel: the A operand reaches the tensor core through tensor memory.
 //
 // gemm_tf32x3.cu is bound by shared-memory bandwidth, not by the tensor core: per 32-deep K block it moves the
-// A tile through shared memory five times (TMA write, split read, lo write, and three tcgen05.mma operand reads).
-// Here each of the 128 threads of warps 4-7 owns one row of the A tile (= one TMEM lane): it loads its 32 K
-// values from global memory into registers, splits them hi / lo and writes both halves into tensor memory
-// (tcgen05.st); the MMAs take A from TMEM ("TS" form) and only the B tile (the weights: BN x 32) goes through
-// shared memory.  Shared-memory traffic per K block drops from 5*16 KB + 5*BN*128 B to 5*BN*128 B, which puts
-// the main loop at the tensor-core rate (12 MMAs) for BN >= 64.
+// 16 KB A tile through shared memory six times (TMA write, split read, lo write, three tcgen05.mma operand reads).
+// Here the A tile crosses shared memory twice (TMA write, one read): each of the 128 threads of warps 4-7 owns one
+// row of the tile (= one TMEM lane), reads its 32 K values from the landed tile, splits them hi / lo in registers
+// and writes both halves into tensor memory (tcgen05.st); the MMAs take A from TMEM ("TS" form) and only the B tile
+// (the weights: BN x 32) is read from shared memory by the tensor core.
 //
-//   warp 0 (1 thread)  TMA producer of B tiles (128B swizzle) into a ring
+//   warp 0 (1 thread)  TMA producer: A tile (K-major: 128B-swizzled rows; MN-major: plain [32 k][128 m]) and B tile
 //   warps 2,3,8,9      split the landed B tile into hi (in place) / lo, fence.proxy.async, signal
-//   warps 4-7          A rows: global -> registers (4-deep ring, 3 K blocks in flight) -> TMEM hi | lo; then epilogue
-//   warp 1 (1 thread)  per K block 4 k-steps x 3 tcgen05.mma (A from TMEM), commits free the A and B stages
+//   warps 4-7          A rows: shared memory -> registers -> TMEM hi | lo (one row per thread); then the epilogue
+//   warp 1 (1 thread)  per K block 4 k-steps x 3 tcgen05.mma (A from TMEM); commits free the TMEM and smem stages
 // TMEM columns: [0, 3*BN) accumulators (as in gemm_tf32x3.cu), then the A ring: 64 columns (hi | lo) per stage.
+// (A first version loaded the rows straight from global memory: one 128-byte line per thread and instruction,
+// which the L1 wavefront queue serialises -- slower than the shared-memory kernel.)
 #include "gemm_common.cuh"
 
 namespace eqh {
@@ -45,33 +46,35 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 template <int BN>
 struct TsCfg {
   static constexpr int SA = BN == 128 ? 2 : 4;                  // A stages in TMEM (64 columns each)
-  static constexpr int SB = BN == 128 ? 6 : 8;                  // B stages in shared memory
+  static constexpr int SB = BN == 128 ? 4 : (BN == 64 ? 6 : 8); // shared-memory stages (A raw, B raw/hi, B lo)
+  static constexpr uint32_t kABytes = kTileBytes;               // 16 KB
   static constexpr uint32_t kBBytes = BN * BK * 4;
-  static constexpr uint32_t kStageBytes = 2 * kBBytes;          // B raw/hi, B lo
-  static constexpr uint32_t kAcol = 3 * BN;                     // first TMEM column of the A ring
+  static constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;
+  static constexpr uint32_t kAcol = AccMap<BN>::NA * BN; // first TMEM column of the A ring
   static constexpr size_t kRing = (size_t)SB * kStageBytes;
   static constexpr size_t kSmem = kRing + 512 + BN * 4;         // ring + barriers + bias tile
   static_assert(kAcol + SA * 64 <= 512, "TMEM budget");
   static_assert(kRing >= (size_t)BM * (BN + 4) * 4, "epilogue staging must fit in the B ring");
 };
 
-constexpr int LA = 4;        // register ring of the A rows: LA-1 K blocks of loads in flight per thread
-
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict__ A, int64_t lda,
+__global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const Params p) {
   using Cfg = TsCfg<BN>;
+  using AM = AccMap<BN>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB;
+  static_assert(Cfg::kAcol == AM::NA * BN, "A ring starts after the accumulators");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* b_raw = reinterpret_cast<uint64_t*>(smem + Cfg::kRing);     // TMA landed
   uint64_t* b_full = b_raw + SB;                                        // hi/lo ready for the tensor core
   uint64_t* b_empty = b_full + SB;
-  uint64_t* a_full = b_empty + SB;
+  uint64_t* a_sfree = b_empty + SB;                                     // A smem tile consumed (read into registers)
+  uint64_t* a_full = a_sfree + SB;
   uint64_t* a_empty = a_full + SA;
   uint64_t* tmem_full = a_empty + SA;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* sbias = reinterpret_cast<float*>(smem + Cfg::kRing + 512);
-  static_assert((3 * SB + 2 * SA + 1) * 8 + 4 <= 512, "barrier block");
+  static_assert((4 * SB + 2 * SA + 1) * 8 + 4 <= 512, "barrier block");
   __shared__ int s_last;
 
   pdl_launch_dependents();
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
       mbar_init(&b_raw[s], 1);
       mbar_init(&b_full[s], 4);          // one elected arrival per B-split warp
       mbar_init(&b_empty[s], 1);
+      mbar_init(&a_sfree[s], 4);         // one elected arrival per A warp
     }
     for (int s = 0; s < SA; ++s) {
       mbar_init(&a_full[s], 4);          // one elected arrival per A warp
@@ -104,18 +108,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) EQH_STAMP(1);
 
-  auto stageB = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
-  auto stageBlo = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes + Cfg::kBBytes; };
+  auto stageA = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+  auto stageB = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes + Cfg::kABytes; };
+  auto stageBlo = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes; };
 
   if (warp == 0) {
-    // ===================== TMA producer (B) =====================
+    // ===================== TMA producer (A and B) =====================
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
         const int s = i % SB;
         const uint32_t ph = (i / SB) & 1;
         mbar_wait(&b_empty[s], ph ^ 1);
-        mbar_expect_tx(&b_raw[s], Cfg::kBBytes);
+        mbar_wait(&a_sfree[s], ph ^ 1);
+        mbar_expect_tx(&b_raw[s], Cfg::kABytes + Cfg::kBBytes);
         const int k0 = (kb_begin + i) * BK;
+        if constexpr (A_KMAJOR) tma_load_2d(stageA(s), &tmA, &b_raw[s], k0, m0);    // box {32 K, 128 M}, 128B swizzle
+        else tma_load_2d(stageA(s), &tmA, &b_raw[s], m0, k0);                       // box {128 M, 32 K}, no swizzle
         if constexpr (B_KMAJOR) {
           tma_load_2d(stageB(s), &tmB, &b_raw[s], k0, n0);                 // box {32 K, BN}
         } else {
@@ -126,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_KMAJOR ? 0u : 1u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       constexpr uint32_t lboB = B_KMAJOR ? 0u : BK * 128u;
@@ -138,84 +146,70 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
         const int sa = i % SA, sb = i % SB;
         mbar_wait(&b_full[sb], (i / SB) & 1);
         mbar_wait(&a_full[sa], (i / SA) & 1);
-        if (i == 0) EQH_STAMP(3);
+        if (lane == 0 && i == 0) EQH_STAMP(3);
+        if (lane == 0 && i < 8) EQH_STAMP(48 + i);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t bH = smem_u32(stageB(sb)), bL = smem_u32(stageBlo(sb));
         const uint32_t aH = tmem_base + Cfg::kAcol + sa * 64, aL = aH + 32;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t dBh = make_desc(bH + ks * kstepB, lboB, sboB, ltB), dBl = make_desc(bL + ks * kstepB, lboB, sboB, ltB);
-          const uint32_t step = (uint32_t)(i * (BK / 8) + ks);
-          umma_tf32_ts(tmem_base + 2 * BN, aL + ks * 8, dBh, idesc, step != 0);
-          umma_tf32_ts(tmem_base + 2 * BN, aH + ks * 8, dBl, idesc, 1);
-          umma_tf32_ts(tmem_base + (step & 1) * BN, aH + ks * 8, dBh, idesc, step >= 2);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t dBh = make_desc(bH + ks * kstepB, lboB, sboB, ltB), dBl = make_desc(bL + ks * kstepB, lboB, sboB, ltB);
+            umma_tf32_ts(tmem_base + AM::lh(ks) * BN, aL + ks * 8, dBh, idesc, !AM::first_lh(i, ks));
+            umma_tf32_ts(tmem_base + AM::hh(ks) * BN, aH + ks * 8, dBh, idesc, !AM::first_big(i, ks));
+            umma_tf32_ts(tmem_base + AM::hl(ks) * BN, aH + ks * 8, dBl, idesc, !AM::first_hl(i, ks));
+          }
+          umma_commit(&a_empty[sa]);     // both stages are free once these MMAs have read them
+          umma_commit(&b_empty[sb]);
         }
-        umma_commit(&a_empty[sa]);     // both stages are free once these MMAs have read them
-        umma_commit(&b_empty[sb]);
+        __syncwarp();
+        if (lane == 0 && i < 8) EQH_STAMP(56 + i);
       }
-      if (nkb > 0) EQH_STAMP(5);
-      umma_commit(tmem_full);
+      if (lane == 0 && nkb > 0) EQH_STAMP(5);
+      if (elect_one()) umma_commit(tmem_full);
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== A rows: global -> registers -> TMEM (hi | lo) =====================
+    // ===================== A rows: shared memory -> registers -> TMEM (hi | lo) =====================
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
+    const int r = q * 32 + lane;                                   // tile row = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAcol;
-    uint32_t a[LA][32];
-    auto load = [&](int i, uint32_t* dst) {
-      const int k0 = (kb_begin + i) * BK;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % SB, sa = i % SA;
+      mbar_wait(&b_raw[s], (i / SB) & 1);
+      if (r == 0 && i < 8) EQH_STAMP(32 + i);
+      uint32_t v[32];
       if constexpr (A_KMAJOR) {
-        const float* src = A + (int64_t)m * lda + k0;            // the thread's own row: 128 contiguous bytes
-        if (row_ok && k0 + BK <= p.K) {
+        const uint8_t* row = stageA(s) + r * 128;                  // 128B swizzle: chunk c sits at c ^ (r & 7)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + c);
-            dst[4 * c] = __float_as_uint(v.x); dst[4 * c + 1] = __float_as_uint(v.y);
-            dst[4 * c + 2] = __float_as_uint(v.z); dst[4 * c + 3] = __float_as_uint(v.w);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) dst[c] = (row_ok && k0 + c < p.K) ? __float_as_uint(__ldg(src + c)) : 0u;
+        for (int c = 0; c < 8; ++c) {
+          const uint4 t4 = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+          v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
         }
       } else {
-        const float* src = A + (int64_t)k0 * lda + m;            // stored [K, lda]: a warp reads 128 contiguous bytes per k
+        const uint32_t* col = reinterpret_cast<const uint32_t*>(stageA(s)) + r;     // [32 k][128 m]: lanes are consecutive words
 #pragma unroll
-        for (int c = 0; c < 32; ++c) dst[c] = (row_ok && k0 + c < p.K) ? __float_as_uint(__ldg(src + (int64_t)c * lda)) : 0u;
+        for (int c = 0; c < 32; ++c) v[c] = col[c * 128];
       }
-    };
-    auto push = [&](int i, uint32_t* v) {
-      const int sa = i % SA;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_sfree[s]);                     // the tile is in registers: TMA may refill the slot
       mbar_wait(&a_empty[sa], ((i / SA) & 1) ^ 1);
+      if (r == 0 && i < 8) EQH_STAMP(64 + i);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_st32(lane_addr + sa * 64, v);                         // hi: the tensor core ignores the low 13 bits
+      tmem_st32(lane_addr + sa * 64, v);                           // hi: the tensor core ignores the low 13 bits
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const float x = __uint_as_float(v[c]);
         v[c] = __float_as_uint(x - __uint_as_float(v[c] & 0xffffe000u));
       }
-      tmem_st32(lane_addr + sa * 64 + 32, v);                    // lo
+      tmem_st32(lane_addr + sa * 64 + 32, v);                      // lo
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[sa]);
-    };
-#pragma unroll
-    for (int u = 0; u < LA - 1; ++u)
-      if (u < nkb) load(u, a[u]);
-#pragma unroll 1
-    for (int i0 = 0; i0 < nkb; i0 += LA) {
-#pragma unroll
-      for (int u = 0; u < LA; ++u) {
-        const int i = i0 + u;
-        if (i < nkb) {
-          if (i + LA - 1 < nkb) load(i + LA - 1, a[(u + LA - 1) % LA]);
-          push(i, a[u]);
-        }
-      }
+      if (r == 0 && i < 8) EQH_STAMP(40 + i);
     }
     // ===================== epilogue (same warps) =====================
-    epilogue_tile<BN>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0);
+    epilogue_tile<BN, AM>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0);
   } else {
     // ===================== B split (hi / lo): warps 2, 3, 8, 9 =====================
     const int t = ((warp < 4 ? warp - 2 : warp - 6) << 5) + lane;      // 0..127
@@ -223,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
       const int s = i % SB;
       mbar_wait(&b_raw[s], (i / SB) & 1);
       if (t == 0 && i == 0) EQH_STAMP(2);
+      if (t == 0 && i < 8) EQH_STAMP(16 + i);
       const float4* bh = reinterpret_cast<const float4*>(stageB(s));
       float4* bl = reinterpret_cast<float4*>(stageBlo(s));
       constexpr int NB = Cfg::kBBytes / 16 / 128;     // 8 (BN=128), 4, 2
@@ -238,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_full[s]);
+      if (t == 0 && i < 8) EQH_STAMP(24 + i);
     }
   }
   if (threadIdx.x == 128) EQH_STAMP(8);
@@ -249,23 +245,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const float* __restrict
 }
 
 template <int BN, bool AK, bool BK_>
-static int launch_one(const float* A, int64_t lda, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+static int launch_one(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = TsCfg<BN>::kSmem;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   cudaError_t e = cudaFuncSetAttribute(k_gemm_ts<BN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  launch_kernel(k_gemm_ts<BN, AK, BK_>, dim3(grid), dim3(kThreads), smem, st, A, lda, b, p);
+  launch_kernel(k_gemm_ts<BN, AK, BK_>, dim3(grid), dim3(kThreads), smem, st, a, b, p);
   EQH_LAUNCH_RC();
 }
 
-int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const float* A, int64_t lda, const CUtensorMap& tmB, const Params& p,
+int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
               dim3 grid, cudaStream_t st) {
 #define EQH_TS_MAJORS(BNV)                                                                \
   do {                                                                                    \
-    if (a_kmajor && b_kmajor) return launch_one<BNV, true, true>(A, lda, tmB, p, grid, st);   \
-    if (a_kmajor && !b_kmajor) return launch_one<BNV, true, false>(A, lda, tmB, p, grid, st); \
-    if (!a_kmajor && !b_kmajor) return launch_one<BNV, false, false>(A, lda, tmB, p, grid, st); \
-    return launch_one<BNV, false, true>(A, lda, tmB, p, grid, st);                        \
+    if (a_kmajor && b_kmajor) return launch_one<BNV, true, true>(tmA, tmB, p, grid, st);   \
+    if (a_kmajor && !b_kmajor) return launch_one<BNV, true, false>(tmA, tmB, p, grid, st); \
+    if (!a_kmajor && !b_kmajor) return launch_one<BNV, false, false>(tmA, tmB, p, grid, st); \
+    return launch_one<BNV, false, true>(tmA, tmB, p, grid, st);                        \
   } while (0)
   if (BN == 32) EQH_TS_MAJORS(32);
   if (BN == 64) EQH_TS_MAJORS(64);
@@ -278,6 +274,6 @@ int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const float* A, int64_t lda,
 
 #ifdef EQH_TRACE
 extern "C" EQH_API int eqh_debug_gemm_ts_trace(unsigned long long* host16) {
-  return (int)cudaMemcpyFromSymbol(host16, eqh::gemm::g_trace, sizeof(unsigned long long) * 16);
+  return (int)cudaMemcpyFromSymbol(host16, eqh::gemm::g_trace, sizeof(unsigned long long) * 80);
 }
 #endif

@@ -39,6 +39,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a converged warp.  The MMA / TMA issuing loops run warp-uniformly and only the instruction itself is
+// predicated on this: inside an `if (lane == 0)` region ptxas has to build every descriptor in vector registers and
+// move it to the uniform file (R2UR, ~25 cycles each, serialised) -- measured: ~70 cycles per tcgen05.mma issued.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
                : "memory");

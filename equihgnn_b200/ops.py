@@ -509,7 +509,7 @@ _ACT = {None: 0, "none": 0, "relu": 1, "silu": 2}
 SM_COUNT = 148
 
 
-GEMM_FLAGS = int(os.environ.get("EQH_GEMM_FLAGS", "0"), 0)     # tuning: forced tile width / co-resident CTAs
+GEMM_FLAGS = int(os.environ.get("EQH_GEMM_FLAGS", "0"), 0)     # tuning: forced tile width / kernel variant
 
 
 def gemm_plan(M: int, N: int, K: int, splits: int = 1, flags: int = 0):

@@ -20,7 +20,7 @@ def timeit(fn, reps=20):
     for _ in range(5): g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / (5 * reps) * 1e3
-variants = {"auto": 0, "bn32": 1 << 9, "bn64": 2 << 9, "bn128": 3 << 9, "ts": 0x2000}
+variants = {"auto": 0, "bn32": 1 << 9, "bn64": 2 << 9, "bn128": 3 << 9, "v1": 0x1000}
 for (M, N, K) in [(2560, 256, 256), (2560, 1088, 256), (2560, 512, 272), (30000, 256, 256), (30000, 1088, 256), (77000, 256, 256)]:
     A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); dY = torch.randn(M, N, device=dev)
     t_ft = timeit(lambda: A @ B.t()); t_wt = timeit(lambda: dY.t() @ A)

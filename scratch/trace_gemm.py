@@ -15,7 +15,7 @@ for (M, N, K, fl) in [(2560, 256, 256, 0), (2560, 256, 256, 3 << 9), (2560, 256,
         e0.record(); ops.gemm_raw(A, True, B, True, M, N, K, flags=fl); e1.record()
         torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
-    (lib.eqh_debug_gemm_ts_trace if fl & 0x2000 else lib.eqh_debug_gemm_trace)(buf)
+    (lib.eqh_debug_gemm_ts_trace if not (fl & 0x1000) else lib.eqh_debug_gemm_trace)(buf)
     t0 = buf[0]
     print(f"M={M} N={N} K={K} flags={fl:#x} plan={ops.gemm_plan(M,N,K,1,fl)} event time {e0.elapsed_time(e1)*1e3:.1f} us")
     for i, n in enumerate(names):

@@ -41,18 +41,17 @@ def test_gemm_dgrad_layout(M, N, K):
     assert rel_err(D, ref) < 2e-6
 
 
-@pytest.mark.parametrize("flags", [1 << 9, 2 << 9, 3 << 9, (1 << 9) | 0x2000, (2 << 9) | 0x2000, (3 << 9) | 0x2000,
-                                   (1 << 9) | 0x800, (2 << 9) | 0x800])
+@pytest.mark.parametrize("flags", [1 << 9, 2 << 9, 3 << 9, (1 << 9) | 0x1000, (2 << 9) | 0x1000, (3 << 9) | 0x1000])
 @pytest.mark.parametrize("M,N,K", [(2341, 256, 256), (300, 72, 272), (129, 1088, 64)])
 def test_gemm_every_tile_width(M, N, K, flags):
-    """Forced tile widths 32 / 64 / 128 and the two-CTAs-per-SM variant give the same result as the planner's choice
-    (bit-identical: the K order per output element does not depend on the tile width)."""
+    """Forced tile widths 32 / 64 / 128 and the first-generation (shared-memory A) kernel agree with the planner's choice and are deterministic."""
     g = torch.Generator().manual_seed(M + N + K)
     A, B, bias, W = _mk((M, K), g), _mk((N, K), g), _mk((N,), g), _mk((K, N), g)
     ref = torch.relu(A.double() @ B.double().t() + bias.double())
     D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu", flags=flags)
     assert rel_err(D, ref) < 2e-6
-    assert torch.equal(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu"))
+    assert rel_err(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu")) < 1e-6
+    assert torch.equal(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu", flags=flags))
     D = ops.gemm_raw(A, True, W, False, M, N, K, flags=flags)                   # MN-major B (dgrad layout)
     assert rel_err(D, A.double() @ W.double()) < 2e-6
     X = _mk((M, N), g)
