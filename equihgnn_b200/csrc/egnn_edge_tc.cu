@@ -144,8 +144,8 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       }
     }
   } else if (warp == 12) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
+    {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
@@ -160,21 +160,25 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t aH = smem_u32(smem + (size_t)s * kStageBytes), aL = aH + kABytes;
           const uint32_t bH = aH + 2 * kABytes, bL = bH + kBBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint32_t step = (uint32_t)(kb * (BK / 8) + ks);
-            const uint64_t dAh = make_desc(aH + ks * 32, 0, 1024, 2), dAl = make_desc(aL + ks * 32, 0, 1024, 2);
-            const uint64_t dBh = make_desc(bH + ks * 32, 0, 1024, 2), dBl = make_desc(bL + ks * 32, 0, 1024, 2);
-            // Back-to-back MMAs into the SAME accumulator serialise on the accumulate latency, and each truncating
-            // accumulation adds rounding error: spread the products over 8 independent 16-column accumulators
-            // (hi.hi: one per k-step of the block; lo.hi and hi.lo: two each, alternating), summed in the epilogue.
-            umma_tf32(acc + (4 + (ks & 1)) * 16, dAl, dBh, idesc, step >= 2);
-            umma_tf32(acc + (6 + (ks & 1)) * 16, dAh, dBl, idesc, step >= 2);
-            umma_tf32(acc + ks * 16, dAh, dBh, idesc, kb != 0);
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint32_t step = (uint32_t)(kb * (BK / 8) + ks);
+              const uint64_t dAh = make_desc(aH + ks * 32, 0, 1024, 2), dAl = make_desc(aL + ks * 32, 0, 1024, 2);
+              const uint64_t dBh = make_desc(bH + ks * 32, 0, 1024, 2), dBl = make_desc(bL + ks * 32, 0, 1024, 2);
+              // Back-to-back MMAs into the SAME accumulator serialise on the accumulate latency, and each truncating
+              // accumulation adds rounding error: spread the products over 8 independent 16-column accumulators
+              // (hi.hi: one per k-step of the block; lo.hi and hi.lo: two each, alternating), summed in the epilogue.
+              umma_tf32(acc + (4 + (ks & 1)) * 16, dAl, dBh, idesc, step >= 2);
+              umma_tf32(acc + (6 + (ks & 1)) * 16, dAh, dBl, idesc, step >= 2);
+              umma_tf32(acc + ks * 16, dAh, dBh, idesc, kb != 0);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
         }
-        umma_commit(&tmem_full[buf]);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
     }
   } else {

@@ -95,7 +95,26 @@ class EGNN(nn.Module):
         self.coor_weights_clamp_value = coor_weights_clamp_value
         self.dropout_p = dropout
         self.init_eps = init_eps
+        # set by equihgnn_b200.train.Trainer: the layer runs as one hand-scheduled Function whose parameter gradients
+        # are accumulated straight into p.grad (layers/fused_egnn.py)
+        self.direct_param_grad = False
+        self._packed = None
         self.apply(self.init_)
+
+    def _fusable(self, h, x, need_coors) -> bool:
+        return (self.direct_param_grad and torch.is_grad_enabled() and not need_coors and not x.requires_grad
+                and self.node_mlp is not None and isinstance(self.node_norm, nn.LayerNorm) and h.is_cuda
+                and h.dtype == torch.float32 and ops.row_ln_supported(h, h.shape[-1]))
+
+    def _packed_buffers(self, device, C):
+        """Persistent zero-padded, TMA-aligned copies of phi_e's weights (refreshed from the parameters every forward):
+        H = 2(2C+1) padded to a multiple of 64; the pad rows / columns stay zero."""
+        if self._packed is None or self._packed["W1a"].device != device:
+            H0 = self.edge_mlp[0].weight.shape[0]
+            Hp = _round_up(H0, 64)
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
+            self._packed = {"W1a": z(Hp, C), "W1b": z(Hp, C), "wc": z(Hp), "b1": z(Hp), "W2": z(ops.M_DIM, Hp)}
+        return self._packed
 
     def init_(self, module):
         if type(module) in {nn.Linear}:
@@ -117,6 +136,13 @@ class EGNN(nn.Module):
         x = coors[0]
         N, C = h.shape
         graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=torch.is_grad_enabled())
+        if self._fusable(h, x, need_coors):
+            from .fused_egnn import EGNNFused
+            lin0, lin3, n0, n3 = self.edge_mlp[0], self.edge_mlp[3], self.node_mlp[0], self.node_mlp[3]
+            out = EGNNFused.apply(h, graph, self._packed_buffers(h.device, C), self.node_norm.eps, lin0.weight, lin0.bias,
+                                  lin3.weight, lin3.bias, self.node_norm.weight, self.node_norm.bias, n0.weight, n0.bias,
+                                  n3.weight, n3.bias)
+            return out.unsqueeze(0), coors
         idx_long = None
         if x.requires_grad:
             # differentiable squared distances with the same arithmetic as the kernel / reference

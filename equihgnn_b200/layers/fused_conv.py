@@ -24,10 +24,10 @@ def _rowln_fwd(x, g, b, eps):
     return y
 
 
-def _rowln_bwd(x, g, eps, dy):
+def _rowln_bwd(x, g, eps, dy, relu=1):
     dx = torch.empty_like(x)
     part = torch.empty((partial_rows(), 2 * x.shape[1]), dtype=torch.float32, device=x.device)
-    _call("eqh_rowln_bwd", 1, _p(x), _p(g), eps, 1, _p(dy), x.shape[0], x.shape[1], _p(dx), _p(part), _stream())
+    _call("eqh_rowln_bwd", 1, _p(x), _p(g), eps, relu, _p(dy), x.shape[0], x.shape[1], _p(dx), _p(part), _stream())
     return dx, part
 
 
