@@ -90,8 +90,12 @@ class EGNNFused(torch.autograd.Function):
         # ---- phi_e parameter gradients (side stream)
         gw1 = sink.out[id(w1)]
         with ops.side_work.fork(dev, keep=(dP, dQ, h, part)):
-            gemm_raw(dP, False, h, False, H0, C, N, splits=0, out=gw1[:, :C], residual=gw1[:, :C])
-            gemm_raw(dQ, False, h, False, H0, C, N, splits=0, out=gw1[:, C:2 * C], residual=gw1[:, C:2 * C])
+            # into a 16-byte-aligned staging matrix (vector stores, vector split-K finish), then one add into the
+            # [H0, 2C+1] gradient whose odd row stride would force the scalar epilogue
+            tmp = torch.empty((H0, 2 * C), dtype=torch.float32, device=dev)
+            gemm_raw(dP, False, h, False, H0, C, N, splits=0, out=tmp[:, :C])
+            gemm_raw(dQ, False, h, False, H0, C, N, splits=0, out=tmp[:, C:])
+            gw1[:, :2 * C].add_(tmp)
             red = torch.empty(cols, dtype=torch.float32, device=dev)
             batch = ops.ColsumBatch(dev)
             batch.add(part, red)
