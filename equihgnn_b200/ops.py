@@ -671,7 +671,10 @@ def atom_encode(x: torch.Tensor, tables) -> torch.Tensor:
     return _AtomEncode.apply(x, *tables)
 
 
-def knn16(pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+KNN_GRID_MIN = int(os.environ.get("EQH_KNN_GRID_MIN", "8192"))     # atoms per batch from which the cell grid is used
+
+
+def knn16(pos: torch.Tensor, method: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """pos [N,3] float32 -> (idx [N,16] int32, d2 [N,16] float32), ascending, self first.
     Raises RuntimeError when N < 16, as the reference's topk does (egnn_layer.py:281-283)."""
     pos = _f32(pos.detach(), "knn16 pos")
@@ -682,7 +685,13 @@ def knn16(pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         raise RuntimeError(f"selected index k out of range (k={KNN_K} > n={N})")
     idx = torch.empty((N, KNN_K), dtype=torch.int32, device=pos.device)
     d2 = torch.empty((N, KNN_K), dtype=torch.float32, device=pos.device)
-    _call("eqh_knn16", 1, _p(pos), N, _p(idx), _p(d2), _stream())
+    use_grid = N >= KNN_GRID_MIN if method is None else method == "grid"
+    if use_grid:        # cell grid: same bits, O(N * neighbourhood)
+        nb = _lib.load().eqh_knn16_grid_workspace_bytes(N)
+        ws = torch.empty(nb, dtype=torch.uint8, device=pos.device)
+        _call("eqh_knn16_grid", 8, _p(pos), N, _p(idx), _p(d2), _p(ws), nb, _stream())
+    else:
+        _call("eqh_knn16", 1, _p(pos), N, _p(idx), _p(d2), _stream())
     return idx, d2
 
 

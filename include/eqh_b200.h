@@ -164,6 +164,12 @@ EQH_API int eqh_colsum_batch(const eqh_colsum_job* jobs /* host array */, int n_
  * ---------------------------------------------------------------------------------------- */
 EQH_API int eqh_knn16(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /*[N,16]*/, float* d2 /*[N,16]*/,
               eqh_stream_t stream);
+/* Same contract and same output bits through a uniform cell grid built on device (robust box, counting sort by
+ * cell, ring-by-ring search with an exact stopping bound): O(N * neighbourhood) instead of O(N^2), for the
+ * configurations with tens of thousands of atoms per batch.  ws: eqh_knn16_grid_workspace_bytes(N), 16-byte aligned. */
+EQH_API size_t eqh_knn16_grid_workspace_bytes(int64_t N);
+EQH_API int eqh_knn16_grid(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /*[N,16]*/, float* d2 /*[N,16]*/, void* ws,
+                   size_t ws_bytes, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * EGNN edge model phi_e + neighbour pooling (egnn_layer.py:298-310,357-358).

@@ -204,6 +204,44 @@ def test_knn16_golden_and_errors():
     assert float(cross) > 0.5
 
 
+@pytest.mark.parametrize("case", ["qm9_128", "pcqm_768", "mol3d_1024_padded", "opv_64", "lattice_ties", "two_clusters",
+                                  "collinear", "tiny"])
+def test_knn16_cell_grid_matches_all_pairs_scan(case):
+    """The cell-grid search returns the same bits as the all-candidates scan (and as the oracle) on every profile,
+    on ghost-padded batches (a far-away cluster the robust box must ignore), on exact ties (lattice), on degenerate
+    clouds (collinear points: zero extent on two axes) and on N barely above 16."""
+    from equihgnn_b200.graphed import bucket_of, pad_batch
+    g = torch.Generator().manual_seed(3)
+    if case == "qm9_128":
+        pos = synthetic.make_batch("qm9", 128, 5).pos
+    elif case == "pcqm_768":
+        pos = synthetic.make_batch("pcqm4mv2", 768, 6).pos
+    elif case == "mol3d_1024_padded":
+        b = synthetic.make_batch("molecule3d", 1024, 7)
+        pos = pad_batch(b, bucket_of(b)).pos
+    elif case == "opv_64":
+        pos = synthetic.make_batch("opv", 64, 8).pos
+    elif case == "lattice_ties":
+        r = torch.arange(12, dtype=torch.float32)
+        pos = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3) * 1.5
+        pos = pos[torch.randperm(pos.shape[0], generator=g)]
+    elif case == "two_clusters":
+        pos = torch.cat([torch.randn(3000, 3, generator=g), torch.randn(40, 3, generator=g) * 0.5 + 500.0])
+    elif case == "collinear":
+        pos = torch.zeros(2000, 3)
+        pos[:, 0] = torch.rand(2000, generator=g) * 100
+    else:
+        pos = torch.randn(17, 3, generator=g)
+    pos = pos.to(DEV)
+    i_scan, d_scan = ops.knn16(pos, method="scan")
+    i_grid, d_grid = ops.knn16(pos, method="grid")
+    assert torch.equal(d_scan, d_grid)
+    assert torch.equal(i_scan, i_grid)
+    if pos.shape[0] <= 25000 and case != "lattice_ties":      # (the order of exact ties is unspecified in torch.topk)
+        ridx, rd2 = R.knn(pos.cpu(), 16)
+        _assert_knn_equal(i_grid, d_grid, ridx, rd2)
+
+
 def test_knn16_ties_are_ordered_by_index():
     pos = torch.zeros(40, 3)
     pos[20:] = 1.0
