@@ -35,6 +35,7 @@ WORKLOADS = {
     "qm9_b128_mhnnm": ("qm9", 128, 1, "mhnnm"),
 }
 METRIC = "training molecules/sec (egnn_equihnns, QM9-shape)"
+NCU_TRAFFIC_BYTES = 832.7e6 + 353.4e6   # eqh_gather_reduce on the stacked workload (see roofline.traffic_source)
 
 
 def parse():
@@ -381,7 +382,12 @@ def run_b200(a):
                 "bound": "hbm", "kernel": "eqh_gather_reduce (deterministic segmented mean, the torch_scatter.scatter "
                                           "replacement, SURVEY.md 8(d) figure P)",
                 "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": d["achieved_gbs"] / peak,
-                "traffic": None, "peak_source": peak_src, "us_per_launch": d["us_per_launch"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one launch, from the
+                # `ncu --set full` capture summarised in profiles/r01_segmented_reduction_stacked_ncu.md
+                "traffic": NCU_TRAFFIC_BYTES if (stacked["Z"], stacked["C"]) == (808488, 256) else None,
+                "traffic_source": "ncu --set full (profiles/r01_segmented_reduction_stacked_ncu.md): 832.7 MB read + 353.4 MB "
+                                  "written per launch",
+                "peak_source": peak_src, "us_per_launch": d["us_per_launch"],
                 "bytes_per_launch": d["bytes_per_launch"],
                 "workload": "stacked-batch microbenchmark inside bench.py: incidence of a Molecule3D-shaped batch of 1024 "
                             "molecules stacked 12x (N=%d, E=%d, Z=%d), C=%d; 10 launches, L2 flushed between launches, "

@@ -115,7 +115,7 @@ class MHNNSConvFused(torch.autograd.Function):
         Bm = gemm_raw(Xe, True, w20[:, C:], True, inc.E, C, C, bias=b20)
         U = torch.empty((N, C), dtype=torch.float32, device=X.device)
         _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
-              mode, _p(U), _stream())                                                                # conv.py:175-177
+              mode, _p(U), _stream(), nbytes=4.0 * C * (2 * N + inc.E) + 4.0 * (inc.Z + N + 1))      # conv.py:175-177
         rowscale = inc.nonempty("v") if mode == MEAN else inc.counts("v")
         # last Linear of W2 commuted with the reduction, and the residual mix (conv.py:179) in the same epilogue
         Xm = gemm_raw(U, True, w21, True, N, C, C, bias=b21, rowscale=rowscale, out_scale=1.0 - alpha, residual=X0,
@@ -161,9 +161,11 @@ class MHNNSConvFused(torch.autograd.Function):
         part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=X.device)
         u_rp = inc.rowptr_v if mode == MEAN else None
         _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), N, C, _p(g2), _p(t2),
-              eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream())
+              eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream(),
+              nbytes=4.0 * C * (3 * N + E) + 4.0 * (inc.Z + N + 1) + 8.0 * C * partial_rows())
         _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), E, C,
-              _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream())
+              _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream(),
+              nbytes=4.0 * C * (2 * N + 2 * E) + 4.0 * (2 * inc.Z + E + 1))
         sink.affine(g2, t2, part)
         dX = gemm_raw(dA, True, w20[:, :C], False, N, C, C)
         dXe = gemm_raw(dBm, True, w20[:, C:], False, E, C, C)
