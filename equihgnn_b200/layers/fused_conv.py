@@ -144,14 +144,14 @@ class MHNNSConvFused(torch.autograd.Function):
         sink.bias(b31, dOut)
         dh3, part = _rowln_bwd(h3, g3, eps[2], dy3)
         sink.affine(g3, t3, part)
-        dXm = gemm_raw(dh3, True, w30, False, N, C, C)
+        # ---- residual mix (conv.py:179): for alpha = 0.5 both branches get 0.5 * dXm, scaled in the GEMM epilogue
+        if alpha == 0.5:
+            dXv = dX0 = gemm_raw(dh3, True, w30, False, N, C, C, out_scale=0.5)
+        else:
+            dXm = gemm_raw(dh3, True, w30, False, N, C, C)
+            dXv, dX0 = dXm * (1.0 - alpha), dXm * alpha
         sink.weight(w30, dh3, Xm)
         sink.bias(b30, dh3)
-        # ---- residual mix
-        if alpha == 0.5:
-            dXv = dX0 = dXm * 0.5
-        else:
-            dXv, dX0 = dXm * (1.0 - alpha), dXm * alpha
         # ---- W2: last Linear (commuted), fused message, split first Linear
         dU = gemm_raw(dXv, True, w21, False, N, C, C)
         sink.weight(w21, dXv, U)

@@ -247,6 +247,20 @@ def counters(n: int, device) -> torch.Tensor:
     return buf[off:off + n]
 
 
+# Set by equihgnn_b200.train.Trainer.  When True, the generic autograd Functions below (Linear, row LayerNorm, atom
+# encoder) accumulate the gradients of leaf parameters that already own a `.grad` buffer straight into it (on the side
+# stream) and return None for them, instead of handing fresh tensors to autograd's AccumulateGrad (one add launch per
+# parameter).  The layer-level Functions (layers/fused_*.py) have their own flag.
+DIRECT_PARAM_GRADS = False
+
+
+def _direct_target(p) -> Optional[torch.Tensor]:
+    """p.grad if gradients of p may be accumulated in place (see DIRECT_PARAM_GRADS)."""
+    if DIRECT_PARAM_GRADS and p is not None and p.is_leaf and p.requires_grad and p.grad is not None:
+        return p.grad
+    return None
+
+
 class _SideWork:
     """Off-critical-path work (weight / bias gradients that are accumulated straight into the flat gradient buffer)
     runs on a second stream, forked from and joined back into the step's stream with events, so that inside the
@@ -273,9 +287,17 @@ class _SideWork:
         side = self.stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         key = side.device.index
+        first = not self.pending.get(key)
         self.pending.setdefault(key, []).extend(keep)
         if not self.pending[key]:
             self.pending[key].append(None)
+        if first:
+            # whoever reads the gradients after backward() returns must see them: join at the end of this backward
+            # pass (the Trainer joins explicitly as well; a second join is a no-op)
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(lambda k=key: self.join(k))
+            except RuntimeError:
+                pass                      # not inside a backward pass: the caller joins
         return torch.cuda.stream(side)
 
     def join(self, device=None) -> None:
@@ -470,6 +492,7 @@ class _RowLayerNorm(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, relu):
+        gamma_param, beta_param = gamma, beta
         x = _f32(x, "rowln x")
         gamma = _f32(gamma, "rowln gamma")
         beta = _f32(beta, "rowln beta")
@@ -479,6 +502,7 @@ class _RowLayerNorm(torch.autograd.Function):
               nbytes=8.0 * rows * C)
         ctx.save_for_backward(x, gamma)
         ctx.eps, ctx.relu = eps, relu
+        ctx.gamma_param, ctx.beta_param = gamma_param, beta_param
         return y
 
     @staticmethod
@@ -490,6 +514,14 @@ class _RowLayerNorm(torch.autograd.Function):
         part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=x.device)
         _call("eqh_rowln_bwd", 1, _p(x), _p(gamma), ctx.eps, int(ctx.relu), _p(dy), rows, C, _p(dx), _p(part), _stream(),
               nbytes=12.0 * rows * C)
+        tg, tb = _direct_target(ctx.gamma_param), _direct_target(ctx.beta_param)
+        if tg is not None and tb is not None:
+            with side_work.fork(x.device, keep=(part,)):
+                batch = ColsumBatch(x.device)
+                batch.add(part, tg, accumulate=True, col0=0, cols=C)
+                batch.add(part, tb, accumulate=True, col0=C, cols=C)
+                batch.run()
+            return dx, None, None, None, None
         gb = colsum_raw(part)
         return dx, gb[:C], gb[C:], None, None
 
@@ -567,6 +599,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, act, residual):
+        ctx.w_param, ctx.b_param = w, b
         x = _as_gemm_operand(x)
         w = _as_gemm_operand(w)
         M, K = x.shape
@@ -594,9 +627,19 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_raw(dy, True, w, False, M, K, N)                      # dX = dY . W        (W is [N,K]: MN-major B)
-        if ctx.needs_input_grad[1]:
+        tw = _direct_target(ctx.w_param) if ctx.needs_input_grad[1] else None
+        tb = _direct_target(ctx.b_param) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        if tw is not None and _gemm_ok(tw):
+            with side_work.fork(dy.device, keep=(dy, x)):
+                gemm_raw(dy, False, x, False, N, K, M, splits=0, out=tw, residual=tw)          # dW accumulated in place
+                if tb is not None:
+                    batch = ColsumBatch(dy.device)
+                    batch.add(dy, tb, accumulate=True)
+                    batch.run()
+        elif ctx.needs_input_grad[1]:
             dw = gemm_raw(dy, False, x, False, N, K, M, splits=_wgrad_splits(N, K, M))   # dW = dY^T . X
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            tb = None
+        if tb is None and ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum_tall(dy)
         return dx, dw, db, None, dres
 
@@ -633,6 +676,7 @@ class _AtomEncode(torch.autograd.Function):
         if not x.is_cuda or x.dtype != torch.int64:
             raise RuntimeError("atom_encode: expected CUDA int64 categorical features [N,F]")
         x = x.contiguous()
+        table_params = list(tables)
         tables = [_f32(t, "atom_encode table") for t in tables]
         N, F = x.shape
         C = tables[0].shape[1]
@@ -644,6 +688,7 @@ class _AtomEncode(torch.autograd.Function):
         ctx.save_for_backward(x)
         ctx.rows = [t.shape[0] for t in tables]
         ctx.C = C
+        ctx.table_params = table_params
         return out
 
     @staticmethod
@@ -659,6 +704,16 @@ class _AtomEncode(torch.autograd.Function):
         rows_c = (ctypes.c_int32 * F)(*rows)
         _call("eqh_atom_encoder_bwd", 1, x.data_ptr(), _p(g), ctypes.cast(rows_c, ctypes.c_void_p), F, N, C, _p(part),
               _stream(), nbytes=4.0 * C * (N * F + S * R))
+        targets = [_direct_target(t) for t in ctx.table_params]
+        if all(t is not None and t.is_contiguous() for t in targets):
+            with side_work.fork(g.device, keep=(part,)):            # one launch: every table's gradient into its .grad
+                batch = ColsumBatch(g.device)
+                off = 0
+                for r, t in zip(rows, targets):
+                    batch.add(part, t.view(-1), accumulate=True, col0=off * C, cols=r * C)
+                    off += r
+                batch.run()
+            return (None,) * (1 + F)
         full = colsum_raw(part).view(R, C)
         grads, off = [], 0
         for r in rows:

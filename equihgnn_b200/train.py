@@ -59,6 +59,7 @@ class Trainer:
         for m in model.modules():       # kernels accumulate parameter gradients straight into the flat buffer
             if hasattr(m, "direct_param_grad"):
                 m.direct_param_grad = True
+        ops.DIRECT_PARAM_GRADS = True    # ... and so do the generic Linear / LayerNorm / atom-encoder Functions
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
