@@ -62,23 +62,28 @@ struct Params {
 // Epilogue of one 128 x BN tile, executed by warps 4-7 (TMEM lane quadrant = warp & 3):
 // TMEM -> registers -> (bias, act, scales) -> padded smem (`smem`, the idle operand ring) -> coalesced stores
 // (+ residual).  AM::NA accumulators of BN columns at tmem_base (see AccMap): big hi.hi tiles first, small ones after.
+// ep_tid: 0..127 index of the thread among the four epilogue warps; full_parity: phase of tmem_full to wait for;
+// tmem_empty (optional): arrived on by every epilogue thread once the accumulators are in registers / staged, so a
+// persistent kernel can start the next tile's MMAs into this buffer while the stores are still in flight.
 template <int BN, class AM>
 __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint32_t tmem_base, uint64_t* tmem_full, int warp,
-                                              int lane, int nkb, const Params& p, int m0, int n0) {
+                                              int lane, int nkb, const Params& p, int m0, int n0, int ep_tid = -1,
+                                              uint32_t full_parity = 0, uint64_t* tmem_empty = nullptr) {
+    if (ep_tid < 0) ep_tid = threadIdx.x - 128;
     // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
     constexpr int PITCH = BN + 4;
     float* stage_out = reinterpret_cast<float*>(smem);   // the operand ring is idle once tmem_full fires
     const int q = warp & 3;                              // TMEM lane quadrant this warp may read (warps 4-7 -> 0-3)
     const int row = q * 32 + lane;
     if (nkb > 0) {
-      mbar_wait(tmem_full, 0);
+      mbar_wait(tmem_full, full_parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    if (threadIdx.x == 128) EQH_STAMP(6);
+    if (ep_tid == 0) EQH_STAMP(6);
     const bool final_out = (p.ws == nullptr);
     // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
     {
-      const int tt = threadIdx.x - 128;
+      const int tt = ep_tid;
       if (tt < BN) sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -132,8 +137,12 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
         *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) =
             make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
     }
+    if (tmem_empty != nullptr) {                         // all TMEM reads of this thread are complete
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tmem_empty);
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
-    if (threadIdx.x == 128) EQH_STAMP(7);
+    if (ep_tid == 0) EQH_STAMP(7);
     float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
     const int64_t ld = final_out ? p.ldd : p.N;
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);

@@ -252,6 +252,9 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
 int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
               dim3 grid, cudaStream_t st);
 
+// gemm_ps.cu: persistent 128 x 64 variant with double-buffered accumulators (multi-wave problems, no split-K)
+int launch_ps(bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t st);
+
 // Tile width and split count.  Cost model (clocks per CTA): a 32-deep K block costs ~300 (operand split of the
 // 128-row A tile) + 6.4*BN (12 MMAs); the split-K finish costs ~4*BN per split in the last CTA.
 static void plan(int64_t M, int64_t N, int64_t K, int splits_req, int bn_req, int* bn_out, int* splits_out) {
@@ -316,6 +319,10 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   const bool smem_a = (act_flags & 0x1000) != 0 || write_hi;   // first kernel: both operands staged and split in shared memory
   int BN, s_plan;
   plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
+  // multi-wave problems without split-K: the persistent kernel (128 x 64 tiles, epilogue overlapped with the next tile)
+  const int64_t tiles64 = ((M + BM - 1) / BM) * ((N + 63) / 64);
+  const bool persistent = !smem_a && splits == 1 && bn_code == 0 && (act_flags & 0x4000) == 0 && tiles64 > 2 * kSMs;
+  if (persistent) BN = 64;
   const int kb_total = (int)((K + BK - 1) / BK);
   const int kbps = (kb_total + splits - 1) / splits;
   EQH_CHECK_ARG((kb_total + kbps - 1) / kbps == splits);          // every split owns at least one K block
@@ -339,6 +346,7 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   p.kb_per_split = kbps;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (persistent) return launch_ps(a_kmajor != 0, b_kmajor != 0, tmA, tmB, p, st);
   if (!smem_a) return launch_ts(BN, a_kmajor != 0, b_kmajor != 0, tmA, tmB, p, grid, st);
 #define EQH_GEMM_MAJORS(BNV, WHV, STG, MB)                                                            \
   do {                                                                                                \

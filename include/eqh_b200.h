@@ -234,7 +234,8 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
  *   returns the tile width the kernel will use, the effective split count and the number of output tiles.
  *   act flags: bits 0-7 activation; 0x100 store the masked hi part (verification); bits 9-10 force the tile
  *   width (1/2/3 = 32/64/128); 0x1000 first-generation kernel (both operands staged and split in shared memory;
- *   the default kernel moves A from shared memory through registers into tensor memory, gemm_ts.cu).
+ *   the default kernel moves A from shared memory through registers into tensor memory, gemm_ts.cu); 0x4000
+ *   never use the persistent variant (gemm_ps.cu: chosen automatically for multi-wave problems without split-K).
  * Ragged M / N / K are handled (TMA zero fill, bounds-checked stores).
  * ---------------------------------------------------------------------------------------- */
 EQH_API int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits_req, int flags, int* bn, int* splits, int64_t* tiles);

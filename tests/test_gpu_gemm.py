@@ -59,6 +59,27 @@ def test_gemm_every_tile_width(M, N, K, flags):
     assert rel_err(D, A.double().t() @ X.double()) < 5e-6
 
 
+@pytest.mark.parametrize("M,N,K", [(30000, 256, 256), (9700, 1088, 256), (20012, 272, 512), (40000, 64, 96)])
+def test_gemm_persistent_variant(M, N, K):
+    """Multi-wave problems run on the persistent kernel (128 x 64 tiles, double-buffered accumulators): every epilogue
+    feature, both B layouts and an MN-major A, against fp64 and against the one-tile-per-CTA kernel (flag 0x4000)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, bias, W = _mk((M, K), g), _mk((N, K), g), _mk((N,), g), _mk((K, N), g)
+    res, rs = _mk((M, N), g), torch.rand(M, generator=g).to(DEV)
+    ref = A.double() @ B.double().t()
+    D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu")
+    assert rel_err(D, torch.relu(ref + bias.double())) < 2e-6
+    assert rel_err(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu", flags=0x4000)) < 1e-6
+    assert torch.equal(D, ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu"))
+    D = ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, rowscale=rs, residual=res, out_scale=0.5, res_scale=2.0)
+    assert rel_err(D, 0.5 * (ref + bias.double() * rs.double()[:, None]) + 2.0 * res.double()) < 2e-6
+    D = ops.gemm_raw(A, True, W, False, M, N, K)                                  # MN-major B (dgrad layout)
+    assert rel_err(D, A.double() @ W.double()) < 2e-6
+    At = A.t().contiguous()                                                       # MN-major A: stored [K, M]
+    D = ops.gemm_raw(At, False, B, True, M, N, K, residual=res)
+    assert rel_err(D, ref + res.double()) < 2e-6
+
+
 def test_gemm_splitk_epilogue_in_place_and_strided():
     """Split-K finish in the last-arriving CTA: out_scale, accumulation into a strided view of a wider matrix."""
     g = torch.Generator().manual_seed(11)
