@@ -25,6 +25,7 @@ _SIGNATURES = {
     "eqh_incidence_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "eqh_incidence_build_i64": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "eqh_incidence_build_i32": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "eqh_pool_index": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P]),
     "eqh_gather_reduce": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _P, _P]),
     "eqh_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "eqh_fused_msg_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, c_int, _P, _P]),
@@ -40,6 +41,7 @@ _SIGNATURES = {
     "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
     "eqh_knn16_grid_workspace_bytes": (c_size_t, [c_int64]),
     "eqh_knn16_grid": (c_int, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "eqh_egnn_pack": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
     "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "eqh_egnn_edge_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),

@@ -254,9 +254,46 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
   if (tid < kM) row[(int64_t)(kM + 1) * H + tid] = db2;
 }
 
+// phi_e's parameters re-laid for the kernels: W1 [H0, 2C+1] -> W1a | W1b [Hp, C] (16-byte row strides for TMA) and the
+// d2 column wc [Hp]; b1 -> [Hp]; W2 [16, H0] -> [16, Hp].  Pad rows / columns are never written (they stay zero).
+__global__ void __launch_bounds__(256) k_egnn_pack(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                    const float* __restrict__ W2, int H0, int C, int Hp, float* __restrict__ W1a,
+                                                    float* __restrict__ W1b, float* __restrict__ wc, float* __restrict__ b1p,
+                                                    float* __restrict__ W2p) {
+  pdl_prologue();
+  const int64_t ld = 2 * (int64_t)C + 1;
+  const int64_t n1 = (int64_t)H0 * ld, n2 = n1 + H0, n3 = n2 + (int64_t)kM * H0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < n1) {
+      const int64_t r = t / ld, c = t - r * ld;
+      const float v = __ldg(W1 + t);
+      if (c < C) W1a[r * C + c] = v;
+      else if (c < 2 * C) W1b[r * C + (c - C)] = v;
+      else wc[r] = v;
+    } else if (t < n2) {
+      b1p[t - n1] = __ldg(b1 + (t - n1));
+    } else {
+      const int64_t u = t - n2, o = u / H0, h = u - o * H0;
+      W2p[o * Hp + h] = __ldg(W2 + u);
+    }
+  }
+}
+
 }  // namespace eqh
 
 extern "C" {
+
+int eqh_egnn_pack(const float* W1, const float* b1, const float* W2, int64_t H0, int64_t C, int64_t Hp, float* W1a, float* W1b,
+                  float* wc, float* b1p, float* W2p, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(W1 && b1 && W2 && W1a && W1b && wc && b1p && W2p && H0 > 0 && C > 0 && Hp >= H0);
+  const int64_t n = H0 * (2 * C + 1) + H0 + (int64_t)kM * H0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  launch_kernel(k_egnn_pack, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), W1, b1, W2, (int)H0, (int)C,
+                (int)Hp, W1a, W1b, wc, b1p, W2p);
+  EQH_LAUNCH_RC();
+}
 
 size_t eqh_egnn_edge_fwd_smem_bytes(int64_t H) {
   return H > 0 ? sizeof(float) * (size_t)H * (eqh::kPitch + 1) : 0;

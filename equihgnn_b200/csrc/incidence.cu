@@ -122,9 +122,29 @@ static int build(const IdxT* dst, const IdxT* other, int64_t Z, int64_t n_dst, i
   EQH_LAUNCH_RC();
 }
 
+// global_add_pool over a PyG batch: `batch` is sorted, so the CSR of the pooling is `ptr` itself with the identity
+// permutation -- only the int64 -> int32 narrowing is left (one launch instead of the 4-kernel counting sort).
+__global__ void __launch_bounds__(256) k_pool_index(const int64_t* __restrict__ ptr, int64_t nb1, const int64_t* __restrict__ batch,
+                                                     int64_t n, int32_t* __restrict__ rowptr32, int32_t* __restrict__ batch32) {
+  pdl_prologue();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nb1) rowptr32[t] = (int32_t)ptr[t];
+  if (t < n) batch32[t] = (int32_t)batch[t];
+}
+
 }  // namespace eqh
 
 extern "C" {
+
+int eqh_pool_index(const int64_t* ptr, int64_t num_graphs, const int64_t* batch, int64_t n, int32_t* rowptr32,
+                   int32_t* batch32, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(ptr && batch && rowptr32 && batch32 && num_graphs >= 0 && n >= 0 && n < ((int64_t)1 << 31));
+  const int64_t m = (num_graphs + 1 > n ? num_graphs + 1 : n);
+  launch_kernel(k_pool_index, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), ptr,
+                num_graphs + 1, batch, n, rowptr32, batch32);
+  EQH_LAUNCH_RC();
+}
 
 size_t eqh_incidence_workspace_bytes(int64_t Z, int64_t n_dst) {
   if (Z < 0 || n_dst < 0) return 0;

@@ -71,7 +71,7 @@ def pad_batch(b: HBatch, bucket: Tuple[int, int, int]) -> HBatch:
 
 
 _ALL = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "n_e", "e_order", "batch", "ptr", "y")
-_FIELDS = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "batch", "y")   # what the model wrappers read
+_FIELDS = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "batch", "ptr", "y")   # what the model wrappers read
 
 
 def step_input_bytes(b: HBatch) -> int:

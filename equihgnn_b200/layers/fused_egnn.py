@@ -28,12 +28,8 @@ class EGNNFused(torch.autograd.Function):
         Hp = bufs["W1a"].shape[0]
         # refresh the packed copies of phi_e's weights (TMA needs 16-byte row strides; 2C+1 floats is not)
         W1a, W1b, wc, b1p, W2p = bufs["W1a"], bufs["W1b"], bufs["wc"], bufs["b1"], bufs["W2"]
-        with torch.no_grad():
-            W1a[:H0].copy_(w1[:, :C])
-            W1b[:H0].copy_(w1[:, C:2 * C])
-            wc[:H0].copy_(w1[:, 2 * C])
-            b1p[:H0].copy_(b1)
-            W2p[:, :H0].copy_(w2)
+        _call("eqh_egnn_pack", 1, _p(ops._f32(w1, "edge_mlp.0.weight")), _p(ops._f32(b1, "edge_mlp.0.bias")),
+              _p(ops._f32(w2, "edge_mlp.3.weight")), H0, C, Hp, _p(W1a), _p(W1b), _p(wc), _p(b1p), _p(W2p), _stream())
         P = gemm_raw(h, True, W1a, True, N, Hp, C, bias=b1p)
         Q = gemm_raw(h, True, W1b, True, N, Hp, C)
         dev = h.device

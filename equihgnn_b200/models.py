@@ -94,7 +94,7 @@ class EGNNEquiHNNS(nn.Module):
             x = self.conv(x, V, E, x0, incidence=inc)
             x = self.act(x)
         x = self.dropout(x)
-        x = ops.global_add_pool(x, data.batch, _num_graphs(data))
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None))
         return self.mlp_out(x).view(-1)
 
 
@@ -141,7 +141,7 @@ class MHNNM(nn.Module):
                 x, e = self.dropout(x), self.dropout(e)
             else:
                 x, e = self.dropout(self.act(x)), self.dropout(self.act(e))
-        x = ops.global_add_pool(x, data.batch, _num_graphs(data))
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None))
         return self.mlp_out(x).view(-1)
 
 

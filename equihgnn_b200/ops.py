@@ -922,8 +922,17 @@ class _PoolCache:
 _pool_cache = _PoolCache()
 
 
-def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = None) -> torch.Tensor:
-    """Drop-in for torch_geometric.nn.global_add_pool (mhnn.py:216, equihnn_egnn.py:167)."""
+def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = None,
+                    ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for torch_geometric.nn.global_add_pool (mhnn.py:216, equihnn_egnn.py:167).  With the batch's `ptr`
+    (PyG Batch.ptr, int64 [num_graphs+1]) the sorted `batch` vector needs no grouping pass: ptr IS the CSR."""
+    if ptr is not None and size is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == size + 1 \
+            and batch.dtype == torch.int64:
+        rowptr = torch.empty(size + 1, dtype=torch.int32, device=x.device)
+        dst32 = torch.empty(batch.numel(), dtype=torch.int32, device=x.device)
+        _call("eqh_pool_index", 1, _p(ptr.contiguous()), size, _p(batch.contiguous()), batch.numel(), _p(rowptr), _p(dst32),
+              _stream())
+        return segment_reduce(x, rowptr, None, dst32, size, "sum")
     n, rowptr, perm, dst32 = _pool_cache.get(batch, size)
     return segment_reduce(x, rowptr, perm, dst32, n, "sum")
 

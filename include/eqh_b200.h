@@ -72,6 +72,11 @@ EQH_API int eqh_incidence_build_i32(const int32_t* dst, const int32_t* other, in
                             int32_t* perm, int32_t* dst32, int32_t* other_sorted, int32_t* status, void* ws,
                             size_t ws_bytes, eqh_stream_t stream);
 
+/* Pooling index of a PyG batch (global_add_pool, mhnn.py:216, equihnn_egnn.py:167): `batch` [n] is sorted, so the CSR
+ * of the pooling is `ptr` [num_graphs+1] with the identity permutation; this only narrows both to int32. */
+EQH_API int eqh_pool_index(const int64_t* ptr, int64_t num_graphs, const int64_t* batch, int64_t n, int32_t* rowptr32,
+                   int32_t* batch32, eqh_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Deterministic segmented reduction (no atomics), the replacement of
  * torch_scatter.scatter(src, index, dim=-2, reduce="sum"|"mean") (conv.py:91-93,97,173,177)
@@ -180,6 +185,11 @@ EQH_API int eqh_knn16_grid(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /
  *     m_ij = silu(s2) ;  m_i = sum_k m_ij      (m_pool_method="sum")
  *   S2 [N*16,16] (pre-activations) is kept for the backward; Mij [N*16,16] (optional) feeds phi_x.
  * ---------------------------------------------------------------------------------------- */
+/* Re-lay phi_e's parameters for the kernels in one launch: edge_mlp.0.weight W1 [H0, 2C+1] -> W1a | W1b [Hp, C] and the
+ * d2 column wc [Hp]; edge_mlp.0.bias -> b1p [Hp]; edge_mlp.3.weight W2 [16, H0] -> W2p [16, Hp] (Hp = H0 rounded up to
+ * 64; the caller zeroes the destination buffers once, pad entries are never written). */
+EQH_API int eqh_egnn_pack(const float* W1, const float* b1, const float* W2, int64_t H0, int64_t C, int64_t Hp, float* W1a,
+                  float* W1b, float* wc, float* b1p, float* W2p, eqh_stream_t stream);
 EQH_API int eqh_egnn_edge_fwd(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                       const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
                       float* Mi, eqh_stream_t stream);
