@@ -38,7 +38,7 @@ class _GradSink:
         self.direct = direct
         # direct mode: nobody reads the gradients before the optimizer, so they are produced on the side stream
         # (a parallel branch of the captured graph) and joined by the Trainer
-        self.side = direct and ops.side_work.enabled
+        self.side = direct        # (ops.side_work.fork degrades to the current stream outside graph capture)
         self.out = {}
         for p in params:
             if direct:

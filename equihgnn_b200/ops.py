@@ -7,6 +7,7 @@ sm_100a kernel in csrc/.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import weakref
 from dataclasses import dataclass
@@ -271,6 +272,7 @@ class _SideWork:
         self.streams = {}
         self.pending = {}
         self.enabled = os.environ.get("EQH_SIDE_STREAM", "1") != "0"
+        self.always = os.environ.get("EQH_SIDE_STREAM", "1") == "always"      # also outside graph capture (tests)
 
     def stream(self, device) -> torch.cuda.Stream:
         key = torch.device(device).index
@@ -283,7 +285,10 @@ class _SideWork:
 
     def fork(self, device, keep=()):
         """Context manager: work issued inside runs on the side stream after everything issued so far on the
-        current stream."""
+        current stream.  Only while a CUDA graph is being captured (where the fork becomes a parallel branch for free):
+        an eager step is bound by the host's launch rate, and the extra event record / wait per fork only slows it."""
+        if not self.enabled or not (self.always or torch.cuda.is_current_stream_capturing()):
+            return contextlib.nullcontext()
         side = self.stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         key = side.device.index

@@ -344,6 +344,7 @@ def test_trainer_direct_gradient_path_matches_autograd_and_oracle(side, monkeypa
     must equal the gradients of the plain autograd path of the same modules and those of the CPU oracle."""
     from equihgnn_b200.train import Trainer
     monkeypatch.setattr(ops.side_work, "enabled", side == "1")
+    monkeypatch.setattr(ops.side_work, "always", side == "1")        # exercise the side stream outside graph capture too
     C, B = 64, 32
     b = synthetic.make_batch("qm9", B, 4242)
     args = synthetic.model_args(hidden=C)
