@@ -37,7 +37,9 @@ constexpr unsigned kFull = 0xffffffffu;
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
+#ifndef EQH_PDL_NO_EARLY_TRIGGER
   pdl_launch_dependents();
+#endif
   pdl_wait();
 }
 
