@@ -257,10 +257,29 @@ int launch_ps(bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtens
 
 // Tile width and split count.  Cost model (clocks per CTA): a 32-deep K block costs ~300 (operand split of the
 // 128-row A tile) + 6.4*BN (12 MMAs); the split-K finish costs ~4*BN per split in the last CTA.
-static void plan(int64_t M, int64_t N, int64_t K, int splits_req, int bn_req, int* bn_out, int* splits_out) {
+static void plan(int64_t M, int64_t N, int64_t K, int splits_req, int bn_req, int* bn_out, int* splits_out,
+                 bool background = false) {
   const int64_t tiles_m = (M + BM - 1) / BM, kb = (K + BK - 1) / BK;
   double best = 1e300;
   int best_bn = 128, best_s = 1;
+  if (background && splits_req == 0) {
+    // A GEMM issued on the side stream (weight gradients) is not on the critical path: its latency is hidden, its SM
+    // time is not -- 144 CTAs for 12 us keep every SM away from the dX chain.  Minimise CTAs x duration instead:
+    // ~24 K blocks per CTA (~12 us), the widest tile.
+    for (int bn = 128; bn >= 32; bn >>= 1) {
+      if (bn_req && bn != bn_req) continue;
+      if (!bn_req && bn > 32 && bn / 2 >= N) continue;
+      const int64_t t = tiles_m * ((N + bn - 1) / bn);
+      int64_t s = (kb + 23) / 24;
+      s = s < 1 ? 1 : (s > 32 ? 32 : s);
+      const int64_t kbps = (kb + s - 1) / s, s_eff = (kb + kbps - 1) / kbps;
+      const double cost = (double)(t * s_eff) * ((double)kbps * (300.0 + 6.4 * bn) + 1500.0 + (s_eff > 1 ? 4.0 * bn * s_eff : 0.0));
+      if (cost < best - 1e-9) { best = cost; best_bn = bn; best_s = (int)s_eff; }
+    }
+    *bn_out = best_bn;
+    *splits_out = best_s;
+    return;
+  }
   for (int bn = 128; bn >= 32; bn >>= 1) {
     if (bn_req && bn != bn_req) continue;
     if (!bn_req && bn > 32 && bn / 2 >= N) continue;               // do not pad N by more than 2x
@@ -293,7 +312,7 @@ int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits, int flags, int* b
   using namespace eqh;
   EQH_CHECK_ARG(M > 0 && N > 0 && K > 0 && splits >= 0 && bn && splits_out && tiles);
   const int code = (flags >> 9) & 3;
-  gemm::plan(M, N, K, splits, (flags & 0x100) ? 128 : (code ? (16 << code) : 0), bn, splits_out);
+  gemm::plan(M, N, K, splits, (flags & 0x100) ? 128 : (code ? (16 << code) : 0), bn, splits_out, (flags & 0x8000) != 0);
   *tiles = ((M + gemm::BM - 1) / gemm::BM) * ((N + *bn - 1) / *bn);
   return EQH_OK;
 }
@@ -318,7 +337,12 @@ int eqh_gemm_tf32x3(const float* A, int a_kmajor, int64_t lda, const float* B, i
   const bool write_hi = (act_flags & 0x100) != 0;       // debug/verification switch, see kWriteHi
   const bool smem_a = (act_flags & 0x1000) != 0 || write_hi;   // first kernel: both operands staged and split in shared memory
   int BN, s_plan;
-  plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
+  if ((act_flags & 0x8000) != 0) {      // background plan: the caller passes the split count eqh_gemm_plan returned
+    plan(M, N, K, 0, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan, true);
+    EQH_CHECK_ARG(s_plan == splits);
+  } else {
+    plan(M, N, K, splits, write_hi ? 128 : (bn_code ? (16 << bn_code) : 0), &BN, &s_plan);
+  }
   // multi-wave problems without split-K: the persistent kernel (128 x 64 tiles, epilogue overlapped with the next tile)
   const int64_t tiles64 = ((M + BM - 1) / BM) * ((N + 63) / 64);
   const bool persistent = !smem_a && splits == 1 && bn_code == 0 && (act_flags & 0x4000) == 0 && tiles64 > 2 * kSMs;

@@ -273,6 +273,7 @@ class _SideWork:
         self.pending = {}
         self.enabled = os.environ.get("EQH_SIDE_STREAM", "1") != "0"
         self.always = os.environ.get("EQH_SIDE_STREAM", "1") == "always"      # also outside graph capture (tests)
+        self.active = 0
 
     def stream(self, device) -> torch.cuda.Stream:
         key = torch.device(device).index
@@ -289,6 +290,10 @@ class _SideWork:
         an eager step is bound by the host's launch rate, and the extra event record / wait per fork only slows it."""
         if not self.enabled or not (self.always or torch.cuda.is_current_stream_capturing()):
             return contextlib.nullcontext()
+        return self._forked(device, keep)
+
+    @contextlib.contextmanager
+    def _forked(self, device, keep):
         side = self.stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         key = side.device.index
@@ -303,7 +308,12 @@ class _SideWork:
                 torch.autograd.Variable._execution_engine.queue_callback(lambda k=key: self.join(k))
             except RuntimeError:
                 pass                      # not inside a backward pass: the caller joins
-        return torch.cuda.stream(side)
+        self.active += 1                  # GEMMs planned inside are "background" work (see eqh_gemm_plan flag 0x8000)
+        try:
+            with torch.cuda.stream(side):
+                yield
+        finally:
+            self.active -= 1
 
     def join(self, device=None) -> None:
         """Make the current stream wait for all side work issued so far (no-op when there is none)."""
@@ -546,6 +556,7 @@ _ACT = {None: 0, "none": 0, "relu": 1, "silu": 2}
 SM_COUNT = 148
 
 
+BACKGROUND_WGRAD = os.environ.get("EQH_BACKGROUND_WGRAD", "0") != "0"   # measured slower: the side-stream tail gates the step
 GEMM_FLAGS = int(os.environ.get("EQH_GEMM_FLAGS", "0"), 0)     # tuning: forced tile width / kernel variant
 
 
@@ -571,6 +582,8 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
     if residual is not None and residual.stride(0) != ldd:
         raise RuntimeError("gemm_raw: residual must have the row stride of the output")
     fl = (GEMM_FLAGS if flags is None else flags) | _ACT[act] | (0x100 if write_hi else 0)
+    if side_work.active and splits == 0 and BACKGROUND_WGRAD:
+        fl |= 0x8000                  # side-stream weight gradient: plan for SM time, not latency
     ws = cnt = None
     if splits != 1:
         _, splits, tiles = gemm_plan(M, N, K, splits, fl)

@@ -245,7 +245,9 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
  *   act flags: bits 0-7 activation; 0x100 store the masked hi part (verification); bits 9-10 force the tile
  *   width (1/2/3 = 32/64/128); 0x1000 first-generation kernel (both operands staged and split in shared memory;
  *   the default kernel moves A from shared memory through registers into tensor memory, gemm_ts.cu); 0x4000
- *   never use the persistent variant (gemm_ps.cu: chosen automatically for multi-wave problems without split-K).
+ *   never use the persistent variant (gemm_ps.cu: chosen automatically for multi-wave problems without split-K);
+ *   0x8000 (eqh_gemm_plan with splits_req 0) background GEMM: minimise CTAs x duration instead of latency (weight
+ *   gradients issued on a side stream next to the critical path).
  * Ragged M / N / K are handled (TMA zero fill, bounds-checked stores).
  * ---------------------------------------------------------------------------------------- */
 EQH_API int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits_req, int flags, int* bn, int* splits, int64_t* tiles);

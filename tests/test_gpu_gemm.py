@@ -80,6 +80,21 @@ def test_gemm_persistent_variant(M, N, K):
     assert rel_err(D, ref + res.double()) < 2e-6
 
 
+@pytest.mark.parametrize("R,N,K", [(2341, 256, 256), (30000, 1088, 256), (2341, 1026, 256), (300, 64, 272)])
+def test_gemm_background_plan(R, N, K):
+    """Optional planning mode for side-stream weight gradients: SM time (few CTAs, ~24 K blocks each) instead of latency.
+    (Off by default: measured slower on the whole step, the side-stream tail gates it.)"""
+    g = torch.Generator().manual_seed(R + N + K)
+    dY, X = _mk((R, N), g), _mk((R, K), g)
+    D = ops.gemm_raw(dY, False, X, False, N, K, R, splits=0, flags=0x8000)
+    assert rel_err(D, dY.double().t() @ X.double()) < 5e-6
+    assert torch.equal(D, ops.gemm_raw(dY, False, X, False, N, K, R, splits=0, flags=0x8000))
+    bn_b, s_b, t_b = ops.gemm_plan(N, K, R, 0, 0x8000)
+    bn_l, s_l, t_l = ops.gemm_plan(N, K, R, 0, 0)
+    if R <= 5000:
+        assert t_b * s_b <= t_l * s_l
+
+
 def test_gemm_splitk_epilogue_in_place_and_strided():
     """Split-K finish in the last-arriving CTA: out_scale, accumulation into a strided view of a wider matrix."""
     g = torch.Generator().manual_seed(11)
