@@ -80,7 +80,7 @@ def test_gemm_persistent_variant(M, N, K):
     assert rel_err(D, ref + res.double()) < 2e-6
 
 
-@pytest.mark.parametrize("R,N,K", [(2341, 256, 256), (30000, 1088, 256), (2341, 1026, 256), (300, 64, 272)])
+@pytest.mark.parametrize("R,N,K", [(2341, 256, 256), (30000, 1088, 256), (2341, 1028, 256), (300, 64, 272)])
 def test_gemm_background_plan(R, N, K):
     """Optional planning mode for side-stream weight gradients: SM time (few CTAs, ~24 K blocks each) instead of latency.
     (Off by default: measured slower on the whole step, the side-stream tail gates it.)"""
