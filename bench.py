@@ -267,13 +267,13 @@ def run_b200(a):
         # collation pads every batch to its shape bucket with an inert ghost molecule (graphed.py)
         from equihgnn_b200.graphed import GraphedTrainer, bucket_of, pad_batch, step_input_bytes
         trainer = GraphedTrainer(model, real_graphs=B, lr=1e-4)
-        host = [pad_batch(b, bucket_of(b)).pin_memory() for b in raw]
-        h2d_bytes = sum(step_input_bytes(h) for h in host) / len(host)
+        host = [pad_batch(b, bucket_of(b)).pack(pin=True) for b in raw]        # one pinned buffer per collated batch
+        h2d_bytes = sum(h._flat.numel() for h in host) / len(host)
     else:
         trainer = Trainer(model, lr=1e-4)
         host = [b.pin_memory() for b in raw]
         h2d_bytes = sum(h.h2d_bytes() for h in host) / len(host)
-    resident = [h.to(dev) for h in host]
+    resident = [h.pack(device=dev) if graphed else h.to(dev) for h in host]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def flush_l2():

@@ -108,10 +108,9 @@ class GraphedTrainer(Trainer):
 
     def _capture(self, like: HBatch) -> _Bucket:
         dev = self.fp.flat.device
-        static = HBatch(**{f: torch.empty_like(getattr(like, f), device=dev) for f in _ALL},
-                        num_graphs=like.num_graphs)
-        for f in _ALL:
-            getattr(static, f).copy_(getattr(like, f))
+        # static inputs: one contiguous buffer with every field a view into it (HBatch.pack), so a packed batch of the
+        # same shapes arrives with a single copy
+        static = like.pack(device=dev)
         # warm-up on a side stream (cuBLAS workspaces, autograd buffers), then capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -135,8 +134,12 @@ class GraphedTrainer(Trainer):
 
     def forward_backward(self, data: HBatch) -> torch.Tensor:
         bk = self._bucket(data)
-        for f in _FIELDS:                                   # D2D (resident batch) or H2D (pinned host batch)
-            getattr(bk.static, f).copy_(getattr(data, f), non_blocking=True)
+        flat = getattr(data, "_flat", None)
+        if flat is not None and flat.numel() == bk.static._flat.numel():
+            bk.static._flat.copy_(flat, non_blocking=True)  # one copy: D2D (resident batch) or H2D (pinned host batch)
+        else:
+            for f in _FIELDS:
+                getattr(bk.static, f).copy_(getattr(data, f), non_blocking=True)
         bk.graph.replay()
         self.replays += 1
         self.own_launches += bk.launches

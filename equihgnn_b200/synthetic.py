@@ -75,6 +75,29 @@ class HBatch:
             kw[f.name] = v.pin_memory() if isinstance(v, torch.Tensor) else v
         return HBatch(**kw)
 
+    def pack(self, device=None, pin: bool = False) -> "HBatch":
+        """The same batch with every tensor a view into ONE contiguous buffer (16-byte aligned fields, fixed order), so
+        that a whole batch moves with a single copy: pinned host -> device, or device -> the static inputs of a captured
+        graph.  Batches of equal shapes have equal layouts.  The buffer is kept as `._flat`."""
+        names = [f.name for f in fields(self) if isinstance(getattr(self, f.name), torch.Tensor)]
+        offs, total = [], 0
+        for n in names:
+            t = getattr(self, n)
+            total = (total + 15) // 16 * 16
+            offs.append(total)
+            total += t.numel() * t.element_size()
+        flat = torch.empty(total, dtype=torch.uint8, device=device if device is not None else "cpu",
+                           pin_memory=bool(pin and device is None))
+        kw = {}
+        for n, o in zip(names, offs):
+            t = getattr(self, n)
+            v = flat[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t)
+            kw[n] = v
+        out = HBatch(**kw, num_graphs=self.num_graphs)
+        out._flat = flat
+        return out
+
     def h2d_bytes(self) -> int:
         return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size()
                    for f in fields(self) if isinstance(getattr(self, f.name), torch.Tensor))
