@@ -171,6 +171,8 @@ def _oracle_run(fn, sd, b, dtype, nbhd):
     ("egnn_equihnns", EGNNEquiHNNS, R.egnn_equihnns, "qm9", 128, 256),        # BASELINE config 2, script sizes
     ("mhnnm", MHNNM, R.mhnnm, "qm9", 128, 256),                              # BASELINE config 1
     ("egnn_equihnns", EGNNEquiHNNS, R.egnn_equihnns, "opv", 8, 64),          # long conjugated hyperedges
+    # N ~ 8.7k atoms: the cell-grid kNN and the persistent GEMM (P / Q of phi_e) inside the whole model
+    ("egnn_equihnns", EGNNEquiHNNS, R.egnn_equihnns, "molecule3d", 300, 256),
 ])
 def test_models_vs_oracle_at_baseline_sizes(method, cls, fn, profile, B, C):
     """Whole training step at BASELINE.json sizes.  A 3-layer ReLU/LayerNorm network in fp32 is not
@@ -207,7 +209,13 @@ def test_models_vs_oracle_at_baseline_sizes(method, cls, fn, profile, B, C):
         den = max(float(g64[k].abs().max()), 0.05 * scale)
         e_gpu = float((got[k].double().cpu() - g64[k]).abs().max()) / den
         e_ref = float((g32[k].double() - g64[k]).abs().max()) / den
-        if e_gpu > max(1e-4, 8 * e_ref):
+        # Floor: one ReLU whose pre-activation lies within fp32 rounding of zero flips its gate and changes every weight
+        # gradient below it by a rank-1 term of relative size ~1e-4..1e-3.  With N*C*9 ~ 2e7 ReLU inputs (N ~ 8.7k) a
+        # few such flips are certain for ANY fp32 implementation: over seeds the fp32 oracle itself jumps between 4e-7
+        # (no flip) and 5e-4 (scratch/dbg_m3d2.py), so at that size e_ref of one seed is not a usable yardstick.  The
+        # layers above the pooling (129 rows, no flips observed) keep the strict bar.
+        floor = 1e-4 if (b.num_atoms < 5000 or k.startswith("mlp_out")) else 5e-3
+        if e_gpu > max(floor, 8 * e_ref):
             bad[k] = (e_gpu, e_ref)
     assert not bad, dict(sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
     # determinism: a second identical step is bit-identical (atomics-free path)
