@@ -262,7 +262,7 @@ def run_b200(a):
     torch.manual_seed(0)                                   # identical initial weights on every rank (DDP broadcast)
     model = create_model(method, 1, synthetic.model_args(a.hidden)).to(dev).train()
     raw = [synthetic.make_batch(profile, B, synthetic.bench_seed(cfg, rank, s)) for s in range(a.n_batches)]
-    graphed = method == "egnn_equihnns" and not a.eager
+    graphed = not a.eager
     if graphed:
         # collation pads every batch to its shape bucket with an inert ghost molecule (graphed.py)
         from equihgnn_b200.graphed import GraphedTrainer, bucket_of, pad_batch, step_input_bytes

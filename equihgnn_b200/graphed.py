@@ -15,8 +15,9 @@ Variable batch shapes vs static graphs: a batch is padded on the host to its buc
     incidence CSR is unchanged;
   * the ghost molecule is graph id B and is excluded from the loss, so every gradient that flows
     through a ghost row is exactly zero.
-Nothing in the kernels knows about padding.  BatchNorm over atom rows (mhnnm) would see the
-ghost rows, so MHNNM is only graphed with exact (unpadded) shapes.
+Nothing in the kernels knows about padding.  BatchNorm over atom rows (mhnnm) is the one operator whose
+result depends on every row: MHNNM evaluates it with the ghost rows masked out of the batch statistics
+(models.masked_batch_norm), so that the real rows get exactly the unpadded result.
 """
 from __future__ import annotations
 
@@ -67,7 +68,7 @@ def pad_batch(b: HBatch, bucket: Tuple[int, int, int]) -> HBatch:
         batch=torch.cat([b.batch, torch.full((ga,), B, dtype=b.batch.dtype)]),
         ptr=torch.cat([b.ptr, torch.tensor([Np], dtype=b.ptr.dtype)]),
         y=torch.cat([b.y, torch.zeros(1, dtype=b.y.dtype)]),
-        num_graphs=B + 1)
+        num_graphs=B + 1, num_real_graphs=B)
 
 
 _ALL = ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "n_e", "e_order", "batch", "ptr", "y")
@@ -111,7 +112,9 @@ class GraphedTrainer(Trainer):
         # static inputs: one contiguous buffer with every field a view into it (HBatch.pack), so a packed batch of the
         # same shapes arrives with a single copy
         static = like.pack(device=dev)
-        # warm-up on a side stream (cuBLAS workspaces, autograd buffers), then capture
+        # warm-up on a side stream (cuBLAS workspaces, autograd buffers), then capture.  The warm-up steps must leave
+        # no trace: module buffers (BatchNorm running statistics of mhnnm) are restored afterwards.
+        buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -119,6 +122,9 @@ class GraphedTrainer(Trainer):
                 self._fwd_bwd(static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            for b, saved in buffers:
+                b.copy_(saved)
         g = torch.cuda.CUDAGraph()
         before = ops.STATS["launches"]
         with torch.cuda.graph(g):        # private pool per bucket: buckets may replay in any order

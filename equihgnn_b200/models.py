@@ -56,6 +56,28 @@ def _num_graphs(data):
     return int(ng) if ng else None
 
 
+def masked_batch_norm(x: torch.Tensor, bn: nn.BatchNorm1d, mask: torch.Tensor) -> torch.Tensor:
+    """nn.BatchNorm1d over the rows with mask == 1 only (mhnn.py:182,206 on a ghost-padded batch): batch statistics,
+    running-statistics update (momentum, unbiased variance) and normalisation as torch's BatchNorm1d, with the ghost
+    rows excluded from the statistics; their own outputs are irrelevant (they only reach ghost hyperedges and the
+    ghost molecule, which is not in the loss)."""
+    if not bn.training:
+        return bn(x)
+    m = mask.to(x.dtype).unsqueeze(-1)
+    n = m.sum()
+    mean = (x * m).sum(0) / n
+    xc = x - mean
+    var = (xc * xc * m).sum(0) / n                                   # biased: what BatchNorm normalises with
+    if bn.track_running_stats:
+        with torch.no_grad():
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - mom).add_(mean * mom)
+            bn.running_var.mul_(1 - mom).add_(var * (n / (n - 1)) * mom)
+            bn.num_batches_tracked.add_(1)
+    y = xc * torch.rsqrt(var + bn.eps)
+    return y * bn.weight + bn.bias if bn.affine else y
+
+
 class EGNNEquiHNNS(nn.Module):
     """`--method egnn_equihnns` (equihnn_egnn.py:98-169)."""
 
@@ -134,9 +156,11 @@ class MHNNM(nn.Module):
         x = self.atom_encoder(data.x)
         e = self.bond_encoder(data.edge_attr.reshape(-1))
         inc = ops.build_incidence(V, E, N, e.shape[0])
+        real = int(getattr(data, "num_real_graphs", 0) or 0)
+        mask = (data.batch < real) if real else None                  # ghost-padded batch: keep ghosts out of BatchNorm
         for i, layer in enumerate(self.layers):
             x, e = layer(x, e, V, E, incidence=inc)
-            x = self.batch_norms[i](x)
+            x = self.batch_norms[i](x) if mask is None else masked_batch_norm(x, self.batch_norms[i], mask)
             if i == self.nlayer - 1:
                 x, e = self.dropout(x), self.dropout(e)
             else:

@@ -48,6 +48,7 @@ class HBatch:
     ptr: torch.Tensor          # [B+1] int64 atom offsets
     y: torch.Tensor            # [B] float32
     num_graphs: int = 0
+    num_real_graphs: int = 0   # > 0 on ghost-padded batches (graphed.pad_batch): molecules [0, num_real_graphs) are real
 
     @property
     def num_atoms(self) -> int:
@@ -94,7 +95,7 @@ class HBatch:
             v = flat[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
             v.copy_(t)
             kw[n] = v
-        out = HBatch(**kw, num_graphs=self.num_graphs)
+        out = HBatch(**kw, num_graphs=self.num_graphs, num_real_graphs=self.num_real_graphs)
         out._flat = flat
         return out
 
