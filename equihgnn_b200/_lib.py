@@ -41,11 +41,14 @@ _SIGNATURES = {
     "eqh_knn16": (c_int, [_P, c_int64, _P, _P, _P]),
     "eqh_knn16_grid_workspace_bytes": (c_size_t, [c_int64]),
     "eqh_knn16_grid": (c_int, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "eqh_knn16_grid_ordered": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "eqh_egnn_pack": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
     "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "eqh_egnn_edge_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "eqh_egnn_edge_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "eqh_egnn_edge_fwd_tc_ordered": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "eqh_egnn_edge_bwd_ordered": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "eqh_atom_encoder_slices": (c_int, [c_int64]),
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),

@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
                                                    const float* __restrict__ S2, const float* __restrict__ dMi,
                                                    const float* __restrict__ dMij, int64_t N, int H,
                                                    float* __restrict__ dP, float* __restrict__ dPre,
-                                                   float* __restrict__ dd2, float* __restrict__ part) {
+                                                   float* __restrict__ dd2, float* __restrict__ part,
+                                                   const int32_t* __restrict__ order) {
   pdl_prologue();
   __shared__ __align__(16) float ds2s[kNbr][kM];
   __shared__ float dd2s[kBwdMaxThreads / 32][kNbr];
@@ -161,7 +162,10 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
   }
   float db2 = 0.f;  // threads < 16
 
-  for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+  for (int64_t slot = blockIdx.x; slot < N; slot += gridDim.x) {
+    // atoms in `order` (the cell order of the kNN grid) when given: the CTAs running side by side work on spatially
+    // close atoms, whose neighbour rows Q[j] overlap and hit in L2
+    const int64_t i = order ? (int64_t)__ldg(order + slot) : slot;
     __syncthreads();  // previous atom's readers of ds2s/js/dds are done
     for (int t = tid; t < kNbr * kM; t += T) {
       const int k = t >> 4, o = t & 15;
@@ -321,6 +325,13 @@ int eqh_egnn_edge_fwd(const float* P, const float* Q, const float* wc, const flo
 int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                       const int32_t* idx, const float* d2, const float* S2, const float* dMi, const float* dMij,
                       int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, eqh_stream_t stream) {
+  return eqh_egnn_edge_bwd_ordered(P, Q, wc, W2, b2, idx, d2, S2, dMi, dMij, N, H, dP, dPre, dd2, part, nullptr, stream);
+}
+
+int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                              const int32_t* idx, const float* d2, const float* S2, const float* dMi, const float* dMij,
+                              int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, const int32_t* order,
+                              eqh_stream_t stream) {
   using namespace eqh;
   (void)b2;
   EQH_CHECK_ARG(P && Q && wc && W2 && idx && d2 && S2 && dP && dPre && part && N >= 0);
@@ -332,7 +343,7 @@ int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, const flo
   T = (T + 31) / 32 * 32;
   const unsigned grid = kPartialRows;  // every CTA writes its partial row (zeros when it owns no atom)
 #define EQH_BWD(HCV)                                                                                              \
-  launch_kernel(k_edge_bwd<HCV>, dim3(grid), dim3(T), 0, st, P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, dd2, part)
+  launch_kernel(k_edge_bwd<HCV>, dim3(grid), dim3(T), 0, st, P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, dd2, part, order)
   switch (HC) {
     case 1: EQH_BWD(1); break;
     case 2: EQH_BWD(2); break;

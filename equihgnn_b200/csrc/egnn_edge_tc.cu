@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ wc,
               const float* __restrict__ W2, const float* __restrict__ b2, const int32_t* __restrict__ idx,
               const float* __restrict__ d2, int64_t N, int H, int64_t ldpq, float* __restrict__ S2,
-              float* __restrict__ Mij, float* __restrict__ Mi) {
+              float* __restrict__ Mij, float* __restrict__ Mi, const int32_t* __restrict__ order) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kStageBytes);
@@ -89,9 +89,11 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t e = tile * BM + rb + 32 * j;
-        ok[j] = e < n_edges;
-        const int64_t ec = ok[j] ? e : 0;
+        const int64_t slot = tile * BM + rb + 32 * j;           // tile row: atom slot (slot >> 4), neighbour (slot & 15)
+        ok[j] = slot < n_edges;
+        // atoms are visited in `order` (the cell order of the kNN grid) when given: spatially close atoms share
+        // neighbours, so the Q[j] rows gathered by one tile and by the tiles running next to it hit in L2
+        const int64_t ec = ok[j] ? ((order ? (int64_t)__ldg(order + (slot >> 4)) : (slot >> 4)) << 4) + (slot & 15) : 0;
         prow[j] = P + (ec >> 4) * ldpq + c16 * 4;
         qrow[j] = Q + (int64_t)__ldg(idx + ec) * ldpq + c16 * 4;
         dd[j] = __ldg(d2 + ec);
@@ -203,8 +205,9 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty[buf]);                 // accumulators are in registers: the buffer may be reused
-      const int64_t e = tile * BM + q * 32 + lane;
-      const bool ok = e < n_edges;
+      const int64_t slot = tile * BM + q * 32 + lane;
+      const bool ok = slot < n_edges;
+      const int64_t e = ok ? ((order ? (int64_t)__ldg(order + (slot >> 4)) : (slot >> 4)) << 4) + (slot & 15) : 0;
       float m[kM];
 #pragma unroll
       for (int o = 0; o < kM; ++o) {
@@ -246,9 +249,9 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
 }  // namespace edge_tc
 }  // namespace eqh
 
-extern "C" int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
-                                    const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
-                                    float* Mi, eqh_stream_t stream) {
+static int edge_fwd_tc_impl(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                            const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij, float* Mi,
+                            const int32_t* order, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::edge_tc;
   EQH_CHECK_ARG(P && Q && wc && W2 && b2 && idx && d2 && S2 && Mi && N >= 0);
@@ -262,6 +265,18 @@ extern "C" int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float*
   const int64_t tiles = (N * kNbr + BM - 1) / BM;
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
   launch_kernel(k_edge_fwd_tc, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), P, Q, wc, W2, b2, idx, d2, N, (int)H, H, S2,
-                                                                           Mij, Mi);
+                Mij, Mi, order);
   EQH_LAUNCH_RC();
+}
+
+extern "C" int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                                    const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
+                                    float* Mi, eqh_stream_t stream) {
+  return edge_fwd_tc_impl(P, Q, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, nullptr, stream);
+}
+
+extern "C" int eqh_egnn_edge_fwd_tc_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                                            const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
+                                            float* Mi, const int32_t* order, eqh_stream_t stream) {
+  return edge_fwd_tc_impl(P, Q, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, order, stream);
 }

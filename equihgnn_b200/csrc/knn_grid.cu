@@ -239,6 +239,11 @@ size_t eqh_knn16_grid_workspace_bytes(int64_t N) {
 }
 
 int eqh_knn16_grid(const float* pos, int64_t N, int32_t* idx, float* d2, void* ws, size_t ws_bytes, eqh_stream_t stream) {
+  return eqh_knn16_grid_ordered(pos, N, idx, d2, nullptr, ws, ws_bytes, stream);
+}
+
+int eqh_knn16_grid_ordered(const float* pos, int64_t N, int32_t* idx, float* d2, int32_t* order, void* ws, size_t ws_bytes,
+                           eqh_stream_t stream) {
   using namespace eqh;
   EQH_CHECK_ARG(pos && idx && d2 && ws);
   EQH_CHECK_ARG(N >= kKg && N < ((int64_t)1 << 31));          // the reference's topk raises for k > N
@@ -252,6 +257,7 @@ int eqh_knn16_grid(const float* pos, int64_t N, int32_t* idx, float* d2, void* w
   GridParams* gp = reinterpret_cast<GridParams*>(w);  w += 256;
   int32_t* cell = reinterpret_cast<int32_t*>(w);      w += sizeof(int32_t) * Np;
   int32_t* perm = reinterpret_cast<int32_t*>(w);      w += sizeof(int32_t) * Np;
+  if (order) perm = order;                            // the caller keeps the cell order of the atoms
   int32_t* dst32 = reinterpret_cast<int32_t*>(w);     w += sizeof(int32_t) * Np;
   int32_t* cell_start = reinterpret_cast<int32_t*>(w); w += sizeof(int32_t) * ((cells + 1 + 3) / 4 * 4);
   float4* sorted = reinterpret_cast<float4*>(w);      w += sizeof(float4) * N;

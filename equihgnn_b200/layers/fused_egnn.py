@@ -35,8 +35,8 @@ class EGNNFused(torch.autograd.Function):
         dev = h.device
         S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_fwd_tc", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), N, Hp, _p(S2),
-              None, _p(Mi), _stream(), nbytes=2.0 * N * KNN_K * Hp * M_DIM)
+        _call("eqh_egnn_edge_fwd_tc_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), N, Hp,
+              _p(S2), None, _p(Mi), _p(graph.order), _stream(), nbytes=2.0 * N * KNN_K * Hp * M_DIM)
         hn = torch.empty_like(h)
         _call("eqh_rowln_fwd", 1, _p(h), _p(g), _p(t), eps, 0, N, C, _p(hn), _stream())
         node_in = torch.cat((hn, Mi), dim=-1)                                        # egnn_layer.py:360
@@ -76,8 +76,8 @@ class EGNNFused(torch.autograd.Function):
         dP = torch.empty_like(P)
         dPre = torch.empty((N * KNN_K, Hp), dtype=torch.float32, device=dev)
         part = torch.empty((partial_rows(), cols), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_bwd", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), _p(S2), _p(dMi), None,
-              N, Hp, _p(dP), _p(dPre), None, _p(part), _stream())
+        _call("eqh_egnn_edge_bwd_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), _p(S2),
+              _p(dMi), None, N, Hp, _p(dP), _p(dPre), None, _p(part), _p(graph.order), _stream())
         dQ = gather_reduce_raw(dPre, graph.perm_j, graph.rowptr_j, None, N, SUM)
         # dh = dOut (residual) + dP.W1a + dQ.W1b + LayerNorm backward
         dh = gemm_raw(dP, True, W1a, False, N, C, Hp, residual=dOut)

@@ -744,10 +744,11 @@ def atom_encode(x: torch.Tensor, tables) -> torch.Tensor:
     return _AtomEncode.apply(x, *tables)
 
 
+EDGE_CELL_ORDER = os.environ.get("EQH_EDGE_CELL_ORDER", "1") != "0"   # edge kernels visit atoms in grid-cell order
 KNN_GRID_MIN = int(os.environ.get("EQH_KNN_GRID_MIN", "8192"))     # atoms per batch from which the cell grid is used
 
 
-def knn16(pos: torch.Tensor, method: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+def knn16(pos: torch.Tensor, method: Optional[str] = None, return_order: bool = False):
     """pos [N,3] float32 -> (idx [N,16] int32, d2 [N,16] float32), ascending, self first.
     Raises RuntimeError when N < 16, as the reference's topk does (egnn_layer.py:281-283)."""
     pos = _f32(pos.detach(), "knn16 pos")
@@ -759,13 +760,16 @@ def knn16(pos: torch.Tensor, method: Optional[str] = None) -> Tuple[torch.Tensor
     idx = torch.empty((N, KNN_K), dtype=torch.int32, device=pos.device)
     d2 = torch.empty((N, KNN_K), dtype=torch.float32, device=pos.device)
     use_grid = N >= KNN_GRID_MIN if method is None else method == "grid"
+    order = None
     if use_grid:        # cell grid: same bits, O(N * neighbourhood)
         nb = _lib.load().eqh_knn16_grid_workspace_bytes(N)
         ws = torch.empty(nb, dtype=torch.uint8, device=pos.device)
-        _call("eqh_knn16_grid", 8, _p(pos), N, _p(idx), _p(d2), _p(ws), nb, _stream())
+        if return_order and EDGE_CELL_ORDER:
+            order = torch.empty(N, dtype=torch.int32, device=pos.device)      # atoms sorted by grid cell
+        _call("eqh_knn16_grid_ordered", 8, _p(pos), N, _p(idx), _p(d2), _p(order), _p(ws), nb, _stream())
     else:
         _call("eqh_knn16", 1, _p(pos), N, _p(idx), _p(d2), _stream())
-    return idx, d2
+    return (idx, d2, order) if return_order else (idx, d2)
 
 
 @dataclass
@@ -776,15 +780,16 @@ class KnnGraph:
     d2: torch.Tensor         # [N,16] float32
     rowptr_j: torch.Tensor   # [N+1] int32
     perm_j: torch.Tensor     # [N*16] int32 edge ids sorted by j (stable)
+    order: Optional[torch.Tensor] = None   # [N] int32 atoms in grid-cell order (large batches): visiting order of the edge kernels
 
 
 def build_knn_graph(pos: torch.Tensor, need_transpose: bool = True) -> KnnGraph:
-    idx, d2 = knn16(pos)
+    idx, d2, order = knn16(pos, return_order=True)
     if need_transpose:
         rowptr_j, perm_j, _, _ = csr_build(idx.view(-1), idx.shape[0], None)
     else:
         rowptr_j = perm_j = None
-    return KnnGraph(idx, d2, rowptr_j, perm_j)
+    return KnnGraph(idx, d2, rowptr_j, perm_j, order)
 
 
 class _EgnnEdge(torch.autograd.Function):
@@ -800,9 +805,12 @@ class _EgnnEdge(torch.autograd.Function):
         Mij = torch.empty((N, KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
         # tensor-core kernel by default; EQH_EDGE_FWD=simt selects the CUDA-core implementation of the same math
-        name = "eqh_egnn_edge_fwd" if os.environ.get("EQH_EDGE_FWD", "tc") == "simt" else "eqh_egnn_edge_fwd_tc"
-        _call(name, 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij), _p(Mi),
-              _stream(), nbytes=2.0 * N * KNN_K * H * M_DIM)
+        if os.environ.get("EQH_EDGE_FWD", "tc") == "simt":
+            _call("eqh_egnn_edge_fwd", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H, _p(S2), _p(Mij),
+                  _p(Mi), _stream(), nbytes=2.0 * N * KNN_K * H * M_DIM)
+        else:
+            _call("eqh_egnn_edge_fwd_tc_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), N, H,
+                  _p(S2), _p(Mij), _p(Mi), _p(graph.order), _stream(), nbytes=2.0 * N * KNN_K * H * M_DIM)
         ctx.save_for_backward(P, Q, wc, W2, b2, d2, S2)
         ctx.graph = graph
         ctx.set_materialize_grads(False)
@@ -827,8 +835,8 @@ class _EgnnEdge(torch.autograd.Function):
         dPre = torch.empty((N * KNN_K, H), dtype=torch.float32, device=dev)
         dd2 = torch.empty_like(d2) if ctx.needs_input_grad[5] else None
         part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_bwd", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi), _p(dMij), N,
-              H, _p(dP), _p(dPre), _p(dd2), _p(part), _stream())
+        _call("eqh_egnn_edge_bwd_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi),
+              _p(dMij), N, H, _p(dP), _p(dPre), _p(dd2), _p(part), _p(g.order), _stream())
         red = colsum_raw(part)
         dW2 = red[:M_DIM * H].view(M_DIM, H)
         dwc = red[M_DIM * H:(M_DIM + 1) * H]

@@ -175,6 +175,10 @@ EQH_API int eqh_knn16(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /*[N,1
 EQH_API size_t eqh_knn16_grid_workspace_bytes(int64_t N);
 EQH_API int eqh_knn16_grid(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /*[N,16]*/, float* d2 /*[N,16]*/, void* ws,
                    size_t ws_bytes, eqh_stream_t stream);
+/* Same, and `order` [N] receives the atoms sorted by grid cell (stable): visiting atoms in this order makes the
+ * neighbour-row gathers of the edge kernels local (the *_ordered entry points below). */
+EQH_API int eqh_knn16_grid_ordered(const float* pos, int64_t N, int32_t* idx, float* d2, int32_t* order /*[N]*/, void* ws,
+                           size_t ws_bytes, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * EGNN edge model phi_e + neighbour pooling (egnn_layer.py:298-310,357-358).
@@ -200,6 +204,11 @@ EQH_API size_t eqh_egnn_edge_fwd_smem_bytes(int64_t H);
 EQH_API int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                          const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
                          float* Mi, eqh_stream_t stream);
+/* eqh_egnn_edge_fwd_tc visiting the atoms in `order` (a permutation of [0,N), e.g. from eqh_knn16_grid_ordered; NULL =
+ * natural order).  Outputs are identical; only the memory access pattern changes. */
+EQH_API int eqh_egnn_edge_fwd_tc_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                                 const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2,
+                                 float* Mij /* optional */, float* Mi, const int32_t* order, eqh_stream_t stream);
 /* Backward.  dMi [N,16] and/or dMij [N*16,16] (either may be NULL).  Outputs:
  *   dP [N,H]; dPre [N*16,H] (per-edge gradient of `pre`: dQ[j] = sum over incoming edges, done by
  *   eqh_gather_reduce over the transposed kNN incidence); dd2 [N,16] (optional);
@@ -209,6 +218,12 @@ EQH_API int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc
 EQH_API int eqh_egnn_edge_bwd(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                       const int32_t* idx, const float* d2, const float* S2, const float* dMi, const float* dMij,
                       int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, eqh_stream_t stream);
+/* Same, atoms visited in `order` (dP / dPre / dd2 identical; the per-CTA partials in `part` are summed in another
+ * order, i.e. the weight gradients agree to rounding). */
+EQH_API int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+                              const int32_t* idx, const float* d2, const float* S2, const float* dMi, const float* dMij,
+                              int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, const int32_t* order,
+                              eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * AtomEncoder (third-party ogb==1.3.6; call sites mhnn.py:201, equihnn_egnn.py:157):

@@ -398,3 +398,31 @@ def test_colsum_batch_many_jobs_one_launch():
     assert rel_err(sub, xs[6][:, 256:].double().sum(0)) < 2e-6
     outs2, sub2 = run()
     assert all(torch.equal(a, b) for a, b in zip(outs, outs2)) and torch.equal(sub, sub2)
+
+
+def test_edge_kernels_in_cell_order_give_the_same_results():
+    """The edge kernels may visit the atoms in the kNN grid's cell order (L2 locality of the Q[j] gathers on large
+    batches): per-atom outputs are bit-identical, the per-CTA weight-gradient partials agree to rounding."""
+    b = synthetic.make_batch("molecule3d", 320, 9)
+    pos = b.pos.to(DEV)
+    N, H = b.num_atoms, 128
+    idx, d2, order = ops.knn16(pos, method="grid", return_order=True)
+    assert order is not None and torch.equal(torch.sort(order.long()).values, torch.arange(N, device=DEV))
+    g = torch.Generator().manual_seed(2)
+    mk = lambda *s, sc=1.0: (sc * torch.randn(*s, generator=g)).to(DEV)
+    P, Q, wc, W2, b2 = mk(N, H, sc=0.3), mk(N, H, sc=0.3), mk(H, sc=0.1), mk(16, H, sc=0.05), mk(16, sc=0.1)
+    dMi = mk(N, 16)
+    res = {}
+    for name, o in (("natural", None), ("cell", order)):
+        S2 = torch.empty(N * 16, 16, device=DEV); Mi = torch.empty(N, 16, device=DEV)
+        ops._call("eqh_egnn_edge_fwd_tc_ordered", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                  idx.data_ptr(), d2.data_ptr(), N, H, S2.data_ptr(), None, Mi.data_ptr(), ops._p(o), ops._stream())
+        dP = torch.empty_like(P); dPre = torch.empty(N * 16, H, device=DEV)
+        part = torch.empty(ops.partial_rows(), 17 * H + 16, device=DEV)
+        ops._call("eqh_egnn_edge_bwd_ordered", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                  idx.data_ptr(), d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), None, N, H, dP.data_ptr(), dPre.data_ptr(), None,
+                  part.data_ptr(), ops._p(o), ops._stream())
+        res[name] = (S2, Mi, dP, dPre, ops.colsum_raw(part))
+    for a_, b_ in zip(res["natural"][:4], res["cell"][:4]):
+        assert torch.equal(a_, b_)
+    assert rel_err(res["cell"][4], res["natural"][4].double()) < 2e-6
