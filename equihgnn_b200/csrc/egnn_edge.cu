@@ -140,11 +140,36 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
   pdl_prologue();
   __shared__ __align__(16) float ds2s[kNbr][kM];
   __shared__ float dd2s[kBwdMaxThreads / 32][kNbr];
-  __shared__ int32_t js[kNbr];
   __shared__ float dds[kNbr];
+  // The 16 neighbour rows Q[j] of the NEXT atom are copied into shared memory with cp.async while the current atom
+  // is processed (double buffer [2][16][H]): the gather latency -- 42 % of this kernel's stall samples when each row
+  // was prefetched only one neighbour ahead through registers -- is hidden behind a whole atom of arithmetic.
+  extern __shared__ __align__(16) float qs[];
   const int T = blockDim.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wib = tid >> 5;
+  const int H4 = H >> 2;
+  // per buffer: 16 neighbour rows of Q, the atom's own row of P, its 16x16 block of S2, dMi [16], d2 [16]
+  const size_t kBufFloats = (size_t)(kNbr + 1) * H + kNbr * kM + kM + kNbr;
+  auto cp16 = [](float* dst, const float* src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  };
+  auto prefetch = [&](int64_t atom, int buf) {
+    float* dst = qs + (size_t)buf * kBufFloats;
+    for (int t = tid; t < kNbr * H4; t += T) {
+      const int k = t / H4, c4 = t - k * H4;
+      cp16(dst + (size_t)k * H + c4 * 4, Q + (int64_t)__ldg(idx + atom * kNbr + k) * H + c4 * 4);
+    }
+    float* pd = dst + (size_t)kNbr * H;
+    for (int t = tid; t < H4; t += T) cp16(pd + t * 4, P + atom * H + t * 4);
+    float* sd = pd + H;
+    if (tid < kNbr * kM / 4) cp16(sd + tid * 4, S2 + atom * kNbr * kM + tid * 4);
+    else if (tid < kNbr * kM / 4 + kNbr / 4) cp16(sd + kNbr * kM + kM + (tid - kNbr * kM / 4) * 4, d2 + atom * kNbr + (tid - kNbr * kM / 4) * 4);
+    else if (dMi && tid < kNbr * kM / 4 + kNbr / 4 + kM / 4)
+      cp16(sd + kNbr * kM + (tid - kNbr * kM / 4 - kNbr / 4) * 4, dMi + atom * kM + (tid - kNbr * kM / 4 - kNbr / 4) * 4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
   float w2[kM][HC], dw2[kM][HC], wcr[HC], dwc[HC];
   bool act[HC];
@@ -162,22 +187,32 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
   }
   float db2 = 0.f;  // threads < 16
 
-  for (int64_t slot = blockIdx.x; slot < N; slot += gridDim.x) {
+  if ((int64_t)blockIdx.x < N) prefetch(order ? (int64_t)__ldg(order + blockIdx.x) : (int64_t)blockIdx.x, 0);
+  int buf = 0;
+  for (int64_t slot = blockIdx.x; slot < N; slot += gridDim.x, buf ^= 1) {
     // atoms in `order` (the cell order of the kNN grid) when given: the CTAs running side by side work on spatially
     // close atoms, whose neighbour rows Q[j] overlap and hit in L2
     const int64_t i = order ? (int64_t)__ldg(order + slot) : slot;
-    __syncthreads();  // previous atom's readers of ds2s/js/dds are done
+    __syncthreads();  // previous atom's readers of ds2s/js/dds and of the other Q buffer are done
+    const int64_t nslot = slot + gridDim.x;
+    if (nslot < N) {
+      prefetch(order ? (int64_t)__ldg(order + nslot) : nslot, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this atom's rows have landed (the next may be in flight)
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // every thread's cp.async chunks of this atom are visible
+    const float* cur = qs + (size_t)buf * kBufFloats;
+    const float* pcur = cur + (size_t)kNbr * H;
+    const float* s2cur = pcur + H;
     for (int t = tid; t < kNbr * kM; t += T) {
       const int k = t >> 4, o = t & 15;
       const int64_t e = i * kNbr + k;
-      float g = dMi ? __ldg(dMi + i * kM + o) : 0.f;
+      float g = dMi ? s2cur[kNbr * kM + o] : 0.f;
       if (dMij) g += __ldg(dMij + e * kM + o);
-      ds2s[k][o] = g * dsilu_f(__ldg(S2 + e * kM + o));
+      ds2s[k][o] = g * dsilu_f(s2cur[t]);
     }
-    if (tid < kNbr) {
-      js[tid] = __ldg(idx + i * kNbr + tid);
-      dds[tid] = __ldg(d2 + i * kNbr + tid);
-    }
+    if (tid < kNbr) dds[tid] = s2cur[kNbr * kM + kM + tid];
     __syncthreads();
     if (tid < kM) {
 #pragma unroll
@@ -186,21 +221,15 @@ __global__ void __launch_bounds__(kBwdMaxThreads) k_edge_bwd(const float* __rest
     float pi[HC], dpa[HC];
 #pragma unroll
     for (int c = 0; c < HC; ++c) {
-      pi[c] = act[c] ? __ldg(P + i * H + tid + c * T) : 0.f;
+      pi[c] = act[c] ? pcur[tid + c * T] : 0.f;
       dpa[c] = 0.f;
     }
-    float qn[HC];
-#pragma unroll
-    for (int c = 0; c < HC; ++c) qn[c] = act[c] ? __ldg(Q + (int64_t)js[0] * H + tid + c * T) : 0.f;
+    const float* qbuf = cur;
     for (int k = 0; k < kNbr; ++k) {
       const float dd = dds[k];
       float q[HC];
 #pragma unroll
-      for (int c = 0; c < HC; ++c) q[c] = qn[c];
-      if (k + 1 < kNbr) {
-#pragma unroll
-        for (int c = 0; c < HC; ++c) qn[c] = act[c] ? __ldg(Q + (int64_t)js[k + 1] * H + tid + c * T) : 0.f;
-      }
+      for (int c = 0; c < HC; ++c) q[c] = act[c] ? qbuf[(size_t)k * H + tid + c * T] : 0.f;
       float g[kM];
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -335,6 +364,7 @@ int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const float* wc, c
   using namespace eqh;
   (void)b2;
   EQH_CHECK_ARG(P && Q && wc && W2 && idx && d2 && S2 && dP && dPre && part && N >= 0);
+  EQH_CHECK_ARG(aligned16(Q) && aligned16(P) && aligned16(S2) && aligned16(d2) && aligned16(dMi));   // 16-byte cp.async
   if (H <= 0 || H % 64 != 0) return EQH_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // threads own columns: HC = ceil(H / 576) columns per thread, T = ceil(H / HC) rounded up to a warp
@@ -342,8 +372,16 @@ int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const float* wc, c
   int T = (int)((H + HC - 1) / HC);
   T = (T + 31) / 32 * 32;
   const unsigned grid = kPartialRows;  // every CTA writes its partial row (zeros when it owns no atom)
+  // double-buffered: 16 neighbour rows of Q + the atom's P row + its S2 block, dMi and d2
+  const size_t qsmem = sizeof(float) * 2 * ((size_t)(kNbr + 1) * H + kNbr * kM + kM + kNbr);
+  if (qsmem > 200 * 1024) return EQH_ERR_UNSUPPORTED;
 #define EQH_BWD(HCV)                                                                                              \
-  launch_kernel(k_edge_bwd<HCV>, dim3(grid), dim3(T), 0, st, P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, dd2, part, order)
+  do {                                                                                                            \
+    cudaError_t e_ = cudaFuncSetAttribute(k_edge_bwd<HCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem); \
+    if (e_ != cudaSuccess) return (int)e_;                                                                        \
+    launch_kernel(k_edge_bwd<HCV>, dim3(grid), dim3(T), qsmem, st, P, Q, wc, W2, idx, d2, S2, dMi, dMij, N, (int)H, dP, dPre, \
+                  dd2, part, order);                                                                              \
+  } while (0)
   switch (HC) {
     case 1: EQH_BWD(1); break;
     case 2: EQH_BWD(2); break;
