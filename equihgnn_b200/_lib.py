@@ -52,6 +52,7 @@ _SIGNATURES = {
     "eqh_atom_encoder_slices": (c_int, [c_int64]),
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),
+    "eqh_collate": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
     "eqh_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "eqh_gemm_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
     "eqh_gemm_tf32x3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int,
@@ -69,6 +70,18 @@ class ColsumJob(ctypes.Structure):
 
 
 COLSUM_MAX_JOBS = 32
+
+
+class Store(ctypes.Structure):
+    """struct eqh_store (include/eqh_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("x", "pos", "y", "v_loc", "e_loc", "edge_attr", "e_order", "atom_off", "he_off",
+                                        "inc_off")]
+
+
+class Batch(ctypes.Structure):
+    """struct eqh_batch (include/eqh_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "n_e", "e_order", "batch",
+                                        "ptr", "y")]
 
 _lib = None
 

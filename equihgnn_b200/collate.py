@@ -1,0 +1,124 @@
+"""Device-side batch collation: the reference collates on the host in a single process
+(`DataLoader(num_workers=0)` + PyG `Batch.from_data_list`, main.py:227-229, data/utils.py:150-178) and ships the collated
+batch to the GPU every step.  Here the dataset is resident in HBM as a packed per-molecule store and a batch is
+gathered on the device from the list of molecule ids (`eqh_collate`): per step the host sends the B ids and 3(B+1)
+offsets it computes from its copy of the per-molecule counts (~2 KB) instead of the collated batch (~350 KB at QM9-128),
+and the result lands directly in the static inputs of the captured training graph, ghost molecule included.
+
+Bit-exact against the host collation (`synthetic.collate_host` + `graphed.pad_batch`); tests/test_gpu_collate.py.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .graphed import GHOST_OFFSET, GraphedTrainer
+from .synthetic import HBatch
+
+
+class MoleculeStore:
+    """Packed dataset: concatenated per-molecule arrays on the device + per-molecule counts on the host."""
+
+    def __init__(self, mols, y, device):
+        self.device = torch.device(device)
+        atoms = np.array([m[0] for m in mols], dtype=np.int64)
+        hes = np.array([m[1] for m in mols], dtype=np.int64)
+        incs = np.array([m[4].shape[0] for m in mols], dtype=np.int64)
+        self.n_atoms, self.n_he, self.n_inc = atoms, hes, incs
+        self.max_abs_pos = np.array([np.abs(m[3]).max() for m in mols], dtype=np.float32)
+        off = lambda c: np.concatenate([[0], np.cumsum(c)]).astype(np.int64)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.t = {
+            "x": dev(np.concatenate([m[2] for m in mols])), "pos": dev(np.concatenate([m[3] for m in mols])),
+            "y": dev(np.asarray(y, dtype=np.float32)),
+            "v_loc": dev(np.concatenate([m[4] for m in mols]).astype(np.int32)),
+            "e_loc": dev(np.concatenate([m[5] for m in mols]).astype(np.int32)),
+            "edge_attr": dev(np.concatenate([m[6] for m in mols])), "e_order": dev(np.concatenate([m[7] for m in mols])),
+            "atom_off": dev(off(atoms)), "he_off": dev(off(hes)), "inc_off": dev(off(incs)),
+        }
+        self.c_store = _lib.Store(**{k: v.data_ptr() for k, v in self.t.items()})
+        self.size = len(mols)
+
+    def shape_of(self, ids: Sequence[int]) -> Tuple[int, int, int]:
+        ids = np.asarray(ids, dtype=np.int64)
+        return int(self.n_atoms[ids].sum()), int(self.n_he[ids].sum()), int(self.n_inc[ids].sum())
+
+    def step_inputs(self, ids: Sequence[int]) -> torch.Tensor:
+        """Pinned int32 buffer [B + 3(B+1)]: the ids, then the atom / hyperedge / incidence offsets inside the batch."""
+        ids = np.asarray(ids, dtype=np.int64)
+        B = ids.shape[0]
+        buf = torch.empty(B + 3 * (B + 1), dtype=torch.int32).pin_memory()
+        a = buf.numpy()
+        a[:B] = ids
+        for k, cnt in enumerate((self.n_atoms, self.n_he, self.n_inc)):
+            a[B + k * (B + 1)] = 0
+            np.cumsum(cnt[ids], out=a[B + k * (B + 1) + 1:B + (k + 1) * (B + 1)])
+        return buf
+
+
+def empty_packed(B: int, bucket: Optional[Tuple[int, int, int]], shape: Tuple[int, int, int], device) -> HBatch:
+    """Uninitialised packed batch of the given (padded) shape on the device."""
+    N, E, Z = bucket if bucket is not None else shape
+    G = B + (1 if bucket is not None else 0)
+    i64, f32 = torch.int64, torch.float32
+    like = HBatch(x=torch.empty((N, 9), dtype=i64), pos=torch.empty((N, 3), dtype=f32), edge_index0=torch.empty(Z, dtype=i64),
+                  edge_index1=torch.empty(Z, dtype=i64), edge_attr=torch.empty((E, 1), dtype=i64), n_e=torch.empty(G, dtype=i64),
+                  e_order=torch.empty(E, dtype=i64), batch=torch.empty(N, dtype=i64), ptr=torch.empty(G + 1, dtype=i64),
+                  y=torch.empty(G, dtype=f32), num_graphs=G, num_real_graphs=B if bucket is not None else 0)
+    return like.pack(device=device)
+
+
+def collate_device(store: MoleculeStore, ids: Sequence[int], bucket: Optional[Tuple[int, int, int]] = None,
+                   out: Optional[HBatch] = None, step_inputs: Optional[torch.Tensor] = None) -> HBatch:
+    """Gather the molecules `ids` into one batch on the device.  bucket=(N_pad, E_pad, Z_pad) appends the ghost molecule
+    (graphed.pad_batch); `out` is a packed batch of the right shape to write into (e.g. a captured graph's static
+    inputs); `step_inputs` a pinned buffer from store.step_inputs(ids) (built here when omitted)."""
+    B = len(ids)
+    N, E, Z = store.shape_of(ids)
+    Np, Ep, Zp = bucket if bucket is not None else (N, E, Z)
+    if bucket is not None and (Np - N < 1 or Ep - E < 1 or Zp - Z < 0):
+        raise ValueError(f"batch (N={N},E={E},Z={Z}) does not fit bucket {bucket}")
+    if out is None:
+        out = empty_packed(B, bucket, (N, E, Z), store.device)
+    if step_inputs is None:
+        step_inputs = store.step_inputs(ids)
+    dev_in = step_inputs.to(store.device, non_blocking=True)
+    ga = Np - N
+    side = int(np.ceil(ga ** (1.0 / 3.0))) if ga > 0 else 1
+    ids_np = np.asarray(ids, dtype=np.int64)
+    origin = float(np.float32(GHOST_OFFSET) + store.max_abs_pos[ids_np].max()) if ga > 0 else 0.0
+    c_out = _lib.Batch(**{f: getattr(out, f).data_ptr() for f in ("x", "pos", "edge_index0", "edge_index1", "edge_attr",
+                                                                  "n_e", "e_order", "batch", "ptr", "y")})
+    import ctypes
+    ops._call("eqh_collate", 1, ctypes.byref(store.c_store), dev_in.data_ptr(), dev_in.data_ptr() + 4 * B, B, N, E, Z, Np, Ep,
+              Zp, side, origin, ctypes.byref(c_out), ops._stream())
+    out._keep = dev_in          # the kernel reads it asynchronously
+    return out
+
+
+class StoreTrainer(GraphedTrainer):
+    """GraphedTrainer fed by molecule ids: collation happens on the device, straight into the graph's static inputs."""
+
+    def __init__(self, model, store: MoleculeStore, real_graphs: int, **kw):
+        super().__init__(model, real_graphs, **kw)
+        self.store = store
+
+    def step_from_ids(self, ids: Sequence[int], step_inputs: Optional[torch.Tensor] = None) -> float:
+        shape = self.store.shape_of(ids)
+        N, E, Z = shape
+        bucket = ((N + 1 + 255) // 256 * 256, (E + 1 + 255) // 256 * 256, (Z + 511) // 512 * 512)
+        key = (bucket[0], bucket[1], bucket[2], len(ids) + 1)
+        bk = self.buckets.get(key)
+        if bk is None:
+            like = collate_device(self.store, ids, bucket)
+            bk = self.buckets[key] = self._capture(like)
+        collate_device(self.store, ids, bucket, out=bk.static, step_inputs=step_inputs)
+        bk.graph.replay()
+        self.replays += 1
+        self.own_launches += bk.launches + 1
+        self.sync_gradients()
+        self.optimizer_step()
+        return float(bk.loss.item())

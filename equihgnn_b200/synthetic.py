@@ -161,15 +161,35 @@ def _molecule(rng: np.random.Generator, prof) -> tuple:
             np.concatenate([battr, np.array(c_attr, dtype=np.int64)]), np.array(order, dtype=np.int64))
 
 
+def make_molecules(profile: str, count: int, seed: int):
+    """`count` un-collated synthetic molecules (a dataset): list of (atoms, hyperedges, x [a,9], pos [a,3],
+    local atom id per incidence, local hyperedge id per incidence, edge_attr, e_order) and their targets y."""
+    prof = PROFILES[profile]
+    rng = np.random.default_rng(seed)
+    mols = [_molecule(rng, prof) for _ in range(count)]
+    return mols, rng.normal(size=count).astype(np.float32)
+
+
+def collate_host(mols, y, ids) -> HBatch:
+    """Host collation of the molecules `ids` of a dataset (PyG Batch.from_data_list over HData: data/utils.py:150-178)."""
+    return _collate([mols[i] for i in ids], np.asarray([y[i] for i in ids], dtype=np.float32))
+
+
 def make_batch(profile: str, batch_size: int, seed: int) -> HBatch:
     """One collated batch of `batch_size` synthetic molecules on the host (CPU tensors)."""
     prof = PROFILES[profile]
     rng = np.random.default_rng(seed)
+    mols = [_molecule(rng, prof) for _ in range(batch_size)]
+    return _collate(mols, rng.normal(size=batch_size).astype(np.float32))
+
+
+def _collate(mols, y) -> HBatch:
+    batch_size = len(mols)
     xs, ps, v0, v1, ea, ne, eo, bt = [], [], [], [], [], [], [], []
     ptr = [0]
     a_off = e_off = 0
     for b in range(batch_size):
-        a, ne_b, feats, pos, n_idx, e_idx, attr, order = _molecule(rng, prof)
+        a, ne_b, feats, pos, n_idx, e_idx, attr, order = mols[b]
         xs.append(feats)
         ps.append(pos)
         v0.append(n_idx + a_off)          # HData.__inc__('edge_index0') = x.size(0)
@@ -181,7 +201,6 @@ def make_batch(profile: str, batch_size: int, seed: int) -> HBatch:
         a_off += a
         e_off += ne_b
         ptr.append(a_off)
-    y = rng.normal(size=batch_size).astype(np.float32)
     t = torch.from_numpy
     return HBatch(
         x=t(np.concatenate(xs)), pos=t(np.concatenate(ps)), edge_index0=t(np.concatenate(v0)),

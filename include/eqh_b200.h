@@ -241,6 +241,37 @@ EQH_API int eqh_atom_encoder_bwd(const int64_t* x, const float* dh, const int32_
                          float* partial, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Device-side batch collation (the caller of the path: main.py:227-229 DataLoader + PyG Batch.from_data_list,
+ * data/utils.py:150-178).  The dataset lives in HBM as a packed per-molecule store; a batch is gathered by molecule id:
+ *     x / pos / y copied; edge_index0 = local atom id + atom offset of the molecule in the batch, edge_index1 = local
+ *     hyperedge id + hyperedge offset (HData.__inc__); batch / ptr / n_e as PyG builds them.
+ * `offsets` (device, int32 [3][B+1]): exclusive prefix sums of the selected molecules' atom / hyperedge / incidence
+ * counts (computed by the host from its copy of the store's offsets -- 3(B+1) integers per step instead of the batch).
+ * N_pad > N appends the inert ghost molecule of the CUDA-graph trainer (graphed.pad_batch): ghost atoms on a 1.5 A
+ * lattice of side `ghost_side` at `ghost_origin`, ghost hyperedges (edge_attr 5) and incidences that only connect
+ * ghosts.  Bit-exact against the host collation.  Outputs hold N_pad / E_pad / Z_pad / B(+1) entries.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct eqh_store {
+  const int64_t* x;         /* [atoms, 9] */
+  const float* pos;         /* [atoms, 3] */
+  const float* y;           /* [molecules] */
+  const int32_t* v_loc;     /* [incidences] atom id inside the molecule */
+  const int32_t* e_loc;     /* [incidences] hyperedge id inside the molecule */
+  const int64_t* edge_attr; /* [hyperedges] */
+  const int64_t* e_order;   /* [hyperedges] */
+  const int64_t* atom_off;  /* [molecules+1] */
+  const int64_t* he_off;    /* [molecules+1] */
+  const int64_t* inc_off;   /* [molecules+1] */
+} eqh_store;
+typedef struct eqh_batch {
+  int64_t* x; float* pos; int64_t* edge_index0; int64_t* edge_index1; int64_t* edge_attr; int64_t* n_e; int64_t* e_order;
+  int64_t* batch; int64_t* ptr; float* y;
+} eqh_batch;
+EQH_API int eqh_collate(const eqh_store* store, const int32_t* ids /*dev [B]*/, const int32_t* offsets /*dev [3][B+1]*/,
+                int64_t B, int64_t N, int64_t E, int64_t Z, int64_t N_pad, int64_t E_pad, int64_t Z_pad, int64_t ghost_side,
+                float ghost_origin, const eqh_batch* out, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * fp32-faithful row GEMM on the tcgen05 tensor cores (3xTF32 operand splitting, fp32 accumulate):
  *     D[M,N] = act( A . B^T + bias ) + residual          A logical [M,K], B logical [N,K]
  * Replaces the cuBLAS SIMT sgemm calls behind nn.Linear in mlp.py:91-99, egnn_layer.py:180-208 and

@@ -171,3 +171,18 @@ def test_overlay_installs_reference_module_paths():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_dataset_collation_reproduces_make_batch():
+    """make_molecules + collate_host (the un-collated dataset used by the device-side collation) == make_batch."""
+    import dataclasses
+    from equihgnn_b200 import synthetic
+    for profile, B in (("qm9", 16), ("opv", 4)):
+        mols, y = synthetic.make_molecules(profile, B, 321)
+        a, b = synthetic.collate_host(mols, y, range(B)), synthetic.make_batch(profile, B, 321)
+        for f in dataclasses.fields(a):
+            va, vb = getattr(a, f.name), getattr(b, f.name)
+            assert torch.equal(va, vb) if isinstance(va, torch.Tensor) else va == vb, f.name
+        sub = synthetic.collate_host(mols, y, [2, 0])
+        assert sub.num_graphs == 2 and int(sub.ptr[-1]) == mols[2][0] + mols[0][0]
+        assert int(sub.edge_index0.max()) < sub.num_atoms and int(sub.edge_index1.max()) + 1 == sub.num_hyperedges
