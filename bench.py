@@ -171,6 +171,30 @@ class ClockSampler:
         return out
 
 
+def roofline_tensor(dev, rows, C, flush_l2):
+    """Tensor roofline of the row GEMM that dominates the step's kernel time (eqh_gemm_tf32x3, [rows, C] x [C, C],
+    forward layout): algorithmic flops 2*M*N*K (the kernel executes 3x that on the TF32 pipe to stay fp32-faithful)
+    over the average launch duration (CUDA events around each launch, L2 flushed in between)."""
+    import torch
+    from equihgnn_b200 import ops
+    A = torch.randn(rows, C, device=dev)
+    W = torch.randn(C, C, device=dev) * 0.05
+    for _ in range(3):
+        ops.gemm_raw(A, True, W, True, rows, C, C)
+    ts = []
+    for _ in range(10):
+        flush_l2()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        ops.gemm_raw(A, True, W, True, rows, C, C)
+        s1.record()
+        torch.cuda.synchronize()
+        ts.append(s0.elapsed_time(s1))
+    ts.sort()
+    t = ts[len(ts) // 2] * 1e-3
+    return {"rows": rows, "flops_per_launch": 2.0 * rows * C * C, "us_per_launch": t * 1e6, "tflops": 2.0 * rows * C * C / t / 1e12}
+
+
 def roofline_stacked(dev, C, flush_l2):
     """HBM roofline of the segmented-reduction kernels on a working set far above L2 ('the
     >=60 % HBM target is evaluated on configs 3-5 and on a stacked-batch microbenchmark (>= 1 GB per launch)'):
@@ -382,6 +406,7 @@ def run_b200(a):
                          "achieved_gbs": tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0,
                          "bytes_per_launch": tot_bytes / len(recs)}
     stacked = roofline_stacked(dev, a.hidden, flush_l2) if rank == 0 else None
+    tens = [roofline_tensor(dev, r, a.hidden, flush_l2) for r in (resident[0].num_atoms, 30000)] if rank == 0 else None
 
     if rank == 0:
         out = {
@@ -430,6 +455,21 @@ def run_b200(a):
                 "in_step": {"note": "same kernels inside the QM9-128 step (tensors <= 10 MB, latency-bound by construction; "
                                     "measured in an eager replay of the step with CUDA events around each launch)",
                             "family": fam}}
+        if tens:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            bf16 = float(pk.get("bf16_tflops_sustained", 1402.4))
+            out["roofline_tensor"] = {
+                "bound": "tensor", "kernel": "eqh_gemm_tf32x3 (fp32-faithful 3xTF32 row GEMM, [rows,C] x [C,C]): the largest "
+                                             "share of the step's kernel time (profiles/r01_graph_timeline_qm9.md)",
+                "achieved": tens[0]["tflops"], "peak": bf16, "unit": "TFLOP/s", "frac": tens[0]["tflops"] / bf16,
+                "peak_source": "measured dense bf16, sustained (MEASURED_PEAKS.json); a TF32 MMA runs at half the bf16 rate "
+                               "and the kernel issues 3 TF32 products per algorithmic product, so the ceiling of this "
+                               "formulation is peak/6",
+                "frac_of_3xtf32_ceiling": tens[0]["tflops"] / (bf16 / 6.0),
+                "cases": {f"rows={t_['rows']}": {k: t_[k] for k in ("flops_per_launch", "us_per_launch", "tflops")} | {
+                    "frac_of_3xtf32_ceiling": t_["tflops"] / (bf16 / 6.0)} for t_ in tens},
+                "note": "at the QM9-128 row count the GEMM is latency bound (one 128x64 tile per CTA, 72-80 CTAs); rows=30000 "
+                        "(Molecule3D-1024) runs the persistent variant; see profiles/r01_kernels_ncu_full.md for the counters"}
         if not a.no_cpu_baseline and world == 1:
             val, cores, n, dt = cpu_reference_steps(a.workload, a.hidden, 1000, a.cpu_seconds)
             out["cpu_baseline"] = {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port",
