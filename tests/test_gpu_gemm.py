@@ -156,3 +156,33 @@ def test_tensor_core_truncates_tf32_inputs():
     D1 = ops.gemm_raw(A, True, B, True, 1000, 384, 512, write_hi=True)
     assert torch.equal(D0, D1)
     assert rel_err(D0, A.double() @ B.double().t()) < 2e-6
+
+
+@pytest.mark.parametrize("flags", [0, 0x1000, 1 << 9, 3 << 9])
+@pytest.mark.parametrize("M,N,K", [(300, 72, 272), (129, 52, 36), (1000, 256, 100), (20000, 40, 64)])
+def test_gemm_writes_only_its_output(M, N, K, flags):
+    """Guard bands around D (compute-sanitizer is not available on the GPU pool): ragged M / N / K, every kernel variant
+    incl. the persistent one and the split-K finish, row-strided outputs -- nothing outside [M, N] is touched."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, W = _mk((M, K), g), _mk((N, K), g), _mk((K, N), g)
+    ld = (N + 3) // 4 * 4 + 8
+    for layout in ("fwd", "dgrad", "wgrad"):
+        rows = M if layout != "wgrad" else K
+        buf = torch.full(((rows + 16) * ld + 64,), 12345.0, device=DEV)
+        D = buf[8 * ld:8 * ld + rows * ld].view(rows, ld)[:, :N]
+        if layout == "fwd":
+            ops.gemm_raw(A, True, B, True, M, N, K, out=D, flags=flags)
+            ref = A.double() @ B.double().t()
+        elif layout == "dgrad":
+            ops.gemm_raw(A, True, W, False, M, N, K, out=D, flags=flags)
+            ref = A.double() @ W.double()
+        else:
+            if M % 4:
+                continue                                      # MN-major A needs a 16-byte row stride
+            X = _mk((M, N), g)
+            ops.gemm_raw(A, False, X, False, K, N, M, splits=0, out=D, flags=flags)
+            ref = A.double().t() @ X.double()
+        assert rel_err(D, ref) < 5e-6, layout
+        full = buf[8 * ld:8 * ld + rows * ld].view(rows, ld)
+        assert bool((full[:, N:] == 12345.0).all()), layout                  # columns beyond N in every row
+        assert bool((buf[:8 * ld] == 12345.0).all()) and bool((buf[8 * ld + rows * ld:] == 12345.0).all()), layout
