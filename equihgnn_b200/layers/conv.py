@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .fused_conv import MHNNSConvFused
+from .fused_conv import MHNNConvFused, MHNNSConvFused
 from .mlp import MLP
 
 
@@ -87,6 +87,22 @@ class MHNNConv(nn.Module):
         self.hid_dim = hid_dim
         self.aggr = aggr
         self.dropout = dropout
+        # set by equihgnn_b200.train.Trainer (see MHNNSConv.direct_param_grad)
+        self.direct_param_grad = False
+
+    def _layer_fusable(self, x, e) -> bool:
+        ws = [getattr(self, f"W{k}", None) for k in (1, 2, 3, 4)]
+        return (all(isinstance(w, MLP) and w.fusable() and w.normalization == "ln" for w in ws)
+                and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and e.dim() == 2
+                and self.hid_dim in (32, 64, 128, 256, 512) and self.aggr in ("mean", "sum"))
+
+    def _fused_params(self):
+        out = []
+        for k in (1, 2, 3, 4):
+            w = getattr(self, f"W{k}")
+            n = w.normalizations[1]
+            out += [w.lins[0].weight, w.lins[0].bias, n.weight, n.bias, w.lins[1].weight, w.lins[1].bias]
+        return out
 
     def reset_parameters(self):
         for k in (1, 2, 3, 4):
@@ -99,6 +115,10 @@ class MHNNConv(nn.Module):
         inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, N, Eh)
 
         def layer(x, e):
+            if self._layer_fusable(x, e):
+                eps = tuple(getattr(self, f"W{k}").normalizations[1].eps for k in (1, 2, 3, 4))
+                direct = self.direct_param_grad and torch.is_grad_enabled()
+                return MHNNConvFused.apply(x, e, inc, self.aggr, direct, eps, *self._fused_params())
             Me = _pair_scatter(self.W1, x, e, inc, "e", self.aggr)       # conv.py:90-93
             e = self.W2(torch.cat((e, Me), -1))                           # conv.py:94
             Mv = _pair_scatter(self.W3, x, e, inc, "v", self.aggr)       # conv.py:96-97

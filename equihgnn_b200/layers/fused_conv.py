@@ -184,3 +184,134 @@ class MHNNSConvFused(torch.autograd.Function):
         sink.bias(b10, dh1)
         sink.flush()      # all bias / LayerNorm-affine gradients of the layer: one launch
         return (dX, dX0, None, None, None, None, None) + sink.results()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MHNNConv (mhnnm / mhnn: conv.py:87-101) as one hand-scheduled Function, built from two blocks
+# ----------------------------------------------------------------------------------------------------------------------
+def _msg_call(name, *args, **kw):
+    _call(name, 1, *args, _stream(), **kw)
+
+
+class _PairScatter:
+    """reduce over `group` of W(cat(a[vertex], b[edges])) for a fusable 2-layer MLP W (first Linear split over the
+    concat, last Linear commuted with the reduction): a [N,C], b [E,C] -> [E,C] (group 'e') or [N,C] (group 'v')."""
+
+    def __init__(self, p, eps, inc, group, mode, C):
+        self.w0, self.b0, self.g, self.t, self.w1, self.b1 = p
+        self.eps, self.inc, self.group, self.mode, self.C = eps, inc, group, mode, C
+        self.n_out = inc.E if group == "e" else inc.N
+        self.rowscale = inc.nonempty(group) if mode == MEAN else inc.counts(group)
+
+    def fwd(self, a, b):
+        inc, C = self.inc, self.C
+        self.a, self.b = a, b
+        self.A = gemm_raw(a, True, self.w0[:, :C], True, inc.N, C, C)
+        self.B = gemm_raw(b, True, self.w0[:, C:], True, inc.E, C, C, bias=self.b0)
+        self.U = torch.empty((self.n_out, C), dtype=torch.float32, device=a.device)
+        if self.group == "v":
+            ia, ib, rp = None, inc.edge_by_v, inc.rowptr_v
+        else:
+            ia, ib, rp = inc.vtx_by_e, None, inc.rowptr_e
+        _msg_call("eqh_fused_msg_fwd", _p(self.A), _p(self.B), _p(ia), _p(ib), _p(rp), self.n_out, C, _p(self.g), _p(self.t),
+                  self.eps, self.mode, _p(self.U))
+        return gemm_raw(self.U, True, self.w1, True, self.n_out, C, C, bias=self.b1, rowscale=self.rowscale)
+
+    def bwd(self, dout, sink, da_acc=None, db_acc=None):
+        """-> (da, db); da_acc / db_acc: gradients to accumulate into (GEMM epilogue, in place)."""
+        inc, C, dev = self.inc, self.C, dout.device
+        dU = gemm_raw(dout, True, self.w1, False, self.n_out, C, C)
+        sink.weight(self.w1, dout, self.U)
+        sink.bias(self.b1, dout, roww=self.rowscale)
+        dA, dB = torch.empty_like(self.A), torch.empty_like(self.B)
+        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev)
+        A, B, g, t, eps = self.A, self.B, self.g, self.t, self.eps
+        if self.group == "v":
+            u_rp = inc.rowptr_v if self.mode == MEAN else None
+            _msg_call("eqh_fused_msg_bwd", _p(A), _p(B), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), inc.N, C, _p(g), _p(t),
+                      eps, _p(dU), _p(u_rp), _p(dA), _p(part))
+            _msg_call("eqh_fused_msg_bwd", _p(A), _p(B), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), inc.E, C,
+                      _p(g), _p(t), eps, _p(dU), _p(u_rp), _p(dB), None)
+        else:
+            u_rp = inc.rowptr_e if self.mode == MEAN else None
+            _msg_call("eqh_fused_msg_bwd", _p(A), _p(B), _p(inc.vtx_by_e), None, None, _p(inc.rowptr_e), inc.E, C, _p(g), _p(t),
+                      eps, _p(dU), _p(u_rp), _p(dB), _p(part))
+            _msg_call("eqh_fused_msg_bwd", _p(A), _p(B), None, _p(inc.edge_by_v), _p(inc.edge_by_v), _p(inc.rowptr_v), inc.N, C,
+                      _p(g), _p(t), eps, _p(dU), _p(u_rp), _p(dA), None)
+        sink.affine(self.g, self.t, part)
+        da = gemm_raw(dA, True, self.w0[:, :C], False, inc.N, C, C, out=da_acc, residual=da_acc)
+        db = gemm_raw(dB, True, self.w0[:, C:], False, inc.E, C, C, out=db_acc, residual=db_acc)
+        sink.weight(self.w0, dA, self.a, cols=slice(0, C))
+        sink.weight(self.w0, dB, self.b, cols=slice(C, 2 * C))
+        sink.bias(self.b0, dB)
+        return da, db
+
+
+class _ConcatMLP:
+    """W(cat(x, y)) for a 2-layer MLP with LayerNorm on rows [R, 2C] -> [R, C]; the concat is never materialised."""
+
+    def __init__(self, p, eps, C):
+        self.w0, self.b0, self.g, self.t, self.w1, self.b1 = p
+        self.eps, self.C = eps, C
+
+    def fwd(self, x, y):
+        C, R = self.C, x.shape[0]
+        self.x, self.y = x, y
+        h = gemm_raw(x, True, self.w0[:, :C], True, R, C, C, bias=self.b0)
+        gemm_raw(y, True, self.w0[:, C:], True, R, C, C, out=h, residual=h)
+        self.h = h
+        self.yln = _rowln_fwd(h, self.g, self.t, self.eps)
+        return gemm_raw(self.yln, True, self.w1, True, R, C, C, bias=self.b1)
+
+    def bwd(self, dout, sink, dx_acc=None, dy_acc=None):
+        C, R = self.C, dout.shape[0]
+        dyln = gemm_raw(dout, True, self.w1, False, R, C, C)
+        sink.weight(self.w1, dout, self.yln)
+        sink.bias(self.b1, dout)
+        dh, part = _rowln_bwd(self.h, self.g, self.eps, dyln)
+        sink.affine(self.g, self.t, part)
+        dx = gemm_raw(dh, True, self.w0[:, :C], False, R, C, C, out=dx_acc, residual=dx_acc)
+        dy = gemm_raw(dh, True, self.w0[:, C:], False, R, C, C, out=dy_acc, residual=dy_acc)
+        sink.weight(self.w0, dh, self.x, cols=slice(0, C))
+        sink.weight(self.w0, dh, self.y, cols=slice(C, 2 * C))
+        sink.bias(self.b0, dh)
+        return dx, dy
+
+
+class MHNNConvFused(torch.autograd.Function):
+    """(X [N,C], E [E,C]) -> (W4(cat(X, aggr_v W3(cat(X[v], E'[e])))), E' = W2(cat(E, aggr_e W1(cat(X[v], E[e])))))."""
+
+    @staticmethod
+    def forward(ctx, X, E, inc, aggr, direct, eps, *params):
+        X = ops._f32(X, "MHNNConv X")
+        E = ops._f32(E, "MHNNConv E")
+        C = X.shape[1]
+        mode = _MODES[aggr]
+        p = [params[6 * k:6 * k + 6] for k in range(4)]
+        b1 = _PairScatter(p[0], eps[0], inc, "e", mode, C)
+        b2 = _ConcatMLP(p[1], eps[1], C)
+        b3 = _PairScatter(p[2], eps[2], inc, "v", mode, C)
+        b4 = _ConcatMLP(p[3], eps[3], C)
+        Me = b1.fwd(X, E)                              # conv.py:90-93
+        E2 = b2.fwd(E, Me)                             # conv.py:94
+        Mv = b3.fwd(X, E2)                             # conv.py:96-97
+        X2 = b4.fwd(X, Mv)                             # conv.py:98
+        ctx.blocks, ctx.direct, ctx.params = (b1, b2, b3, b4), direct, params
+        ctx.save_for_backward(*params)                 # (the activations live on the blocks: internal tensors)
+        return X2, E2
+
+    @staticmethod
+    def backward(ctx, dX2, dE2):
+        params = ctx.saved_tensors
+        b1, b2, b3, b4 = ctx.blocks
+        sink = _GradSink(params, ctx.direct)
+        dev = params[0].device
+        N, Eh, C = b3.inc.N, b3.inc.E, b1.C
+        dX2 = ops._f32(dX2, "MHNNConv grad X") if dX2 is not None else torch.zeros((N, C), dtype=torch.float32, device=dev)
+        dX, dMv = b4.bwd(dX2, sink)
+        dE2_acc = ops._f32(dE2, "MHNNConv grad E").clone() if dE2 is not None else None
+        dX, dE2_tot = b3.bwd(dMv, sink, da_acc=dX, db_acc=dE2_acc)
+        dE, dMe = b2.bwd(dE2_tot, sink)
+        dX, dE = b1.bwd(dMe, sink, da_acc=dX, db_acc=dE)
+        sink.flush()
+        return (dX, dE, None, None, None, None) + sink.results()
