@@ -371,6 +371,7 @@ int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const float* wc, c
   const int HC = (int)((H + kBwdMaxThreads - 1) / kBwdMaxThreads);
   int T = (int)((H + HC - 1) / HC);
   T = (T + 31) / 32 * 32;
+  if (T < 96) T = 96;   // the prefetch of S2 / d2 / dMi uses threads 0..71 (threads past H own no column)
   const unsigned grid = kPartialRows;  // every CTA writes its partial row (zeros when it owns no atom)
   // double-buffered: 16 neighbour rows of Q + the atom's P row + its S2 block, dMi and d2
   const size_t qsmem = sizeof(float) * 2 * ((size_t)(kNbr + 1) * H + kNbr * kM + kM + kNbr);

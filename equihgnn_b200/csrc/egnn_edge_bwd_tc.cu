@@ -1,0 +1,444 @@
+// EGNN edge model phi_e + neighbour pooling, BACKWARD, on the tcgen05 tensor cores.
+//
+// Autograd of egnn_layer.py:298-310,357-358 in the split form of egnn_edge_tc.cu
+//     pre = P[i] + Q[j] + d2*wc ;  hid = SiLU(pre) ;  s2 = hid.W2^T + b2 ;  m_i = sum_k SiLU(s2)
+// given dMi [N,16]:
+//     dS2[e,o] = dMi[i,o] * SiLU'(S2[e,o])                                  (CUDA cores, 16 values per edge)
+//     dH[e,c]  = sum_o dS2[e,o] W2[o,c]                                     (tensor cores, MMA 1)
+//     dPre     = dH * SiLU'(pre) ;  dP[i] = sum_k dPre ;  dwc = sum_e d2 dPre   (CUDA cores, one pass over Q[j])
+//     dW2[o,c] = sum_e dS2[e,o] hid[e,c]                                    (tensor cores, MMA 2)
+// The CUDA-core kernel (egnn_edge.cu) spends 32 of its ~50 instructions per (edge, column) on the two 16-wide
+// contractions; here they cost 14 small tcgen05.mma per 32 edges x 128 columns.
+//
+// Everything is TRANSPOSED relative to the forward kernel so that no operand ever has to be transposed in shared
+// memory: a CTA owns ONE group of 128 hidden columns (= the 128 TMEM lanes) for a contiguous slice of the edges.
+//   MMA 1   D1[c, e]  = W2T[c, o] . dS2[e, o]^T      A = W2^T tile (K-major, shared memory, loaded once per CTA)
+//                                                    B = dS2 block [32 edges][hi 16 | lo 16] (K-major)
+//   thread c (one per lane) reads D1[c, 0..31] from TMEM; Q[j, c] / P[i, c] come from bulk-copied row segments in
+//   shared memory (lanes = consecutive columns), dP and dwc accumulate in registers in edge order (deterministic), dPre rows are coalesced
+//   stores, and hid[c, e] goes straight back into TENSOR MEMORY (tcgen05.st, hi | lo) as the A operand of
+//   MMA 2   D2[c, o] += hid[c, e] . dS2T[o, e]^T     A from TMEM (TS form), B = dS2 transposed [hi 16 | lo 16 rows][32 edges]
+// fp32-faithful (3xTF32: lo.hi + hi.lo + hi.hi as in gemm_tf32x3.cu).  D2 is drained into fp32 registers every 8
+// blocks (two TMEM buffers), so no accumulator sees more than 64 tensor-core accumulations.
+//
+// Warp roles (18 warps):
+//   warps 0-3    dS2 producer (4 values per thread and block), writes both layouts + the block's j / d2 / atom ids;
+//                drains D2; finishes dW2 / dwc / db2 partials
+//   warps 4-15   three "column" warpgroups, round-robin over the blocks: the per-(edge, column) math above
+//   warp 16      MMA issuer (warp-uniform loop, one elected lane), MMA 2 lags MMA 1 by three blocks
+//   warp 17      loader: 34 bulk copies (cp.async.bulk, 512 B each) per block bring the Q[j] / P[i] row segments into an
+//                8-stage shared-memory ring; the column threads read them conflict-free (lane = column)
+// Grid: ceil(H/128) column groups x S edge slices (S = 148 / groups); part row s receives the slice's partial sums.
+#include "tc_common.cuh"
+
+namespace eqh {
+namespace edge_bwd_tc {
+using namespace eqh::tc;
+
+constexpr int kM = EQH_M_DIM;       // 16
+constexpr int kNbr = EQH_KNN_K;     // 16
+constexpr int GC = 128;             // hidden columns per CTA (TMEM lanes)
+constexpr int EB = 32;              // edges per block: two atoms
+constexpr int NSLOT = 4;            // blocks in flight
+constexpr int LAG = 3;              // MMA 2 of block b is issued after MMA 1 of block b + LAG
+constexpr int kEpiWG = 3;
+constexpr int kFlush = 8;           // blocks per D2 accumulation round
+constexpr int QST = 8;              // stages of the Q / P row ring (bulk-copied 512-byte row segments)
+constexpr int kMmaWarp = 4 + 4 * kEpiWG;
+constexpr int kLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = (kLoadWarp + 1) * 32;
+static_assert(kM == 16 && kNbr == 16, "layouts below assume 16 x 16");
+static_assert(LAG == NSLOT - 1 && LAG >= kEpiWG, "pipeline depth");
+
+// tensor memory columns
+constexpr uint32_t kD2Col = 0;                     // 2 buffers x 32 (hi-product columns | lo-product columns)
+constexpr uint32_t kD1Col = 64;                    // NSLOT x 32
+constexpr uint32_t kA2Col = kD1Col + 32 * NSLOT;   // NSLOT x 64 (hid hi | hid lo)
+static_assert(kA2Col + 64 * NSLOT <= 512, "TMEM budget");
+
+// shared memory
+struct Meta {
+  int32_t j[EB];
+  float dd[EB];
+  int32_t atom[2];
+};
+constexpr uint32_t kW2TBytes = GC * 128;           // [128 c][hi 16 | lo 16] K-major, 128B swizzle
+constexpr uint32_t kBBytes = EB * 128;             // 4 KB: B1 [32 e][hi 16 | lo 16], B2 [hi 16 | lo 16 rows][32 e]
+constexpr uint32_t kOffB1 = kW2TBytes;
+constexpr uint32_t kOffB2 = kOffB1 + NSLOT * kBBytes;
+constexpr uint32_t kOffMeta = kOffB2 + NSLOT * kBBytes;
+constexpr uint32_t kMetaStride = 512;
+constexpr uint32_t kOffBar = kOffMeta + NSLOT * kMetaStride;
+constexpr uint32_t kOffRedWc = kOffBar + 512;                       // [kEpiWG][128] floats
+constexpr uint32_t kOffRedDb = kOffRedWc + kEpiWG * GC * 4;         // [128][4] floats
+constexpr uint32_t kQRows = EB + 2;                                 // 32 neighbour rows of Q + the two atoms' rows of P
+constexpr uint32_t kQStageBytes = kQRows * GC * 4;                  // 17 KB
+constexpr uint32_t kOffQ = (kOffRedDb + 128 * 4 * 4 + 127) / 128 * 128;
+constexpr uint32_t kSmem = kOffQ + QST * kQStageBytes;
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(Meta) <= kMetaStride, "meta block");
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// 16 consecutive TMEM columns of this thread's lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a K-major tile with 128-byte rows and the 128B swizzle
+__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ wc,
+              const float* __restrict__ W2, const int32_t* __restrict__ idx, const float* __restrict__ d2,
+              const float* __restrict__ S2, const float* __restrict__ dMi, int64_t N, int H, int ngroups, int nslices,
+              float* __restrict__ dP, float* __restrict__ dPre, float* __restrict__ part, int64_t part_cols,
+              const int32_t* __restrict__ order) {
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* ds_full = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [NSLOT] dS2 tiles + meta written
+  uint64_t* d1_full = ds_full + NSLOT;                               // [NSLOT] MMA 1 done
+  uint64_t* a2_full = d1_full + NSLOT;                               // [NSLOT] hid written to TMEM
+  uint64_t* slot_free = a2_full + NSLOT;                             // [NSLOT] MMA 2 done: tiles, D1 and A2 reusable
+  uint64_t* d2_full = slot_free + NSLOT;                             // [2] accumulation round complete
+  uint64_t* d2_empty = d2_full + 2;                                  // [2] drained into registers
+  uint64_t* q_full = d2_empty + 2;                                   // [QST] Q / P row segments landed
+  uint64_t* q_free = q_full + QST;                                   // [QST] ... and consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_free + QST);
+  static_assert((4 * NSLOT + 4 + 2 * QST) * 8 + 4 <= 512, "barrier block");
+  float* red_wc = reinterpret_cast<float*>(smem + kOffRedWc);
+  float* red_db = reinterpret_cast<float*>(smem + kOffRedDb);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % ngroups;          // column group
+  const int sl = blockIdx.x / ngroups;         // edge slice (= row of `part`)
+  const int64_t nblk = (N + 1) >> 1;           // blocks of two atoms
+  const int64_t b_begin = nblk * sl / nslices, b_end = nblk * (sl + 1) / nslices;
+  const int nb = (int)(b_end - b_begin);
+  const int64_t ld = H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&ds_full[s], 4);
+      mbar_init(&d1_full[s], 1);
+      mbar_init(&a2_full[s], 4);
+      mbar_init(&slot_free[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&d2_full[b], 1);
+      mbar_init(&d2_empty[b], 128);
+    }
+    for (int s = 0; s < QST; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_free[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+  // W2^T tile of this column group: row c = [W2[0..15, col] raw | their tf32 remainders]; zero rows past H
+  for (int t = threadIdx.x; t < GC * kM; t += kThreads) {
+    const int c = t & (GC - 1), o = t >> 7;
+    const int col = g * GC + c;
+    const float w = col < H ? __ldg(W2 + (int64_t)o * H + col) : 0.f;
+    *reinterpret_cast<float*>(smem + sw128(c, o >> 2) + (o & 3) * 4) = w;
+    *reinterpret_cast<float*>(smem + sw128(c, 4 + (o >> 2)) + (o & 3) * 4) = tf32_lo(w);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ============================ dS2 producer / D2 drain ============================
+    const int t = threadIdx.x;           // 0..127 (= column c for the drain)
+    const int el = t >> 2, oq = t & 3;   // edge of the block, quad of outputs
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[kM];                       // dW2[0..15, column t] of this slice
+#pragma unroll
+    for (int o = 0; o < kM; ++o) acc[o] = 0.f;
+    auto drain = [&](uint32_t r) {
+      const uint32_t buf = r & 1u;
+      mbar_wait(&d2_full[buf], (r >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float v[32];
+      tmem_ld32(tmem_base + lane_off + kD2Col + buf * 32, v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&d2_empty[buf]);
+#pragma unroll
+      for (int o = 0; o < kM; ++o) acc[o] += v[o] + v[kM + o];
+    };
+    uint32_t drained = 0;
+    for (int bl = 0; bl < nb; ++bl) {
+      const int s = bl % NSLOT;
+      const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
+      const int64_t aslot = (b_begin + bl) * 2 + (el >> 4);
+      const bool ok = aslot < N;
+      const int64_t atom = ok ? (order ? (int64_t)__ldg(order + aslot) : aslot) : 0;
+      const int64_t e = atom * kNbr + (el & 15);
+      float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+      int32_t jj = 0;
+      float dd = 0.f;
+      if (ok) {
+        const float4 s2 = __ldg(reinterpret_cast<const float4*>(S2 + e * kM) + oq);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(dMi + atom * kM) + oq);
+        ds = make_float4(gm.x * dsilu_f(s2.x), gm.y * dsilu_f(s2.y), gm.z * dsilu_f(s2.z), gm.w * dsilu_f(s2.w));
+        if (oq == 0) {
+          jj = __ldg(idx + e);
+          dd = __ldg(d2 + e);
+        }
+      }
+      const float4 dl = make_float4(tf32_lo(ds.x), tf32_lo(ds.y), tf32_lo(ds.z), tf32_lo(ds.w));
+      mbar_wait(&slot_free[s], ph ^ 1u);
+      uint8_t* b1 = smem + kOffB1 + s * kBBytes;
+      uint8_t* b2 = smem + kOffB2 + s * kBBytes;
+      *reinterpret_cast<float4*>(b1 + sw128(el, oq)) = ds;
+      *reinterpret_cast<float4*>(b1 + sw128(el, 4 + oq)) = dl;
+      {
+        const float hv[4] = {ds.x, ds.y, ds.z, ds.w}, lv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t n = oq * 4 + u;
+          *reinterpret_cast<float*>(b2 + sw128(n, el >> 2) + (el & 3) * 4) = hv[u];
+          *reinterpret_cast<float*>(b2 + sw128(kM + n, el >> 2) + (el & 3) * 4) = lv[u];
+        }
+      }
+      Meta* m = reinterpret_cast<Meta*>(smem + kOffMeta + s * kMetaStride);
+      if (oq == 0) {
+        m->j[el] = jj;
+        m->dd[el] = dd;
+        if ((el & 15) == 0) m->atom[el >> 4] = ok ? (int32_t)atom : -1;
+      }
+      db[0] += ds.x; db[1] += ds.y; db[2] += ds.z; db[3] += ds.w;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[s]);
+      // the round before the current one finished kFlush/2 blocks ago: by now its MMAs have completed
+      if ((bl % kFlush) == kFlush / 2 && bl >= kFlush) {
+        drain((uint32_t)(bl / kFlush) - 1u);
+        drained = (uint32_t)(bl / kFlush);
+      }
+    }
+    const uint32_t nrounds = (uint32_t)((nb + kFlush - 1) / kFlush);
+    for (uint32_t r = drained; r < nrounds; ++r) drain(r);
+    *reinterpret_cast<float4*>(red_db + t * 4) = make_float4(db[0], db[1], db[2], db[3]);
+    if (g * GC + t < H) {
+      float* row = part + (int64_t)sl * part_cols + g * GC + t;
+#pragma unroll
+      for (int o = 0; o < kM; ++o) row[(int64_t)o * H] = acc[o];
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(GC >> 4) << 24);
+    constexpr uint32_t idesc16 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(GC >> 4) << 24);
+    const uint32_t w2t = smem_u32(smem);
+    for (int step = 0; step < nb + LAG; ++step) {
+      if (step < nb) {
+        const int s = step % NSLOT;
+        const uint32_t ph = (uint32_t)(step / NSLOT) & 1u;
+        mbar_wait(&ds_full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b1 = smem_u32(smem + kOffB1 + s * kBBytes);
+        const uint32_t d1 = tmem_base + kD1Col + s * 32;
+        if (elect_one()) {
+          // D1[c, e] = sum_o W2T[c, o] dS2[e, o]: lo.hi, hi.lo (small terms first), then hi.hi; two k-steps of 8 each
+          umma_tf32(d1, make_desc(w2t + 64, 0, 1024, 2), make_desc(b1, 0, 1024, 2), idesc32, 0);
+          umma_tf32(d1, make_desc(w2t + 96, 0, 1024, 2), make_desc(b1 + 32, 0, 1024, 2), idesc32, 1);
+          umma_tf32(d1, make_desc(w2t, 0, 1024, 2), make_desc(b1 + 64, 0, 1024, 2), idesc32, 1);
+          umma_tf32(d1, make_desc(w2t + 32, 0, 1024, 2), make_desc(b1 + 96, 0, 1024, 2), idesc32, 1);
+          umma_tf32(d1, make_desc(w2t, 0, 1024, 2), make_desc(b1, 0, 1024, 2), idesc32, 1);
+          umma_tf32(d1, make_desc(w2t + 32, 0, 1024, 2), make_desc(b1 + 32, 0, 1024, 2), idesc32, 1);
+          umma_commit(&d1_full[s]);
+        }
+        __syncwarp();
+      }
+      if (step >= LAG) {
+        const int bl = step - LAG;
+        const int s = bl % NSLOT;
+        const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
+        const uint32_t r = (uint32_t)(bl / kFlush), buf = r & 1u;
+        const bool first = (bl % kFlush) == 0;
+        if (first) mbar_wait(&d2_empty[buf], ((r >> 1) & 1u) ^ 1u);     // drained two rounds ago
+        mbar_wait(&a2_full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b2 = smem_u32(smem + kOffB2 + s * kBBytes);
+        const uint32_t aH = tmem_base + kA2Col + s * 64, aL = aH + 32;
+        const uint32_t dacc = tmem_base + kD2Col + buf * 32;
+        const bool last = (bl % kFlush) == kFlush - 1 || bl == nb - 1;
+        if (elect_one()) {
+          // D2[c, 0..15] += hid_hi.dS2_hi + hid_lo.dS2_hi ;  D2[c, 16..31] += hid_hi.dS2_lo   (summed by the drain)
+#pragma unroll
+          for (int ks = 0; ks < EB / 8; ++ks) {
+            const uint64_t db2 = make_desc(b2 + ks * 32, 0, 1024, 2);
+            umma_tf32_ts(dacc, aH + ks * 8, db2, idesc32, (first && ks == 0) ? 0u : 1u);
+            umma_tf32_ts(dacc, aL + ks * 8, db2, idesc16, 1u);
+          }
+          umma_commit(&slot_free[s]);
+          if (last) umma_commit(&d2_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kLoadWarp) {
+    // ============================ Q / P row loader ============================
+    // lane l bulk-copies the 512-byte segment (this CTA's 128 columns) of Q[j] of edge l of the block; lanes 0 and 1
+    // also the two atoms' segments of P.  QST blocks ahead of the math: the gather latency never reaches a register.
+    const uint32_t row_bytes = (uint32_t)min(GC, H - g * GC) * 4u;
+    for (int bl = 0; bl < nb; ++bl) {
+      const int st = bl % QST;
+      const uint32_t ph = (uint32_t)(bl / QST) & 1u;
+      const int64_t aslot = (b_begin + bl) * 2 + (lane >> 4);
+      const int64_t atom = aslot < N ? (order ? (int64_t)__ldg(order + aslot) : aslot) : 0;   // (rows of atom 0 for a missing atom: finite, unused)
+      const int64_t jrow = __ldg(idx + atom * kNbr + (lane & 15));
+      int64_t prow = 0;
+      if (lane < 2) {
+        const int64_t ps = (b_begin + bl) * 2 + lane;
+        prow = ps < N ? (order ? (int64_t)__ldg(order + ps) : ps) : 0;
+      }
+      mbar_wait(&q_free[st], ph ^ 1u);
+      if (lane == 0) mbar_expect_tx(&q_full[st], kQRows * row_bytes);
+      __syncwarp();
+      uint8_t* dst = smem + kOffQ + st * kQStageBytes;
+      bulk_g2s(dst + lane * (GC * 4), Q + jrow * ld + g * GC, row_bytes, &q_full[st]);
+      if (lane < 2) bulk_g2s(dst + (EB + lane) * (GC * 4), P + prow * ld + g * GC, row_bytes, &q_full[st]);
+    }
+  } else {
+    // ============================ column warpgroups ============================
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;                        // TMEM lane quadrant
+    const int c = q * 32 + lane;
+    const int col = g * GC + c;
+    const bool cv = col < H;
+    const float wcr = cv ? __ldg(wc + col) : 0.f;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float dwc = 0.f;
+    for (int bl = wg; bl < nb; bl += kEpiWG) {
+      const int s = bl % NSLOT;
+      const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
+      mbar_wait(&ds_full[s], ph);
+      const Meta* m = reinterpret_cast<const Meta*>(smem + kOffMeta + s * kMetaStride);
+      const int32_t a0 = m->atom[0], a1 = m->atom[1];
+      const int st = bl % QST;
+      mbar_wait(&q_full[st], (uint32_t)(bl / QST) & 1u);
+      const float* qs = reinterpret_cast<const float*>(smem + kOffQ + st * kQStageBytes) + c;
+      mbar_wait(&d1_full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d1 = tmem_base + lane_off + kD1Col + s * 32;
+      const uint32_t a2 = tmem_base + lane_off + kA2Col + s * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int32_t at = half ? a1 : a0;
+        const bool wr = cv && at >= 0;
+        const float pi = wr ? qs[(EB + half) * GC] : 0.f;
+        float dh[kNbr], hv[kNbr];
+        tmem_ld16(d1 + half * 16, dh);
+        float dpa = 0.f;
+        float* dprow = dPre + ((int64_t)(at >= 0 ? at : 0) * kNbr) * ld + col;
+#pragma unroll
+        for (int k = 0; k < kNbr; ++k) {
+          const float dd = m->dd[half * 16 + k];
+          const float pre = (pi + (cv ? qs[(half * 16 + k) * GC] : 0.f)) + dd * wcr;
+          float ex, sg;                                   // SFU approximations (~1 ulp each), see egnn_edge_tc.cu
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre * -1.4426950408889634f));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + ex));
+          const float hid = pre * sg;
+          const float dsl = sg * (1.f + pre * (1.f - sg));
+          const float dpre = dh[k] * dsl;
+          dpa += dpre;
+          dwc += dd * dpre;
+          if (wr) dprow[(int64_t)k * ld] = dpre;
+          hv[k] = hid;
+        }
+        if (wr) dP[(int64_t)at * ld + col] = dpa;
+        tmem_st16(a2 + half * 16, hv);                    // hi: the tensor core ignores the low 13 bits
+#pragma unroll
+        for (int k = 0; k < kNbr; ++k) hv[k] = tf32_lo(hv[k]);
+        tmem_st16(a2 + 32 + half * 16, hv);               // lo
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a2_full[s]);
+        mbar_arrive(&q_free[st]);
+      }
+    }
+    red_wc[wg * GC + c] = dwc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (warp < 4) {
+    // ---- partial sums of this (group, slice) -> row `sl` of part
+    const int t = threadIdx.x;
+    float* row = part + (int64_t)sl * part_cols;
+    const int col = g * GC + t;
+    if (col < H) {
+      float w = 0.f;
+#pragma unroll
+      for (int k = 0; k < kEpiWG; ++k) w += red_wc[k * GC + t];
+      row[(int64_t)kM * H + col] = w;
+    }
+    if (g == 0 && t < kM) {
+      float b = 0.f;
+      for (int e2 = 0; e2 < EB; ++e2) b += red_db[(e2 * 4 + (t >> 2)) * 4 + (t & 3)];
+      row[(int64_t)(kM + 1) * H + t] = b;
+    }
+  }
+}
+
+static int groups_of(int64_t H) { return (int)((H + GC - 1) / GC); }
+static int slices_of(int64_t H) {
+  const int gr = groups_of(H);
+  const int s = kSMs / gr;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace edge_bwd_tc
+}  // namespace eqh
+
+extern "C" {
+
+int eqh_egnn_edge_bwd_tc_rows(int64_t H) { return H > 0 ? eqh::edge_bwd_tc::slices_of(H) : 0; }
+
+int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const int32_t* idx,
+                         const float* d2, const float* S2, const float* dMi, int64_t N, int64_t H, float* dP, float* dPre,
+                         float* part, const int32_t* order, eqh_stream_t stream) {
+  using namespace eqh;
+  using namespace eqh::edge_bwd_tc;
+  EQH_CHECK_ARG(P && Q && wc && W2 && idx && d2 && S2 && dMi && dP && dPre && part && N >= 0);
+  EQH_CHECK_ARG(aligned16(S2) && aligned16(dMi));
+  if (H <= 0 || H % 64 != 0 || groups_of(H) > kSMs) return EQH_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  if (e != cudaSuccess) return (int)e;
+  const int gr = groups_of(H), sl = slices_of(H);
+  const int64_t part_cols = (int64_t)(kM + 1) * H + kM;
+  launch_kernel(k_edge_bwd_tc, dim3((unsigned)(gr * sl)), dim3(kThreads), (size_t)kSmem, static_cast<cudaStream_t>(stream), P, Q, wc,
+                W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order);
+  EQH_LAUNCH_RC();
+}
+
+}  // extern "C"

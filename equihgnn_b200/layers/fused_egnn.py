@@ -73,11 +73,7 @@ class EGNNFused(torch.autograd.Function):
         if graph.rowptr_j is None:
             graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
         cols = (M_DIM + 1) * Hp + M_DIM
-        dP = torch.empty_like(P)
-        dPre = torch.empty((N * KNN_K, Hp), dtype=torch.float32, device=dev)
-        part = torch.empty((partial_rows(), cols), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_bwd_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), _p(S2),
-              _p(dMi), None, N, Hp, _p(dP), _p(dPre), None, _p(part), _p(graph.order), _stream())
+        dP, dPre, _, part = ops.egnn_edge_bwd_raw(P, Q, wc, W2p, b2, graph, graph.d2, S2, dMi, None, False)
         dQ = gather_reduce_raw(dPre, graph.perm_j, graph.rowptr_j, None, N, SUM)
         # dh = dOut (residual) + dP.W1a + dQ.W1b + LayerNorm backward
         dh = gemm_raw(dP, True, W1a, False, N, C, Hp, residual=dOut)

@@ -792,6 +792,30 @@ def build_knn_graph(pos: torch.Tensor, need_transpose: bool = True) -> KnnGraph:
     return KnnGraph(idx, d2, rowptr_j, perm_j, order)
 
 
+def egnn_edge_bwd_raw(P, Q, wc, W2, b2, graph, d2, S2, dMi, dMij, need_dd2: bool):
+    """Backward of the phi_e edge kernel.  Returns (dP [N,H], dPre [N*16,H], dd2 | None, part [rows, 17H+16]); the
+    weight-gradient partials in `part` are finished with a column sum.  The case egnn_equihnns trains (only dMi, no
+    gradient w.r.t. the distances) runs on the tensor cores (eqh_egnn_edge_bwd_tc); EQH_EDGE_BWD=simt or any other case
+    selects the CUDA-core kernel of the same math."""
+    N, H = P.shape
+    dev = P.device
+    cols = (M_DIM + 1) * H + M_DIM
+    dP = torch.empty_like(P)
+    dPre = torch.empty((N * KNN_K, H), dtype=torch.float32, device=dev)
+    if dMi is not None and dMij is None and not need_dd2 and os.environ.get("EQH_EDGE_BWD", "tc") != "simt":
+        rows = _lib.load().eqh_egnn_edge_bwd_tc_rows(H)
+        part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        _call("eqh_egnn_edge_bwd_tc", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(graph.idx), _p(d2), _p(S2), _p(dMi), N, H,
+              _p(dP), _p(dPre), _p(part), _p(graph.order), _stream(), nbytes=4.0 * N * KNN_K * H * M_DIM)
+        return dP, dPre, None, part
+    dd2 = torch.empty_like(d2) if need_dd2 else None
+    part = torch.empty((partial_rows(), cols), dtype=torch.float32, device=dev)
+    _call("eqh_egnn_edge_bwd_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(graph.idx), _p(d2), _p(S2), _p(dMi),
+          _p(dMij), N, H, _p(dP), _p(dPre), _p(dd2), _p(part), _p(graph.order), _stream())
+    return dP, dPre, dd2, part
+
+
+
 class _EgnnEdge(torch.autograd.Function):
     """(P, Q, wc, W2, b2, d2) -> (m_i [N,16], m_ij [N,16,16]) -- see eqh_egnn_edge_fwd."""
 
@@ -829,14 +853,7 @@ class _EgnnEdge(torch.autograd.Function):
         dMij = _f32(dMij, "egnn_edge dMij") if dMij is not None else None
         if g.rowptr_j is None:
             g.rowptr_j, g.perm_j, _, _ = csr_build(g.idx.view(-1), N, None)
-        rows = partial_rows()
-        cols = (M_DIM + 1) * H + M_DIM
-        dP = torch.empty_like(P)
-        dPre = torch.empty((N * KNN_K, H), dtype=torch.float32, device=dev)
-        dd2 = torch.empty_like(d2) if ctx.needs_input_grad[5] else None
-        part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        _call("eqh_egnn_edge_bwd_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2), _p(b2), _p(g.idx), _p(d2), _p(S2), _p(dMi),
-              _p(dMij), N, H, _p(dP), _p(dPre), _p(dd2), _p(part), _p(g.order), _stream())
+        dP, dPre, dd2, part = egnn_edge_bwd_raw(P, Q, wc, W2, b2, g, d2, S2, dMi, dMij, ctx.needs_input_grad[5])
         red = colsum_raw(part)
         dW2 = red[:M_DIM * H].view(M_DIM, H)
         dwc = red[M_DIM * H:(M_DIM + 1) * H]

@@ -225,6 +225,17 @@ EQH_API int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const floa
                               int64_t N, int64_t H, float* dP, float* dPre, float* dd2, float* part, const int32_t* order,
                               eqh_stream_t stream);
 
+/* Backward on the tcgen05 tensor cores (egnn_edge_bwd_tc.cu) for the case egnn_equihnns trains: only dMi given
+ * (no dMij), no gradient w.r.t. d2.  Both 16-wide contractions (dH = dS2.W2, dW2 = dS2^T.hid) run as 3xTF32 MMAs; a
+ * CTA owns 128 hidden columns (the TMEM lanes) for a slice of the edges, hid goes back to tensor memory as the A
+ * operand of the weight-gradient MMA.  Same outputs as eqh_egnn_edge_bwd_ordered (dP, dPre identical up to fp32
+ * rounding of the contraction), except that `part` has eqh_egnn_edge_bwd_tc_rows(H) rows (<= eqh_partial_rows()),
+ * every one of them fully written.  order: optional visiting order of the atoms (NULL = natural). */
+EQH_API int eqh_egnn_edge_bwd_tc_rows(int64_t H);
+EQH_API int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const int32_t* idx,
+                         const float* d2, const float* S2, const float* dMi, int64_t N, int64_t H, float* dP, float* dPre,
+                         float* part, const int32_t* order, eqh_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * AtomEncoder (third-party ogb==1.3.6; call sites mhnn.py:201, equihnn_egnn.py:157):
  *     out[n,:] = sum_f tables[f][x[n,f], :]            x [N,F] int64, tables[f] [rows_per_table[f], C]

@@ -299,6 +299,66 @@ def test_egnn_edge_fwd_bwd(C):
         assert rel_err(got.grad, want.grad) < TOL, name
 
 
+@pytest.mark.parametrize("profile,B,H,ordered", [("qm9", 12, 64, False), ("qm9", 13, 192, False), ("qm9", 128, 1088, False),
+                                                  ("molecule3d", 320, 320, True), ("molecule3d", 121, 1088, True)])
+def test_egnn_edge_bwd_tc_matches_the_cuda_core_kernel_and_fp64(profile, B, H, ordered):
+    """eqh_egnn_edge_bwd_tc (both 16-wide contractions of the phi_e backward on tcgen05, 3xTF32) against the CUDA-core
+    kernel of the same math and against an fp64 restatement: dP / dPre / weight-gradient partial sums, odd atom counts
+    (half-empty last block), a last column group that is half empty (H % 128 == 64) and the cell visiting order."""
+    b = synthetic.make_batch(profile, B, 5)
+    pos = b.pos.to(DEV)
+    N = b.num_atoms
+    if ordered:
+        idx, d2, order = ops.knn16(pos, method="grid", return_order=True)
+    else:
+        idx, d2 = ops.knn16(pos)
+        order = None
+    g = torch.Generator().manual_seed(H + B)
+    mk = lambda *s, sc=1.0: (sc * torch.randn(*s, generator=g)).to(DEV)
+    P, Q, wc, W2, b2 = mk(N, H, sc=0.5), mk(N, H, sc=0.5), mk(H, sc=0.3), mk(16, H, sc=0.1), mk(16, sc=0.1)
+    dMi = mk(N, 16)
+    S2 = torch.empty(N * 16, 16, device=DEV); Mi = torch.empty(N, 16, device=DEV)
+    ops._call("eqh_egnn_edge_fwd_tc_ordered", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+              idx.data_ptr(), d2.data_ptr(), N, H, S2.data_ptr(), None, Mi.data_ptr(), ops._p(order), ops._stream())
+    out = {}
+    for name in ("simt", "tc", "tc2"):
+        dP = torch.full_like(P, float("nan")); dPre = torch.full((N * 16, H), float("nan"), device=DEV)
+        if name == "simt":
+            part = torch.empty(ops.partial_rows(), 17 * H + 16, device=DEV)
+            ops._call("eqh_egnn_edge_bwd_ordered", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                      idx.data_ptr(), d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), None, N, H, dP.data_ptr(), dPre.data_ptr(),
+                      None, part.data_ptr(), ops._p(order), ops._stream())
+        else:
+            rows = ops._lib.load().eqh_egnn_edge_bwd_tc_rows(H)
+            assert 1 <= rows <= ops.partial_rows()
+            part = torch.full((rows, 17 * H + 16), float("nan"), device=DEV)
+            ops._call("eqh_egnn_edge_bwd_tc", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), idx.data_ptr(),
+                      d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), N, H, dP.data_ptr(), dPre.data_ptr(), part.data_ptr(),
+                      ops._p(order), ops._stream())
+        out[name] = (dP, dPre, ops.colsum_raw(part))
+    torch.cuda.synchronize()
+    # fp64 restatement
+    Pd, Qd, wcd, W2d = (t.double().cpu() for t in (P, Q, wc, W2))
+    jj = idx.cpu().long()
+    pre = Pd[:, None, :] + Qd[jj] + d2.cpu().double()[..., None] * wcd
+    sg = torch.sigmoid(pre)
+    hid = pre * sg
+    s2 = S2.cpu().double().view(N, 16, 16)
+    s2g = torch.sigmoid(s2)
+    dS2 = dMi.cpu().double()[:, None, :] * (s2g * (1 + s2 * (1 - s2g)))
+    dpre = (dS2 @ W2d) * (sg * (1 + pre * (1 - sg)))
+    want = (dpre.sum(1), dpre.reshape(N * 16, H),
+            torch.cat([(dS2.reshape(-1, 16).t() @ hid.reshape(-1, H)).reshape(-1),
+                       (dpre * d2.cpu().double()[..., None]).sum((0, 1)), dS2.sum((0, 1))]))
+    for name in ("simt", "tc"):
+        for got, ref, what in zip(out[name], want, ("dP", "dPre", "dW2|dwc|db2")):
+            assert torch.isfinite(got).all(), (name, what)
+            assert rel_err(got, ref) < TOL, (name, what)
+    # deterministic: a second launch gives the same bits
+    for a_, b_ in zip(out["tc"], out["tc2"]):
+        assert torch.equal(a_, b_)
+
+
 def test_adam_step_matches_torch():
     g = torch.Generator().manual_seed(0)
     p0 = torch.randn(10001, generator=g)
