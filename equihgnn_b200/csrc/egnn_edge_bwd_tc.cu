@@ -14,20 +14,20 @@
 // memory: a CTA owns ONE group of 128 hidden columns (= the 128 TMEM lanes) for a contiguous slice of the edges.
 //   MMA 1   D1[c, e]  = W2T[c, o] . dS2[e, o]^T      A = W2^T tile (K-major, shared memory, loaded once per CTA)
 //                                                    B = dS2 block [32 edges][hi 16 | lo 16] (K-major)
-//   thread c (one per lane) reads D1[c, 0..31] from TMEM; Q[j, c] / P[i, c] come from bulk-copied row segments in
-//   shared memory (lanes = consecutive columns), dP and dwc accumulate in registers in edge order (deterministic), dPre rows are coalesced
+//   thread c (one per lane) reads D1[c, 0..31] from TMEM; Q[j, c] / P[i, c] come from row segments the warpgroup copied
+//   into shared memory one block ahead (16-byte cp.async, one 512-byte row per warp instruction; per-lane
+//   cp.async.bulk copies were measured first: the uniform-datapath instruction serialises over the lanes, ~90 cycles
+//   per row), dP and dwc accumulate in registers in edge order (deterministic), dPre rows are coalesced
 //   stores, and hid[c, e] goes straight back into TENSOR MEMORY (tcgen05.st, hi | lo) as the A operand of
 //   MMA 2   D2[c, o] += hid[c, e] . dS2T[o, e]^T     A from TMEM (TS form), B = dS2 transposed [hi 16 | lo 16 rows][32 edges]
 // fp32-faithful (3xTF32: lo.hi + hi.lo + hi.hi as in gemm_tf32x3.cu).  D2 is drained into fp32 registers every 8
 // blocks (two TMEM buffers), so no accumulator sees more than 64 tensor-core accumulations.
 //
-// Warp roles (18 warps):
+// Warp roles (17 warps):
 //   warps 0-3    dS2 producer (4 values per thread and block), writes both layouts + the block's j / d2 / atom ids;
 //                drains D2; finishes dW2 / dwc / db2 partials
 //   warps 4-15   three "column" warpgroups, round-robin over the blocks: the per-(edge, column) math above
 //   warp 16      MMA issuer (warp-uniform loop, one elected lane), MMA 2 lags MMA 1 by three blocks
-//   warp 17      loader: 34 bulk copies (cp.async.bulk, 512 B each) per block bring the Q[j] / P[i] row segments into an
-//                8-stage shared-memory ring; the column threads read them conflict-free (lane = column)
 // Grid: ceil(H/128) column groups x S edge slices (S = 148 / groups); part row s receives the slice's partial sums.
 #include "tc_common.cuh"
 
@@ -39,14 +39,13 @@ constexpr int kM = EQH_M_DIM;       // 16
 constexpr int kNbr = EQH_KNN_K;     // 16
 constexpr int GC = 128;             // hidden columns per CTA (TMEM lanes)
 constexpr int EB = 32;              // edges per block: two atoms
-constexpr int NSLOT = 4;            // blocks in flight
+constexpr int NSLOT = 4;            // blocks in flight in tensor memory (D1 / hid slots)
+constexpr int DSLOT = 8;            // dS2 tile + meta ring in shared memory: the producer runs this far ahead
 constexpr int LAG = 3;              // MMA 2 of block b is issued after MMA 1 of block b + LAG
 constexpr int kEpiWG = 3;
 constexpr int kFlush = 8;           // blocks per D2 accumulation round
-constexpr int QST = 8;              // stages of the Q / P row ring (bulk-copied 512-byte row segments)
 constexpr int kMmaWarp = 4 + 4 * kEpiWG;
-constexpr int kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = (kLoadWarp + 1) * 32;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 static_assert(kM == 16 && kNbr == 16, "layouts below assume 16 x 16");
 static_assert(LAG == NSLOT - 1 && LAG >= kEpiWG, "pipeline depth");
 
@@ -65,16 +64,17 @@ struct Meta {
 constexpr uint32_t kW2TBytes = GC * 128;           // [128 c][hi 16 | lo 16] K-major, 128B swizzle
 constexpr uint32_t kBBytes = EB * 128;             // 4 KB: B1 [32 e][hi 16 | lo 16], B2 [hi 16 | lo 16 rows][32 e]
 constexpr uint32_t kOffB1 = kW2TBytes;
-constexpr uint32_t kOffB2 = kOffB1 + NSLOT * kBBytes;
-constexpr uint32_t kOffMeta = kOffB2 + NSLOT * kBBytes;
+constexpr uint32_t kOffB2 = kOffB1 + DSLOT * kBBytes;
+constexpr uint32_t kOffMeta = kOffB2 + DSLOT * kBBytes;
 constexpr uint32_t kMetaStride = 512;
-constexpr uint32_t kOffBar = kOffMeta + NSLOT * kMetaStride;
+constexpr uint32_t kOffBar = kOffMeta + DSLOT * kMetaStride;
 constexpr uint32_t kOffRedWc = kOffBar + 512;                       // [kEpiWG][128] floats
 constexpr uint32_t kOffRedDb = kOffRedWc + kEpiWG * GC * 4;         // [128][4] floats
+constexpr uint32_t kOffAcc = kOffRedDb + 128 * 4 * 4;               // [16][128] floats: dW2 of this slice (drained D2 rounds)
 constexpr uint32_t kQRows = EB + 2;                                 // 32 neighbour rows of Q + the two atoms' rows of P
 constexpr uint32_t kQStageBytes = kQRows * GC * 4;                  // 17 KB
-constexpr uint32_t kOffQ = (kOffRedDb + 128 * 4 * 4 + 127) / 128 * 128;
-constexpr uint32_t kSmem = kOffQ + QST * kQStageBytes;
+constexpr uint32_t kOffQ = (kOffAcc + kM * GC * 4 + 127) / 128 * 128;
+constexpr uint32_t kSmem = kOffQ + 2 * kEpiWG * kQStageBytes;      // per column warpgroup: current + next block
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 static_assert(sizeof(Meta) <= kMetaStride, "meta block");
 
@@ -107,6 +107,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+#ifdef EQH_BWDTC_TRACE
+__device__ unsigned long long g_bt_trace[64];
+#define TW(i, bar, par)                                  \
+  do {                                                   \
+    const long long t0__ = clock64();                    \
+    mbar_wait(bar, par);                                 \
+    tw[i] += clock64() - t0__;                           \
+  } while (0)
+#define TS(i)                                 \
+  do {                                        \
+    const long long t1__ = clock64();         \
+    ts[i] += t1__ - tprev;                    \
+    tprev = t1__;                             \
+  } while (0)
+#else
+#define TW(i, bar, par) mbar_wait(bar, par)
+#define TS(i)
+#endif
+
+// SiLU'(x) with the two SFU approximations (~1 ulp each; see egnn_edge_tc.cu)
+__device__ __forceinline__ float fast_dsilu(float x) {
+  float e, sg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + e));
+  return sg * (1.f + x * (1.f - sg));
+}
+
 // byte offset of 16-byte chunk `chunk` of row `row` in a K-major tile with 128-byte rows and the 128B swizzle
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
 
@@ -118,20 +145,24 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
               const int32_t* __restrict__ order) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* ds_full = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [NSLOT] dS2 tiles + meta written
-  uint64_t* d1_full = ds_full + NSLOT;                               // [NSLOT] MMA 1 done
+  uint64_t* ds_full = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [DSLOT] dS2 tiles + meta written
+  uint64_t* slot_free = ds_full + DSLOT;                             // [DSLOT] MMA 2 done: tiles and meta reusable
+  uint64_t* d1_full = slot_free + DSLOT;                             // [NSLOT] MMA 1 done
   uint64_t* a2_full = d1_full + NSLOT;                               // [NSLOT] hid written to TMEM
-  uint64_t* slot_free = a2_full + NSLOT;                             // [NSLOT] MMA 2 done: tiles, D1 and A2 reusable
-  uint64_t* d2_full = slot_free + NSLOT;                             // [2] accumulation round complete
-  uint64_t* d2_empty = d2_full + 2;                                  // [2] drained into registers
-  uint64_t* q_full = d2_empty + 2;                                   // [QST] Q / P row segments landed
-  uint64_t* q_free = q_full + QST;                                   // [QST] ... and consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_free + QST);
-  static_assert((4 * NSLOT + 4 + 2 * QST) * 8 + 4 <= 512, "barrier block");
+  uint64_t* d2_full = a2_full + NSLOT;                               // [2] accumulation round complete
+  uint64_t* d2_empty = d2_full + 2;                                  // [2] drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 2);
+  static_assert((2 * DSLOT + 2 * NSLOT + 4) * 8 + 4 <= 512, "barrier block");
   float* red_wc = reinterpret_cast<float*>(smem + kOffRedWc);
   float* red_db = reinterpret_cast<float*>(smem + kOffRedDb);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef EQH_BWDTC_TRACE
+  long long tw[4] = {0, 0, 0, 0};
+  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = clock64();
+  long long tprev = t_start;
+#endif
   const int g = blockIdx.x % ngroups;          // column group
   const int sl = blockIdx.x / ngroups;         // edge slice (= row of `part`)
   const int64_t nblk = (N + 1) >> 1;           // blocks of two atoms
@@ -140,19 +171,17 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
   const int64_t ld = H;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < DSLOT; ++s) {
       mbar_init(&ds_full[s], 4);
+      mbar_init(&slot_free[s], 1);
+    }
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&d1_full[s], 1);
       mbar_init(&a2_full[s], 4);
-      mbar_init(&slot_free[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&d2_full[b], 1);
       mbar_init(&d2_empty[b], 128);
-    }
-    for (int s = 0; s < QST; ++s) {
-      mbar_init(&q_full[s], 1);
-      mbar_init(&q_free[s], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,42 +206,63 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     const int el = t >> 2, oq = t & 3;   // edge of the block, quad of outputs
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     float db[4] = {0.f, 0.f, 0.f, 0.f};
-    float acc[kM];                       // dW2[0..15, column t] of this slice
+    float* acc = reinterpret_cast<float*>(smem + kOffAcc) + t;      // dW2[o, column t] of this slice at acc[o * GC]
 #pragma unroll
-    for (int o = 0; o < kM; ++o) acc[o] = 0.f;
+    for (int o = 0; o < kM; ++o) acc[o * GC] = 0.f;
     auto drain = [&](uint32_t r) {
       const uint32_t buf = r & 1u;
-      mbar_wait(&d2_full[buf], (r >> 1) & 1u);
+      TW(1, &d2_full[buf], (r >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float v[32];
-      tmem_ld32(tmem_base + lane_off + kD2Col + buf * 32, v);
+      float v[kM];
+      tmem_ld16(tmem_base + lane_off + kD2Col + buf * 32 + kM, v);     // hid_hi . dS2_lo
+#pragma unroll
+      for (int o = 0; o < kM; ++o) acc[o * GC] += v[o];
+      tmem_ld16(tmem_base + lane_off + kD2Col + buf * 32, v);          // hid . dS2_hi
+#pragma unroll
+      for (int o = 0; o < kM; ++o) acc[o * GC] += v[o];
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&d2_empty[buf]);
-#pragma unroll
-      for (int o = 0; o < kM; ++o) acc[o] += v[o] + v[kM + o];
     };
     uint32_t drained = 0;
-    for (int bl = 0; bl < nb; ++bl) {
-      const int s = bl % NSLOT;
-      const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
+    // The loads of a block (order -> S2 / dMi / idx / d2: two dependent round trips) are issued PD blocks (values) and
+    // 2 PD blocks (atom ids) ahead of its turn and wait in registers: the producer never stalls on memory latency.
+    constexpr int PD = 4;
+    struct PV {
+      float4 s2, gm;
+      int32_t jj, atom;
+      float dd;
+    };
+    auto load_atom = [&](int bl) -> int32_t {           // atom of this thread's edge in block bl; -1: none
+      if (bl >= nb) return -1;
       const int64_t aslot = (b_begin + bl) * 2 + (el >> 4);
-      const bool ok = aslot < N;
-      const int64_t atom = ok ? (order ? (int64_t)__ldg(order + aslot) : aslot) : 0;
-      const int64_t e = atom * kNbr + (el & 15);
-      float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
-      int32_t jj = 0;
-      float dd = 0.f;
-      if (ok) {
-        const float4 s2 = __ldg(reinterpret_cast<const float4*>(S2 + e * kM) + oq);
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(dMi + atom * kM) + oq);
-        ds = make_float4(gm.x * dsilu_f(s2.x), gm.y * dsilu_f(s2.y), gm.z * dsilu_f(s2.z), gm.w * dsilu_f(s2.w));
+      if (aslot >= N) return -1;
+      return order ? __ldg(order + aslot) : (int32_t)aslot;
+    };
+    auto load_vals = [&](int32_t atom) -> PV {
+      PV v;
+      v.atom = atom;
+      v.s2 = v.gm = make_float4(0.f, 0.f, 0.f, 0.f);
+      v.jj = 0;
+      v.dd = 0.f;
+      if (atom >= 0) {
+        const int64_t e = (int64_t)atom * kNbr + (el & 15);
+        v.s2 = __ldg(reinterpret_cast<const float4*>(S2 + e * kM) + oq);
+        v.gm = __ldg(reinterpret_cast<const float4*>(dMi + (int64_t)atom * kM) + oq);
         if (oq == 0) {
-          jj = __ldg(idx + e);
-          dd = __ldg(d2 + e);
+          v.jj = __ldg(idx + e);
+          v.dd = __ldg(d2 + e);
         }
       }
+      return v;
+    };
+    auto produce = [&](const PV& v, int bl) {
+      const int s = bl % DSLOT;
+      const uint32_t ph = (uint32_t)(bl / DSLOT) & 1u;
+      float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v.atom >= 0)
+        ds = make_float4(v.gm.x * fast_dsilu(v.s2.x), v.gm.y * fast_dsilu(v.s2.y), v.gm.z * fast_dsilu(v.s2.z), v.gm.w * fast_dsilu(v.s2.w));
       const float4 dl = make_float4(tf32_lo(ds.x), tf32_lo(ds.y), tf32_lo(ds.z), tf32_lo(ds.w));
-      mbar_wait(&slot_free[s], ph ^ 1u);
+      TW(0, &slot_free[s], ph ^ 1u);
       uint8_t* b1 = smem + kOffB1 + s * kBBytes;
       uint8_t* b2 = smem + kOffB2 + s * kBBytes;
       *reinterpret_cast<float4*>(b1 + sw128(el, oq)) = ds;
@@ -228,9 +278,9 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       }
       Meta* m = reinterpret_cast<Meta*>(smem + kOffMeta + s * kMetaStride);
       if (oq == 0) {
-        m->j[el] = jj;
-        m->dd[el] = dd;
-        if ((el & 15) == 0) m->atom[el >> 4] = ok ? (int32_t)atom : -1;
+        m->j[el] = v.jj;
+        m->dd[el] = v.dd;
+        if ((el & 15) == 0) m->atom[el >> 4] = v.atom;
       }
       db[0] += ds.x; db[1] += ds.y; db[2] += ds.z; db[3] += ds.w;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -241,6 +291,26 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         drain((uint32_t)(bl / kFlush) - 1u);
         drained = (uint32_t)(bl / kFlush);
       }
+    };
+    PV pv[PD];
+    int32_t an[PD];
+#pragma unroll
+    for (int u = 0; u < PD; ++u) an[u] = load_atom(u);
+#pragma unroll
+    for (int u = 0; u < PD; ++u) {
+      pv[u] = load_vals(an[u]);
+      an[u] = load_atom(u + PD);
+    }
+    for (int base = 0; base < nb; base += PD) {
+#pragma unroll
+      for (int u = 0; u < PD; ++u) {
+        const int bl = base + u;
+        if (bl < nb) {
+          produce(pv[u], bl);
+          pv[u] = load_vals(an[u]);
+          an[u] = load_atom(bl + 2 * PD);
+        }
+      }
     }
     const uint32_t nrounds = (uint32_t)((nb + kFlush - 1) / kFlush);
     for (uint32_t r = drained; r < nrounds; ++r) drain(r);
@@ -248,7 +318,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     if (g * GC + t < H) {
       float* row = part + (int64_t)sl * part_cols + g * GC + t;
 #pragma unroll
-      for (int o = 0; o < kM; ++o) row[(int64_t)o * H] = acc[o];
+      for (int o = 0; o < kM; ++o) row[(int64_t)o * H] = acc[o * GC];
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
@@ -257,11 +327,10 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     const uint32_t w2t = smem_u32(smem);
     for (int step = 0; step < nb + LAG; ++step) {
       if (step < nb) {
-        const int s = step % NSLOT;
-        const uint32_t ph = (uint32_t)(step / NSLOT) & 1u;
-        mbar_wait(&ds_full[s], ph);
+        const int sd = step % DSLOT, s = step % NSLOT;
+        TW(0, &ds_full[sd], (uint32_t)(step / DSLOT) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b1 = smem_u32(smem + kOffB1 + s * kBBytes);
+        const uint32_t b1 = smem_u32(smem + kOffB1 + sd * kBBytes);
         const uint32_t d1 = tmem_base + kD1Col + s * 32;
         if (elect_one()) {
           // D1[c, e] = sum_o W2T[c, o] dS2[e, o]: lo.hi, hi.lo (small terms first), then hi.hi; two k-steps of 8 each
@@ -277,14 +346,14 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       }
       if (step >= LAG) {
         const int bl = step - LAG;
-        const int s = bl % NSLOT;
+        const int s = bl % NSLOT, sd = bl % DSLOT;
         const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
         const uint32_t r = (uint32_t)(bl / kFlush), buf = r & 1u;
         const bool first = (bl % kFlush) == 0;
-        if (first) mbar_wait(&d2_empty[buf], ((r >> 1) & 1u) ^ 1u);     // drained two rounds ago
-        mbar_wait(&a2_full[s], ph);
+        if (first) TW(2, &d2_empty[buf], ((r >> 1) & 1u) ^ 1u);     // drained two rounds ago
+        TW(1, &a2_full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b2 = smem_u32(smem + kOffB2 + s * kBBytes);
+        const uint32_t b2 = smem_u32(smem + kOffB2 + sd * kBBytes);
         const uint32_t aH = tmem_base + kA2Col + s * 64, aL = aH + 32;
         const uint32_t dacc = tmem_base + kD2Col + buf * 32;
         const bool last = (bl % kFlush) == kFlush - 1 || bl == nb - 1;
@@ -296,34 +365,11 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
             umma_tf32_ts(dacc, aH + ks * 8, db2, idesc32, (first && ks == 0) ? 0u : 1u);
             umma_tf32_ts(dacc, aL + ks * 8, db2, idesc16, 1u);
           }
-          umma_commit(&slot_free[s]);
+          umma_commit(&slot_free[sd]);
           if (last) umma_commit(&d2_full[buf]);
         }
         __syncwarp();
       }
-    }
-  } else if (warp == kLoadWarp) {
-    // ============================ Q / P row loader ============================
-    // lane l bulk-copies the 512-byte segment (this CTA's 128 columns) of Q[j] of edge l of the block; lanes 0 and 1
-    // also the two atoms' segments of P.  QST blocks ahead of the math: the gather latency never reaches a register.
-    const uint32_t row_bytes = (uint32_t)min(GC, H - g * GC) * 4u;
-    for (int bl = 0; bl < nb; ++bl) {
-      const int st = bl % QST;
-      const uint32_t ph = (uint32_t)(bl / QST) & 1u;
-      const int64_t aslot = (b_begin + bl) * 2 + (lane >> 4);
-      const int64_t atom = aslot < N ? (order ? (int64_t)__ldg(order + aslot) : aslot) : 0;   // (rows of atom 0 for a missing atom: finite, unused)
-      const int64_t jrow = __ldg(idx + atom * kNbr + (lane & 15));
-      int64_t prow = 0;
-      if (lane < 2) {
-        const int64_t ps = (b_begin + bl) * 2 + lane;
-        prow = ps < N ? (order ? (int64_t)__ldg(order + ps) : ps) : 0;
-      }
-      mbar_wait(&q_free[st], ph ^ 1u);
-      if (lane == 0) mbar_expect_tx(&q_full[st], kQRows * row_bytes);
-      __syncwarp();
-      uint8_t* dst = smem + kOffQ + st * kQStageBytes;
-      bulk_g2s(dst + lane * (GC * 4), Q + jrow * ld + g * GC, row_bytes, &q_full[st]);
-      if (lane < 2) bulk_g2s(dst + (EB + lane) * (GC * 4), P + prow * ld + g * GC, row_bytes, &q_full[st]);
     }
   } else {
     // ============================ column warpgroups ============================
@@ -335,19 +381,52 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     const float wcr = cv ? __ldg(wc + col) : 0.f;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float dwc = 0.f;
-    for (int bl = wg; bl < nb; bl += kEpiWG) {
-      const int s = bl % NSLOT;
+    // Q[j] / P[i] row segments (512 B each) of the warpgroup's NEXT block are copied into shared memory with 16-byte
+    // cp.async (one row per warp instruction, fully coalesced) while the current block is processed.
+    const uint32_t row_bytes = (uint32_t)min(GC, H - g * GC) * 4u;
+    uint8_t* qring = smem + kOffQ + wg * 2 * kQStageBytes;
+    auto fetch_rows = [&](int blk, int stage) {
+      const int sd = blk % DSLOT;
+      TW(0, &ds_full[sd], (uint32_t)(blk / DSLOT) & 1u);
+      const Meta* mm = reinterpret_cast<const Meta*>(smem + kOffMeta + sd * kMetaStride);
+      if ((uint32_t)lane * 16u < row_bytes) {
+        // warp q copies rows q, q+4, ..., q+28 of Q and (q < 2) the P row of atom q: all row ids first, then the copies
+        const float* src[9];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) src[i] = Q + (int64_t)mm->j[q + 4 * i] * ld;
+        {
+          const int32_t a = mm->atom[q & 1];
+          src[8] = P + (int64_t)(a >= 0 ? a : 0) * ld;
+        }
+        const uint32_t d = smem_u32(qring + stage * kQStageBytes + lane * 16 + q * (GC * 4));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4 * (GC * 4)), "l"(src[i] + g * GC + lane * 4) : "memory");
+        if (q < 2)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 8 * 4 * (GC * 4)), "l"(src[8] + g * GC + lane * 4) : "memory");
+      }
+    };
+    if (wg < nb) fetch_rows(wg, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int it = 0;
+    for (int bl = wg; bl < nb; bl += kEpiWG, ++it) {
+      const int s = bl % NSLOT, sd = bl % DSLOT;
       const uint32_t ph = (uint32_t)(bl / NSLOT) & 1u;
-      mbar_wait(&ds_full[s], ph);
-      const Meta* m = reinterpret_cast<const Meta*>(smem + kOffMeta + s * kMetaStride);
+      TS(0);
+      if (bl + kEpiWG < nb) fetch_rows(bl + kEpiWG, (it + 1) & 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      TS(1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");            // this block's rows have landed (the next may be in flight)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");     // ... for all four warps of the warpgroup
+      TS(2);
+      const Meta* m = reinterpret_cast<const Meta*>(smem + kOffMeta + sd * kMetaStride);
       const int32_t a0 = m->atom[0], a1 = m->atom[1];
-      const int st = bl % QST;
-      mbar_wait(&q_full[st], (uint32_t)(bl / QST) & 1u);
-      const float* qs = reinterpret_cast<const float*>(smem + kOffQ + st * kQStageBytes) + c;
-      mbar_wait(&d1_full[s], ph);
+      const float* qs = reinterpret_cast<const float*>(qring + (it & 1) * kQStageBytes) + c;
+      TW(2, &d1_full[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d1 = tmem_base + lane_off + kD1Col + s * 32;
       const uint32_t a2 = tmem_base + lane_off + kA2Col + s * 64;
+      TS(3);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int32_t at = half ? a1 : a0;
@@ -356,7 +435,6 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         float dh[kNbr], hv[kNbr];
         tmem_ld16(d1 + half * 16, dh);
         float dpa = 0.f;
-        float* dprow = dPre + ((int64_t)(at >= 0 ? at : 0) * kNbr) * ld + col;
 #pragma unroll
         for (int k = 0; k < kNbr; ++k) {
           const float dd = m->dd[half * 16 + k];
@@ -364,30 +442,43 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
           float ex, sg;                                   // SFU approximations (~1 ulp each), see egnn_edge_tc.cu
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre * -1.4426950408889634f));
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + ex));
-          const float hid = pre * sg;
-          const float dsl = sg * (1.f + pre * (1.f - sg));
-          const float dpre = dh[k] * dsl;
+          hv[k] = pre * sg;
+          const float dpre = dh[k] * (sg * (1.f + pre * (1.f - sg)));
           dpa += dpre;
           dwc += dd * dpre;
-          if (wr) dprow[(int64_t)k * ld] = dpre;
-          hv[k] = hid;
+          dh[k] = dpre;
         }
-        if (wr) dP[(int64_t)at * ld + col] = dpa;
+        if (wr) {                                         // one branch per atom: the element loop above is straight-line code
+          float* dprow = dPre + ((int64_t)at * kNbr) * ld + col;
+#pragma unroll
+          for (int k = 0; k < kNbr; ++k, dprow += ld) *dprow = dh[k];
+          dP[(int64_t)at * ld + col] = dpa;
+        }
         tmem_st16(a2 + half * 16, hv);                    // hi: the tensor core ignores the low 13 bits
 #pragma unroll
         for (int k = 0; k < kNbr; ++k) hv[k] = tf32_lo(hv[k]);
         tmem_st16(a2 + 32 + half * 16, hv);               // lo
       }
+      TS(4);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&a2_full[s]);
-        mbar_arrive(&q_free[st]);
-      }
+      if (lane == 0) mbar_arrive(&a2_full[s]);
+      TS(5);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");     // all reads of this stage done before it is refilled
+      TS(6);
     }
     red_wc[wg * GC + c] = dwc;
   }
+#ifdef EQH_BWDTC_TRACE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == kMmaWarp)) {
+    const int r = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : 3;
+    g_bt_trace[r * 8 + 0] = (unsigned long long)(clock64() - t_start);
+    for (int i = 0; i < 4; ++i) g_bt_trace[r * 8 + 1 + i] = (unsigned long long)tw[i];
+    g_bt_trace[r * 8 + 5] = (unsigned long long)nb;
+    if (r == 1) for (int i = 0; i < 8; ++i) g_bt_trace[40 + i] = (unsigned long long)ts[i];
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
@@ -442,3 +533,9 @@ int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const 
 }
 
 }  // extern "C"
+
+#ifdef EQH_BWDTC_TRACE
+extern "C" EQH_API int eqh_debug_edge_bwd_tc_trace(unsigned long long* host64) {
+  return (int)cudaMemcpyFromSymbol(host64, eqh::edge_bwd_tc::g_bt_trace, sizeof(unsigned long long) * 64);
+}
+#endif
