@@ -286,8 +286,9 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[s]);
-      // the round before the current one finished kFlush/2 blocks ago: by now its MMAs have completed
-      if ((bl % kFlush) == kFlush / 2 && bl >= kFlush) {
+      // the round before the current one ended kFlush - 1 blocks ago (MMA 2 lags production by the LAG blocks in
+      // flight): its MMAs have completed, and the issuer needs the buffer again only at the next block
+      if ((bl % kFlush) == kFlush - 1 && bl >= kFlush) {
         drain((uint32_t)(bl / kFlush) - 1u);
         drained = (uint32_t)(bl / kFlush);
       }
@@ -442,8 +443,9 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
           float ex, sg;                                   // SFU approximations (~1 ulp each), see egnn_edge_tc.cu
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre * -1.4426950408889634f));
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + ex));
-          hv[k] = pre * sg;
-          const float dpre = dh[k] * (sg * (1.f + pre * (1.f - sg)));
+          const float hid = pre * sg;
+          hv[k] = hid;
+          const float dpre = dh[k] * (sg + hid * (1.f - sg));      // SiLU'(x) = s + x s (1 - s)
           dpa += dpre;
           dwc += dd * dpre;
           dh[k] = dpre;
