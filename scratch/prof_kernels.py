@@ -24,6 +24,8 @@ for _ in range(2):
               g.d2.data_ptr(), N, Hp, S2.data_ptr(), None, Mi.data_ptr(), ops._stream())
     ops._call("eqh_egnn_edge_bwd", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(), g.idx.data_ptr(),
               g.d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), None, N, Hp, dP.data_ptr(), dPre.data_ptr(), None, part.data_ptr(), ops._stream())
+    ops._call("eqh_egnn_edge_bwd_tc", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), g.idx.data_ptr(),
+              g.d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), N, Hp, dP.data_ptr(), dPre.data_ptr(), part.data_ptr(), ops._p(g.order), ops._stream())
     ops.knn16(pos, method="grid")
 torch.cuda.synchronize()
 print("ok", N)
