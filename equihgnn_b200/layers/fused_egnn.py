@@ -17,6 +17,14 @@ from ..ops import KNN_K, M_DIM, SUM, _call, _p, _stream, gather_reduce_raw, gemm
 from .fused_conv import _GradSink, _rowln_bwd
 
 
+def pack_phi_e(bufs, w1, b1, w2, C: int) -> None:
+    """Refresh the packed, zero-padded copies of phi_e's weights (TMA needs 16-byte row strides; 2C+1 floats is not)."""
+    H0, Hp = w1.shape[0], bufs["W1a"].shape[0]
+    _call("eqh_egnn_pack", 1, _p(ops._f32(w1, "edge_mlp.0.weight")), _p(ops._f32(b1, "edge_mlp.0.bias")),
+          _p(ops._f32(w2, "edge_mlp.3.weight")), H0, C, Hp, _p(bufs["W1a"]), _p(bufs["W1b"]), _p(bufs["wc"]), _p(bufs["b1"]),
+          _p(bufs["W2"]), _stream())
+
+
 class EGNNFused(torch.autograd.Function):
     """(h [N,C]) -> node_mlp(cat(LN(h), sum_j phi_e(h_i, h_j, d2_ij))) + h"""
 
@@ -26,10 +34,8 @@ class EGNNFused(torch.autograd.Function):
         N, C = h.shape
         H0 = w1.shape[0]
         Hp = bufs["W1a"].shape[0]
-        # refresh the packed copies of phi_e's weights (TMA needs 16-byte row strides; 2C+1 floats is not)
+        # the packed copies of phi_e's weights were refreshed by the caller (pack_phi_e, possibly on a parallel branch)
         W1a, W1b, wc, b1p, W2p = bufs["W1a"], bufs["W1b"], bufs["wc"], bufs["b1"], bufs["W2"]
-        _call("eqh_egnn_pack", 1, _p(ops._f32(w1, "edge_mlp.0.weight")), _p(ops._f32(b1, "edge_mlp.0.bias")),
-              _p(ops._f32(w2, "edge_mlp.3.weight")), H0, C, Hp, _p(W1a), _p(W1b), _p(wc), _p(b1p), _p(W2p), _stream())
         P = gemm_raw(h, True, W1a, True, N, Hp, C, bias=b1p)
         Q = gemm_raw(h, True, W1b, True, N, Hp, C)
         dev = h.device

@@ -106,10 +106,12 @@ class EGNNEquiHNNS(nn.Module):
     def forward(self, data):
         V, E = data.edge_index0, data.edge_index1
         N = data.x.shape[0]
-        inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+        with ops.prep_work.fork(data.x.device):          # captured graph: the incidence CSR is built next to the encoder / kNN search
+            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
         x = self.atom_encoder(data.x)
         x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)   # coors_out is discarded (:158)
         x = x.squeeze(0)
+        ops.prep_work.join(data.x.device)
         x0 = x
         for _ in range(self.nlayer):
             x = self.dropout(x)

@@ -327,6 +327,9 @@ class _SideWork:
 
 
 side_work = _SideWork()
+# forward-time index / packing work that nothing on the critical path needs yet (incidence CSR next to the atom encoder
+# and the kNN search, the transposed kNN incidence next to the phi_e GEMMs): a second parallel branch of the captured graph
+prep_work = _SideWork()
 
 
 class ColsumBatch:
