@@ -61,7 +61,18 @@ __global__ void __launch_bounds__(32) k_atom_bwd(const int64_t* __restrict__ x, 
   const int64_t lo = (int64_t)blockIdx.x * slice, hi = min(N, lo + slice);
   const float* g = dh + cb * 32 + lane;
   int64_t n = lo;
-  for (; n + 4 <= hi; n += 4) {     // 4 rows in flight
+  for (; n + 16 <= hi; n += 16) {   // 16 rows in flight: the kernel sits on the tail of the backward, latency is what counts
+    int64_t v[16];
+    float d[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(x + (n + u) * F + f);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) d[u] = __ldg(g + (n + u) * C);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (v[u] >= 0 && v[u] < rows) acc[(int)v[u] * 32 + lane] += d[u];   // ascending n: fixed order
+  }
+  for (; n + 4 <= hi; n += 4) {
     int64_t v[4];
     float d[4];
 #pragma unroll
@@ -70,7 +81,7 @@ __global__ void __launch_bounds__(32) k_atom_bwd(const int64_t* __restrict__ x, 
     for (int u = 0; u < 4; ++u) d[u] = __ldg(g + (n + u) * C);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (v[u] >= 0 && v[u] < rows) acc[(int)v[u] * 32 + lane] += d[u];   // ascending n: fixed order
+      if (v[u] >= 0 && v[u] < rows) acc[(int)v[u] * 32 + lane] += d[u];
   }
   for (; n < hi; ++n) {
     const int64_t v = __ldg(x + n * F + f);

@@ -139,20 +139,20 @@ class EGNN(nn.Module):
             from .fused_egnn import EGNNFused, pack_phi_e
             lin0, lin3, n0, n3 = self.edge_mlp[0], self.edge_mlp[3], self.node_mlp[0], self.node_mlp[3]
             bufs = self._packed_buffers(h.device, C)
-            # While a CUDA graph is being captured the weight packing runs next to the kNN search and the transposed
-            # kNN incidence (only the backward reads it) next to the phi_e GEMMs, as parallel branches (ops.prep_work).
-            with ops.prep_work.fork(h.device):
-                pack_phi_e(bufs, lin0.weight, lin0.bias, lin3.weight, C)
-            graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=False)
-            ops.prep_work.join(h.device)
-            if graph.rowptr_j is None:
-                with ops.prep_work.fork(h.device):
+            # While a CUDA graph is being captured the kNN search and the transposed kNN incidence (they need only the
+            # coordinates) run as a parallel branch (ops.prep_work_b) next to the weight packing and the phi_e GEMMs;
+            # EGNNFused joins the branch right before the edge kernel.
+            with ops.prep_work_b.fork(h.device):
+                graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=True)
+                if graph.rowptr_j is None:
                     graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
+            pack_phi_e(bufs, lin0.weight, lin0.bias, lin3.weight, C)
             out = EGNNFused.apply(h, graph, bufs, self.node_norm.eps, lin0.weight, lin0.bias,
                                   lin3.weight, lin3.bias, self.node_norm.weight, self.node_norm.bias, n0.weight, n0.bias,
                                   n3.weight, n3.bias)
-            ops.prep_work.join(h.device)
+            ops.prep_work_b.join(h.device)
             return out.unsqueeze(0), coors
+        ops.prep_work_b.join(h.device)                      # a prebuilt graph may still be in flight on its branch
         graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=torch.is_grad_enabled())
         idx_long = None
         if x.requires_grad:

@@ -41,6 +41,7 @@ class EGNNFused(torch.autograd.Function):
         dev = h.device
         S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
         Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
+        ops.prep_work_b.join(dev)                        # the kNN graph may have been built on a parallel branch
         _call("eqh_egnn_edge_fwd_tc_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), N, Hp,
               _p(S2), None, _p(Mi), _p(graph.order), _stream(), nbytes=2.0 * N * KNN_K * Hp * M_DIM)
         hn = torch.empty_like(h)

@@ -10,6 +10,8 @@ mhnn.py:196-199 is not executed.
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -108,17 +110,25 @@ class EGNNEquiHNNS(nn.Module):
         N = data.x.shape[0]
         with ops.prep_work.fork(data.x.device):          # captured graph: the incidence CSR is built next to the encoder / kNN search
             inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc.nonempty("e"), inc.nonempty("v")             # count / mask vectors of the mean aggregation
+            pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None))
+        # ... and, on small batches, the kNN graph (coordinates only) next to both; the cell-grid search of large batches
+        # fills the GPU by itself (measured: no gain at Molecule3D-1024)
+        with (ops.prep_work_b.fork(data.x.device) if N < 8192 else contextlib.nullcontext()):
+            graph = ops.build_knn_graph(data.pos, need_transpose=torch.is_grad_enabled())
         x = self.atom_encoder(data.x)
-        x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)   # coors_out is discarded (:158)
+        x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False,   # coors_out is discarded (:158)
+                               knn_graph=graph)
         x = x.squeeze(0)
         ops.prep_work.join(data.x.device)
+        ops.prep_work_b.join(data.x.device)
         x0 = x
         for _ in range(self.nlayer):
             x = self.dropout(x)
             x = self.conv(x, V, E, x0, incidence=inc)
             x = self.act(x)
         x = self.dropout(x)
-        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None))
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)
         return self.mlp_out(x).view(-1)
 
 

@@ -330,6 +330,7 @@ side_work = _SideWork()
 # forward-time index / packing work that nothing on the critical path needs yet (incidence CSR next to the atom encoder
 # and the kNN search, the transposed kNN incidence next to the phi_e GEMMs): a second parallel branch of the captured graph
 prep_work = _SideWork()
+prep_work_b = _SideWork()     # second branch: the kNN search (needs only the coordinates) next to the atom encoder and the phi_e GEMMs
 
 
 class ColsumBatch:
@@ -968,18 +969,24 @@ class _PoolCache:
 _pool_cache = _PoolCache()
 
 
-def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = None,
-                    ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Drop-in for torch_geometric.nn.global_add_pool (mhnn.py:216, equihnn_egnn.py:167).  With the batch's `ptr`
-    (PyG Batch.ptr, int64 [num_graphs+1]) the sorted `batch` vector needs no grouping pass: ptr IS the CSR."""
+def pool_index(batch: torch.Tensor, size: Optional[int] = None, ptr: Optional[torch.Tensor] = None):
+    """(n, rowptr, perm | None, dst32) of the per-molecule pooling: with the batch's `ptr` (PyG Batch.ptr, int64
+    [num_graphs+1]) the sorted `batch` vector needs no grouping pass -- ptr IS the CSR."""
     if ptr is not None and size is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == size + 1 \
             and batch.dtype == torch.int64:
-        rowptr = torch.empty(size + 1, dtype=torch.int32, device=x.device)
-        dst32 = torch.empty(batch.numel(), dtype=torch.int32, device=x.device)
+        rowptr = torch.empty(size + 1, dtype=torch.int32, device=batch.device)
+        dst32 = torch.empty(batch.numel(), dtype=torch.int32, device=batch.device)
         _call("eqh_pool_index", 1, _p(ptr.contiguous()), size, _p(batch.contiguous()), batch.numel(), _p(rowptr), _p(dst32),
               _stream())
-        return segment_reduce(x, rowptr, None, dst32, size, "sum")
-    n, rowptr, perm, dst32 = _pool_cache.get(batch, size)
+        return size, rowptr, None, dst32
+    return _pool_cache.get(batch, size)
+
+
+def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = None,
+                    ptr: Optional[torch.Tensor] = None, index=None) -> torch.Tensor:
+    """Drop-in for torch_geometric.nn.global_add_pool (mhnn.py:216, equihnn_egnn.py:167).  `index`: a precomputed
+    pool_index(batch, size, ptr) (the models build it on the forward's parallel branch)."""
+    n, rowptr, perm, dst32 = index if index is not None else pool_index(batch, size, ptr)
     return segment_reduce(x, rowptr, perm, dst32, n, "sum")
 
 
