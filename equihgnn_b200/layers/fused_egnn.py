@@ -76,25 +76,21 @@ class EGNNFused(torch.autograd.Function):
         dMi = dni[:, C:].contiguous()
         dh_ln, part_ln = _rowln_bwd(h, g, eps, dhn, relu=0)
         sink.affine(g, t, part_ln)
+        sink.flush()                                # bias / LayerNorm-affine column sums: every input exists already
         # ---- phi_e
         if graph.rowptr_j is None:
             graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
         cols = (M_DIM + 1) * Hp + M_DIM
         dP, dPre, _, part = ops.egnn_edge_bwd_raw(P, Q, wc, W2p, b2, graph, graph.d2, S2, dMi, None, False)
-        dQ = gather_reduce_raw(dPre, graph.perm_j, graph.rowptr_j, None, N, SUM)
-        # dh = dOut (residual) + dP.W1a + dQ.W1b + LayerNorm backward
-        dh = gemm_raw(dP, True, W1a, False, N, C, Hp, residual=dOut)
-        gemm_raw(dQ, True, W1b, False, N, C, Hp, out=dh, residual=dh)
-        dh = dh + dh_ln
-        # ---- phi_e parameter gradients (side stream)
+        # phi_e parameter gradients on the side stream (a parallel branch of the captured graph), forked as soon as their
+        # inputs exist -- this layer's backward is the tail of the step, nothing later can hide them: what needs only dP /
+        # the partial sums starts next to the dQ reduction, the dQ part next to the dh GEMMs.
         gw1 = sink.out[id(w1)]
-        with ops.side_work.fork(dev, keep=(dP, dQ, h, part)):
-            # into a 16-byte-aligned staging matrix (vector stores, vector split-K finish), then one add into the
-            # [H0, 2C+1] gradient whose odd row stride would force the scalar epilogue
-            tmp = torch.empty((H0, 2 * C), dtype=torch.float32, device=dev)
+        # into a 16-byte-aligned staging matrix (vector stores, vector split-K finish), then one add into the
+        # [H0, 2C+1] gradient whose odd row stride would force the scalar epilogue
+        tmp = torch.empty((H0, 2 * C), dtype=torch.float32, device=dev)
+        with ops.side_work.fork(dev, keep=(dP, h, part, tmp)):
             gemm_raw(dP, False, h, False, H0, C, N, splits=0, out=tmp[:, :C])
-            gemm_raw(dQ, False, h, False, H0, C, N, splits=0, out=tmp[:, C:])
-            gw1[:, :2 * C].add_(tmp)
             red = torch.empty(cols, dtype=torch.float32, device=dev)
             batch = ops.ColsumBatch(dev)
             batch.add(part, red)
@@ -103,5 +99,12 @@ class EGNNFused(torch.autograd.Function):
             sink.out[id(w2)].add_(red[:M_DIM * Hp].view(M_DIM, Hp)[:, :H0])
             gw1[:, 2 * C].add_(red[M_DIM * Hp:M_DIM * Hp + H0])
             sink.out[id(b2)].add_(red[(M_DIM + 1) * Hp:])
-        sink.flush()
+        dQ = gather_reduce_raw(dPre, graph.perm_j, graph.rowptr_j, None, N, SUM)
+        with ops.side_work.fork(dev, keep=(dQ, h, tmp)):
+            gemm_raw(dQ, False, h, False, H0, C, N, splits=0, out=tmp[:, C:])
+            gw1[:, :2 * C].add_(tmp)
+        # dh = dOut (residual) + dP.W1a + dQ.W1b + LayerNorm backward
+        dh = gemm_raw(dP, True, W1a, False, N, C, Hp, residual=dOut)
+        gemm_raw(dQ, True, W1b, False, N, C, Hp, out=dh, residual=dh)
+        dh = dh + dh_ln
         return (dh, None, None, None) + (None,) * 10

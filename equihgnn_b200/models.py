@@ -111,7 +111,8 @@ class EGNNEquiHNNS(nn.Module):
         with ops.prep_work.fork(data.x.device):          # captured graph: the incidence CSR is built next to the encoder / kNN search
             inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
             inc.nonempty("e"), inc.nonempty("v")             # count / mask vectors of the mean aggregation
-            pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None))
+            pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None),
+                                  real=int(getattr(data, "num_real_graphs", 0) or 0) or None)
         # ... and, on small batches, the kNN graph (coordinates only) next to both; the cell-grid search of large batches
         # fills the GPU by itself (measured: no gain at Molecule3D-1024)
         with (ops.prep_work_b.fork(data.x.device) if N < 8192 else contextlib.nullcontext()):
@@ -177,7 +178,8 @@ class MHNNM(nn.Module):
                 x, e = self.dropout(x), self.dropout(e)
             else:
                 x, e = self.dropout(self.act(x)), self.dropout(self.act(e))
-        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None))
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None),
+                                index=ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None), real=real or None))
         return self.mlp_out(x).view(-1)
 
 

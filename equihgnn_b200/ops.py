@@ -969,15 +969,22 @@ class _PoolCache:
 _pool_cache = _PoolCache()
 
 
-def pool_index(batch: torch.Tensor, size: Optional[int] = None, ptr: Optional[torch.Tensor] = None):
+def pool_index(batch: torch.Tensor, size: Optional[int] = None, ptr: Optional[torch.Tensor] = None,
+               real: Optional[int] = None):
     """(n, rowptr, perm | None, dst32) of the per-molecule pooling: with the batch's `ptr` (PyG Batch.ptr, int64
-    [num_graphs+1]) the sorted `batch` vector needs no grouping pass -- ptr IS the CSR."""
+    [num_graphs+1]) the sorted `batch` vector needs no grouping pass -- ptr IS the CSR.
+
+    real: number of real molecules of a ghost-padded batch (graphed.pad_batch).  The ghost molecule holds ALL padding
+    atoms -- one segment of hundreds of rows, reduced by a single warp, sat on the critical path of the captured step
+    (30 us at QM9-128) -- and its pooled row is excluded from the loss, so its segment is emptied: the row is 0."""
     if ptr is not None and size is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == size + 1 \
             and batch.dtype == torch.int64:
         rowptr = torch.empty(size + 1, dtype=torch.int32, device=batch.device)
         dst32 = torch.empty(batch.numel(), dtype=torch.int32, device=batch.device)
         _call("eqh_pool_index", 1, _p(ptr.contiguous()), size, _p(batch.contiguous()), batch.numel(), _p(rowptr), _p(dst32),
               _stream())
+        if real is not None and 0 <= real < size:
+            rowptr[real + 1:] = rowptr[real:real + 1]
         return size, rowptr, None, dst32
     return _pool_cache.get(batch, size)
 
