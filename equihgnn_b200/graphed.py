@@ -24,6 +24,8 @@ from __future__ import annotations
 from typing import Dict, Optional, Tuple
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -127,7 +129,11 @@ class GraphedTrainer(Trainer):
                 b.copy_(saved)
         g = torch.cuda.CUDAGraph()
         before = ops.STATS["launches"]
-        with torch.cuda.graph(g):        # private pool per bucket: buckets may replay in any order
+        # private pool per bucket: buckets may replay in any order.  The capture stream has high priority: the kernel nodes
+        # of the dX chain inherit it, the weight-gradient branch (ops.side_work, default priority) yields SMs to them.
+        prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "-1"))
+        cap = torch.cuda.Stream(priority=prio) if prio != 0 else None
+        with (torch.cuda.graph(g, stream=cap) if cap is not None else torch.cuda.graph(g)):
             loss = self._fwd_bwd(static)
         return _Bucket(static, g, loss, ops.STATS["launches"] - before)
 
