@@ -106,6 +106,33 @@ struct Row {
       }
     }
   }
+  // same layout from shared (or any non-read-only) memory
+  __device__ __forceinline__ void load_plain(const float* row, int lane) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float* p = row + (q * 32 + lane) * W;
+      if constexpr (W == 4) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+      } else if constexpr (W == 2) {
+        float2 t = *reinterpret_cast<const float2*>(p);
+        v[q * 2 + 0] = t.x; v[q * 2 + 1] = t.y;
+      } else {
+        v[q] = *p;
+      }
+    }
+  }
+  // asynchronous copy of a row into shared memory, each lane the chunks it will read back with load_plain
+  __device__ __forceinline__ static void copy_async(float* dst, const float* __restrict__ row, int lane) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (q * 32 + lane) * W);
+      const float* p = row + (q * 32 + lane) * W;
+      if constexpr (W == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p) : "memory");
+      else if constexpr (W == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(p) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(p) : "memory");
+    }
+  }
   __device__ __forceinline__ void store(float* __restrict__ row, int lane) const {
 #pragma unroll
     for (int q = 0; q < Q; ++q) {

@@ -215,6 +215,122 @@ __global__ void __launch_bounds__(256, DGB ? 2 : 4) k_fused_bwd(
   }
 }
 
+// Backward of the primary grouping WITH the LayerNorm affine partials (the variant every training step runs).  Segments
+// are short (2-3 incidences), so the one-segment-per-warp-turn kernel above is bound by the chain of dependent loads at
+// every segment start (rowptr -> index -> gathered row, plus the segment's own rows): 0.54 of the HBM peak.  Here a
+// warp owns a CONTIGUOUS range of segments: its incidences are contiguous too, so the one-ahead prefetch of the gathered
+// rows runs across segment boundaries, rowptr is read one segment ahead, and the next segment's own rows (A|B and dU)
+// arrive by cp.async in a per-warp shared-memory buffer while the current segment is processed.
+template <int V, bool GA, bool GB, bool GU>
+__global__ void __launch_bounds__(256, 2) k_fused_bwd_dgb(
+    const float* __restrict__ A, const float* __restrict__ B, const int32_t* __restrict__ ia,
+    const int32_t* __restrict__ ib, const int32_t* __restrict__ iu, const int32_t* __restrict__ rowptr, int64_t n_seg,
+    const float* __restrict__ gamma, float eps, const float* __restrict__ dU, const int32_t* __restrict__ u_rowptr,
+    float* __restrict__ dOp, float* __restrict__ dgb_partial) {
+  static_assert(GA != GB, "exactly one of A / B is gathered in the backward groupings");
+  pdl_prologue();
+  constexpr int C = 32 * V;
+  extern __shared__ __align__(16) float sbuf[];      // [8 warps][2][C] staging; reused as [8][2C] for the final reduce
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t base = n_seg / nwarps, rem = n_seg - base * nwarps;          // balanced contiguous ranges
+  const int64_t s0 = warp * base + min(warp, rem), s1 = s0 + base + (warp < rem ? 1 : 0);
+  float* wbuf = sbuf + wib * 2 * C;
+  Row<V> g, dg, db;
+  g.load(gamma, lane);
+  dg.zero();
+  db.zero();
+  const float* ownsrc = GA ? B : A;
+  auto own_async = [&](int64_t s) {
+    Row<V>::copy_async(wbuf, ownsrc + s * C, lane);
+    if constexpr (!GU) Row<V>::copy_async(wbuf + C, dU + s * C, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  Row<V> nG, nU;                    // gathered rows of the NEXT incidence
+  float nW = 1.f;
+  auto fetch = [&](int32_t k) {
+    if constexpr (GA) nG.load(A + (int64_t)__ldg(ia + k) * C, lane);
+    else nG.load(B + (int64_t)__ldg(ib + k) * C, lane);
+    if constexpr (GU) {
+      const int32_t r = __ldg(iu + k);
+      nU.load(dU + (int64_t)r * C, lane);
+      nW = inv_count(u_rowptr, r);
+    }
+  };
+  if (s0 < s1) {
+    own_async(s0);
+    int32_t lo = __ldg(rowptr + s0), hi = __ldg(rowptr + s0 + 1);
+    const int32_t kend = __ldg(rowptr + s1);
+    if (lo < kend) fetch(lo);
+    for (int64_t s = s0; s < s1; ++s) {
+      Row<V> own, uc, acc;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");     // each lane reads back only the chunks it copied itself
+      own.load_plain(wbuf, lane);
+      if constexpr (!GU) {
+        uc.load_plain(wbuf + C, lane);
+        const float w = u_rowptr ? 1.f / (float)max(hi - lo, 1) : 1.f;  // dU's grouping is this grouping
+#pragma unroll
+        for (int i = 0; i < V; ++i) uc.v[i] *= w;
+      }
+      if (s + 1 < s1) own_async(s + 1);
+      const int32_t hi_next = s + 2 <= s1 ? __ldg(rowptr + s + 2) : hi;
+      acc.zero();
+      for (int32_t k = lo; k < hi; ++k) {
+        Row<V> pre, gk;
+#pragma unroll
+        for (int i = 0; i < V; ++i) pre.v[i] = own.v[i] + nG.v[i];
+        if constexpr (GU) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) gk.v[i] = nU.v[i] * nW;
+        }
+        if (k + 1 < kend) fetch(k + 1);        // runs across the segment boundary
+        Row<V> t;
+#pragma unroll
+        for (int i = 0; i < V; ++i) t.v[i] = fmaxf(pre.v[i], 0.f);
+        float mean, rstd;
+        ln_stats<V>(t, eps, mean, rstd);
+        float s1_ = 0.f, s2_ = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float gv = GU ? gk.v[i] : uc.v[i];
+          const float xh = (t.v[i] - mean) * rstd;
+          const float dxi = gv * g.v[i];
+          s1_ += dxi;
+          s2_ += dxi * xh;
+          dg.v[i] += gv * xh;
+          db.v[i] += gv;
+          t.v[i] = xh;                 // keep xhat
+        }
+        constexpr float invC = 1.f / C;
+        s1_ = warp_sum(s1_) * invC;
+        s2_ = warp_sum(s2_) * invC;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float gv = GU ? gk.v[i] : uc.v[i];
+          const float dt = rstd * (gv * g.v[i] - s1_ - t.v[i] * s2_);
+          acc.v[i] += pre.v[i] > 0.f ? dt : 0.f;
+        }
+      }
+      acc.store(dOp + s * C, lane);
+      lo = hi;
+      hi = hi_next;
+    }
+  }
+  __syncthreads();                    // every warp is done with its staging rows
+  float* sm = sbuf;                   // [8][2C]
+  dg.store(sm + wib * 2 * C, lane);
+  db.store(sm + wib * 2 * C + C, lane);
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += sm[w * 2 * C + c];  // fixed order
+    dgb_partial[(int64_t)blockIdx.x * 2 * C + c] = v;
+  }
+}
+
 // Row LayerNorm of the dense MLPs (mlp.py:94-96: relu_ then LayerNorm), optionally with the ReLU folded in:
 //   y = LN(relu?(x)) ; backward dx = relu'(x) * LN_backward(dy), per-CTA partials of dgamma / dbeta.
 template <int V, bool RELU>
@@ -344,6 +460,14 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ partia
 
 }  // namespace eqh
 
+static bool legacy_dgb() {      // EQH_FUSED_BWD=legacy: the one-segment-per-turn kernel for the affine-partials variant too (A/B)
+  static const bool v = []() {
+    const char* e = getenv("EQH_FUSED_BWD");
+    return e != nullptr && e[0] == 'l';
+  }();
+  return v;
+}
+
 extern "C" {
 
 int eqh_partial_rows(void) { return eqh::kPartialRows; }
@@ -412,11 +536,21 @@ int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const i
     else if (gu) EQH_BWD(LNV, DGBV, false, true, true);        \
     else EQH_BWD(LNV, DGBV, false, true, false);               \
   } while (0)
+#define EQH_BWD_DGB(GAV, GBV, GUV)                                                                                 \
+  launch_kernel(k_fused_bwd_dgb<V, GAV, GBV, GUV>, dim3(grid), dim3(256), sizeof(float) * 16 * 32 * V, st, A, B, ia, ib, iu, rowptr, \
+                n_seg, gamma, eps, dU, u_rowptr, dOp, dgb_partial)
   EQH_DISPATCH_V(C, {
-    if (dgb_partial) EQH_BWD_G(true, true);
+    if (dgb_partial && legacy_dgb()) EQH_BWD_G(true, true);
+    else if (dgb_partial) {
+      if (ga && gu) EQH_BWD_DGB(true, false, true);
+      else if (ga) EQH_BWD_DGB(true, false, false);
+      else if (gu) EQH_BWD_DGB(false, true, true);
+      else EQH_BWD_DGB(false, true, false);
+    }
     else if (gamma) EQH_BWD_G(true, false);
     else EQH_BWD_G(false, false);
   });
+#undef EQH_BWD_DGB
 #undef EQH_BWD_G
 #undef EQH_BWD
   EQH_LAUNCH_RC();

@@ -129,9 +129,9 @@ class GraphedTrainer(Trainer):
                 b.copy_(saved)
         g = torch.cuda.CUDAGraph()
         before = ops.STATS["launches"]
-        # private pool per bucket: buckets may replay in any order.  The capture stream has high priority: the kernel nodes
-        # of the dX chain inherit it, the weight-gradient branch (ops.side_work, default priority) yields SMs to them.
-        prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "0"))     # -1: high-priority capture stream (A/B pending)
+        # private pool per bucket: buckets may replay in any order.  EQH_CAPTURE_PRIORITY=-1 captures on a high-priority
+        # stream (the dX chain's kernel nodes then win SMs over the weight-gradient branch): measured slower, kept off.
+        prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "0"))
         cap = torch.cuda.Stream(priority=prio) if prio != 0 else None
         with (torch.cuda.graph(g, stream=cap) if cap is not None else torch.cuda.graph(g)):
             loss = self._fwd_bwd(static)
