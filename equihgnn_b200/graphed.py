@@ -31,7 +31,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .synthetic import HBatch
-from .train import Trainer
+from .train import Trainer, model_loss
 
 GHOST_OFFSET = 1000.0   # Angstrom
 
@@ -103,8 +103,7 @@ class GraphedTrainer(Trainer):
 
     def _fwd_bwd(self, data) -> torch.Tensor:
         self.fp.zero_grad()
-        pred = self.model(data)
-        loss = F.mse_loss(pred[:self.B], data.y.view(-1)[:self.B])     # the ghost molecule is not in the loss
+        loss = model_loss(self.model, data, self.B)                    # the ghost molecule is not in the loss
         loss.backward()
         ops.side_work.join()        # the side-stream branch rejoins before the capture ends
         return loss.detach()

@@ -43,12 +43,16 @@ class MLP(nn.Module):
             if not isinstance(m, nn.Identity):
                 m.reset_parameters()
 
-    def forward(self, x):
+    def forward(self, x, upto_last: bool = False):
+        """upto_last=True: stop before the last Linear and return its input (the caller fuses that Linear with the loss,
+        ops.head_mse)."""
         x = self.normalizations[0](x)
         last = len(self.lins) - 1
         lead = x.shape[:-1]
         x = x.reshape(-1, x.shape[-1])
         for li, lin in enumerate(self.lins):
+            if upto_last and li == last:
+                break
             norm = self.normalizations[li + 1] if li < last else None
             if isinstance(norm, nn.LayerNorm) and ops.row_ln_supported(x, lin.out_features):
                 # Linear on the tcgen05 3xTF32 GEMM, then ReLU + LayerNorm as ONE row kernel (fwd and bwd)

@@ -58,6 +58,20 @@ def _num_graphs(data):
     return int(ng) if ng else None
 
 
+def _readout(mlp_out, x, loss_target):
+    """mlp_out(x).view(-1), or -- with loss_target=(y, n) -- (mse loss over the first n rows, predictions) with the last
+    Linear and the loss as one fused op (mhnn.py:216-218 / equihnn_egnn.py:167-169 + main.py:49-51)."""
+    if loss_target is None:
+        return mlp_out(x).view(-1)
+    y, n = loss_target
+    lin = mlp_out.lins[-1]
+    z = mlp_out(x, upto_last=True)
+    if ops.head_mse_supported(z, lin):
+        return ops.head_mse(z, lin.weight, lin.bias, y, n)
+    pred = torch.nn.functional.linear(z, lin.weight, lin.bias).view(-1)
+    return torch.nn.functional.mse_loss(pred[:n], y.view(-1)[:n]), pred.detach()
+
+
 def masked_batch_norm(x: torch.Tensor, bn: nn.BatchNorm1d, mask: torch.Tensor) -> torch.Tensor:
     """nn.BatchNorm1d over the rows with mask == 1 only (mhnn.py:182,206 on a ghost-padded batch): batch statistics,
     running-statistics update (momentum, unbiased variance) and normalisation as torch's BatchNorm1d, with the ghost
@@ -105,7 +119,9 @@ class EGNNEquiHNNS(nn.Module):
         self.conv.reset_parameters()
         self.mlp_out.reset_parameters()
 
-    def forward(self, data):
+    def forward(self, data, loss_target=None):
+        """loss_target=(y, n): return (mse(pred[:n], y[:n]), pred) with the last readout Linear and the loss fused
+        (ops.head_mse) instead of the predictions."""
         V, E = data.edge_index0, data.edge_index1
         N = data.x.shape[0]
         with ops.prep_work.fork(data.x.device):          # captured graph: the incidence CSR is built next to the encoder / kNN search
@@ -130,7 +146,7 @@ class EGNNEquiHNNS(nn.Module):
             x = self.act(x)
         x = self.dropout(x)
         x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)
-        return self.mlp_out(x).view(-1)
+        return _readout(self.mlp_out, x, loss_target)
 
 
 class MHNNM(nn.Module):
@@ -163,7 +179,7 @@ class MHNNM(nn.Module):
             layer.reset_parameters()
         self.mlp_out.reset_parameters()
 
-    def forward(self, data):
+    def forward(self, data, loss_target=None):
         V, E = data.edge_index0, data.edge_index1
         N = data.x.shape[0]
         x = self.atom_encoder(data.x)
@@ -180,7 +196,7 @@ class MHNNM(nn.Module):
                 x, e = self.dropout(self.act(x)), self.dropout(self.act(e))
         x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None),
                                 index=ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None), real=real or None))
-        return self.mlp_out(x).view(-1)
+        return _readout(self.mlp_out, x, loss_target)
 
 
 MODELS = {"egnn_equihnns": EGNNEquiHNNS, "mhnnm": MHNNM}

@@ -997,6 +997,59 @@ def global_add_pool(x: torch.Tensor, batch: torch.Tensor, size: Optional[int] = 
     return segment_reduce(x, rowptr, perm, dst32, n, "sum")
 
 
+class _HeadMSE(torch.autograd.Function):
+    """(z [R,K], w [1,K], b [1] | None, y [>=B]) -> (loss, pred [R]): last Linear of the readout (one target) + MSE over the
+    first B rows, forward and backward as one launch each (eqh_head_mse_fwd / _bwd).  pred is for logging: it carries
+    no gradient."""
+
+    @staticmethod
+    def forward(ctx, z, w, b, y, B):
+        z = _f32(z, "head_mse z")
+        wv = _f32(w, "head_mse weight").reshape(-1)
+        y = _f32(y.reshape(-1), "head_mse target")
+        R, K = z.shape
+        if wv.numel() != K or y.numel() < B or not 1 <= B <= R:
+            raise RuntimeError("head_mse: shape mismatch")
+        pred = torch.empty(R, dtype=torch.float32, device=z.device)
+        resid = torch.empty(R, dtype=torch.float32, device=z.device)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        _call("eqh_head_mse_fwd", 1, _p(z), _p(wv), _p(b), _p(y), R, K, B, _p(pred), _p(resid), _p(loss), _stream())
+        ctx.save_for_backward(z, wv, resid)
+        ctx.w_param, ctx.b_param = w, b
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, dloss, _dpred):
+        z, wv, resid = ctx.saved_tensors
+        R, K = z.shape
+        w, b = ctx.w_param, ctx.b_param
+        dz = torch.empty_like(z)
+        gw, gb = _direct_target(w), _direct_target(b)
+        direct = gw is not None and (b is None or gb is not None)
+        if direct:
+            dw, db = gw.view(-1), (gb if b is not None else None)
+        else:
+            dw = torch.empty(K, dtype=torch.float32, device=z.device)
+            db = torch.empty(1, dtype=torch.float32, device=z.device) if b is not None else None
+        g = _f32(dloss.reshape(1), "head_mse dloss")
+        _call("eqh_head_mse_bwd", 1, _p(z), _p(wv), _p(resid), _p(g), R, K, _p(dz), _p(dw), _p(db), 1 if direct else 0,
+              _stream())
+        if direct:
+            return dz, None, None, None, None
+        return dz, dw.view_as(w), (db.view_as(b) if b is not None else None), None, None
+
+
+def head_mse_supported(z: torch.Tensor, lin) -> bool:
+    return (z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and lin.out_features == 1
+            and lin.in_features <= 1024 and lin.weight.dtype == torch.float32)
+
+
+def head_mse(z: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, n_loss: int):
+    """loss = mse(linear(z, w, b)[:n_loss, 0], y[:n_loss]) and the predictions (no gradient), see _HeadMSE."""
+    return _HeadMSE.apply(z, w, b, y, int(n_loss))
+
+
 def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
                weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
     """In-place fused Adam on flat fp32 buffers (torch.optim.Adam semantics)."""

@@ -237,6 +237,18 @@ EQH_API int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc
                          float* part, const int32_t* order, eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Readout head + loss: the last Linear of the readout MLP with ONE target
+ * (mhnn.py:216-218, equihnn_egnn.py:167-169) and the MSE loss of main.py:49-51 over the first B rows
+ * (row B.. of a ghost-padded batch are not in the loss), forward and backward, one launch each.
+ *   fwd: pred [R] = z [R,K] . w [K] + b ; resid [R] = 2 (pred - y) / B (0 for r >= B) ; loss [1] = mean_{r<B} (pred - y)^2
+ *   bwd: dz [R,K] = g resid w ; dw [K] (+)= g sum_r resid[r] z[r,:] ; db [1] (+)= g sum_r resid[r]
+ *        g: device scalar (d loss), NULL = 1; accumulate != 0 adds into dw / db.   K <= 1024. */
+EQH_API int eqh_head_mse_fwd(const float* z, const float* w, const float* b /* optional */, const float* y, int64_t R,
+                     int64_t K, int64_t B, float* pred, float* resid, float* loss, eqh_stream_t stream);
+EQH_API int eqh_head_mse_bwd(const float* z, const float* w, const float* resid, const float* g /* optional */, int64_t R,
+                     int64_t K, float* dz, float* dw, float* db /* optional */, int accumulate, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * AtomEncoder (third-party ogb==1.3.6; call sites mhnn.py:201, equihnn_egnn.py:157):
  *     out[n,:] = sum_f tables[f][x[n,f], :]            x [N,F] int64, tables[f] [rows_per_table[f], C]
  * (tables / rows_per_table are HOST arrays of F device pointers / row counts, F <= 16).

@@ -359,6 +359,42 @@ def test_egnn_edge_bwd_tc_matches_the_cuda_core_kernel_and_fp64(profile, B, H, o
         assert torch.equal(a_, b_)
 
 
+@pytest.mark.parametrize("R,K,B", [(129, 128, 128), (1025, 128, 1024), (40, 100, 40), (7, 256, 3)])
+def test_head_mse_matches_torch(R, K, B):
+    """Last readout Linear (one target) + MSE over the first B rows, fused forward / backward:
+    loss, predictions, dz, dw, db against torch in fp64; direct accumulation into existing .grad; bit-identical reruns."""
+    g = torch.Generator().manual_seed(R + K)
+    z = torch.randn(R, K, generator=g)
+    w = 0.2 * torch.randn(1, K, generator=g)
+    b = 0.1 * torch.randn(1, generator=g)
+    y = torch.randn(R, generator=g)
+    zr, wr, br = (t.clone().double().requires_grad_(True) for t in (z, w, b))
+    pred_r = F.linear(zr, wr, br).view(-1)
+    loss_r = F.mse_loss(pred_r[:B], y.double()[:B])
+    (3.0 * loss_r).backward()
+    zd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (z, w, b))
+    loss, pred = ops.head_mse(zd, wd, bd, y.to(DEV), B)
+    assert not pred.requires_grad
+    (3.0 * loss).backward()
+    assert rel_err(loss, loss_r) < TOL and rel_err(pred, pred_r) < TOL
+    for got, want, name in ((zd.grad, zr.grad, "dz"), (wd.grad, wr.grad, "dw"), (bd.grad, br.grad, "db")):
+        assert rel_err(got, want) < TOL, name
+    assert float(zd.grad[B:].abs().max()) == 0.0 if B < R else True
+    # direct accumulation (the Trainer's flat gradient buffer): adds into the existing .grad
+    old = ops.DIRECT_PARAM_GRADS
+    ops.DIRECT_PARAM_GRADS = True
+    try:
+        w2, b2 = wd.detach().clone().requires_grad_(True), bd.detach().clone().requires_grad_(True)
+        w2.grad, b2.grad = torch.ones_like(w2), torch.ones_like(b2)
+        z2 = zd.detach().clone().requires_grad_(True)
+        l2, _ = ops.head_mse(z2, w2, b2, y.to(DEV), B)
+        (3.0 * l2).backward()
+        assert rel_err(w2.grad - 1.0, wr.grad) < TOL and rel_err(b2.grad - 1.0, br.grad) < 4 * TOL
+        assert torch.equal(z2.grad, zd.grad) and torch.equal(l2, loss)
+    finally:
+        ops.DIRECT_PARAM_GRADS = old
+
+
 def test_adam_step_matches_torch():
     g = torch.Generator().manual_seed(0)
     p0 = torch.randn(10001, generator=g)
