@@ -24,8 +24,8 @@
 // blocks (two TMEM buffers), so no accumulator sees more than 64 tensor-core accumulations.
 //
 // Warp roles (17 warps):
-//   warps 0-3    dS2 producer (4 values per thread and block), writes both layouts + the block's j / d2 / atom ids;
-//                drains D2; finishes dW2 / dwc / db2 partials
+//   warps 0-3    dS2 producer (4 values per thread and block; its loads are issued 4 / 8 blocks ahead), writes both
+//                layouts + the block's j / d2 / atom ids into an 8-deep ring; drains D2; finishes dW2 / dwc / db2 partials
 //   warps 4-15   three "column" warpgroups, round-robin over the blocks: the per-(edge, column) math above
 //   warp 16      MMA issuer (warp-uniform loop, one elected lane), MMA 2 lags MMA 1 by three blocks
 // Grid: ceil(H/128) column groups x S edge slices (S = 148 / groups); part row s receives the slice's partial sums.
@@ -98,13 +98,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
-}
-
-// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 
 #ifdef EQH_BWDTC_TRACE
