@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kHeadThreads) k_head_mse_bwd(const float* __re
   float acc = 0.f, accb = 0.f;
   if (rg < groups) {
     const float wk = __ldg(w + k);
+#pragma unroll 8
     for (int r = rg; r < R; r += groups) {
       const float c = gs * __ldg(resid + r);
       dz[(int64_t)r * K + k] = c * wk;
