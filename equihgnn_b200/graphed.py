@@ -98,6 +98,7 @@ class GraphedTrainer(Trainer):
         super().__init__(model, **kw)
         self.B = real_graphs
         self.buckets: Dict[Tuple[int, int, int, int], _Bucket] = {}
+        self._pool = None
         self.replays = 0
         self.own_launches = 0
 
@@ -128,11 +129,21 @@ class GraphedTrainer(Trainer):
                 b.copy_(saved)
         g = torch.cuda.CUDAGraph()
         before = ops.STATS["launches"]
-        # private pool per bucket: buckets may replay in any order.  EQH_CAPTURE_PRIORITY=-1 captures on a high-priority
-        # stream (the dX chain's kernel nodes then win SMs over the weight-gradient branch): measured slower, kept off.
+        # ONE memory pool for all buckets: the graphs replay one at a time, everything a replay reads it has written
+        # itself (inputs, parameters, gradients and optimizer state live outside the pool) and the loss is read before the
+        # next replay, so the buckets' intermediates may alias.  With a private pool per bucket 8 OPV-768-shaped buckets
+        # (~21 GB each: dPre alone is 5.4 GB) do not fit in 180 GB.  EQH_GRAPH_POOL=private restores one pool per bucket.
+        # EQH_CAPTURE_PRIORITY=-1 captures on a high-priority stream (the dX chain's kernel nodes then win SMs over the
+        # weight-gradient branch): measured slower, kept off.
+        kw = {}
+        if os.environ.get("EQH_GRAPH_POOL", "shared") != "private":
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            kw["pool"] = self._pool
         prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "0"))
-        cap = torch.cuda.Stream(priority=prio) if prio != 0 else None
-        with (torch.cuda.graph(g, stream=cap) if cap is not None else torch.cuda.graph(g)):
+        if prio != 0:
+            kw["stream"] = torch.cuda.Stream(priority=prio)
+        with torch.cuda.graph(g, **kw):
             loss = self._fwd_bwd(static)
         return _Bucket(static, g, loss, ops.STATS["launches"] - before)
 
