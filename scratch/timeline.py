@@ -9,9 +9,11 @@ from equihgnn_b200.graphed import GraphedTrainer, bucket_of, pad_batch
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = create_model("egnn_equihnns", 1, synthetic.model_args(256)).to(dev).train()
-tr = GraphedTrainer(model, real_graphs=128, lr=1e-4)
-b = synthetic.make_batch("qm9", 128, synthetic.bench_seed(2, 0, 0))
-d = pad_batch(b, bucket_of(b)).to(dev)
+PROF = sys.argv[1] if len(sys.argv) > 1 else "qm9"
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+b = synthetic.make_batch(PROF, NB, synthetic.bench_seed(2, 0, 0))
+tr = GraphedTrainer(model, real_graphs=NB, lr=1e-4)
+d = pad_batch(b, bucket_of(b)).pack(device=dev)
 for _ in range(5): tr.step(d)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -27,6 +29,6 @@ lo = adam[-2] + 1 if len(adam) >= 2 else 0
 step = rows[lo:adam[-1] + 1]
 t0 = step[0][0]
 out = [{"t": round(s - t0, 2), "dur": round(e - s, 2), "name": n[:70], "stream": st} for s, e, n, st in step]
-json.dump(out, open("gpurun_out/timeline_qm9_pdl%s.json" % os.environ.get("EQH_PDL", "1"), "w"))
+json.dump(out, open("gpurun_out/timeline_%s_pdl%s.json" % (PROF, os.environ.get("EQH_PDL", "1")), "w"))
 busy = sum(o["dur"] for o in out)
 print(f"{len(out)} kernels, span {step[-1][1] - t0:.1f} us, sum of durations {busy:.1f} us")
