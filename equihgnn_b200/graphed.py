@@ -21,13 +21,11 @@ result depends on every row: MHNNM evaluates it with the ghost rows masked out o
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import os
+from typing import Dict, Tuple
 
 import numpy as np
-import os
-
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .synthetic import HBatch

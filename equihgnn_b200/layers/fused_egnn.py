@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 
 from .. import ops
-from ..ops import KNN_K, M_DIM, SUM, _call, _p, _stream, gather_reduce_raw, gemm_raw, partial_rows
+from ..ops import KNN_K, M_DIM, SUM, _call, _p, _stream, gather_reduce_raw, gemm_raw
 from .fused_conv import _GradSink, _rowln_bwd
 
 
