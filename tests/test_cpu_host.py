@@ -186,3 +186,28 @@ def test_dataset_collation_reproduces_make_batch():
         sub = synthetic.collate_host(mols, y, [2, 0])
         assert sub.num_graphs == 2 and int(sub.ptr[-1]) == mols[2][0] + mols[0][0]
         assert int(sub.edge_index0.max()) < sub.num_atoms and int(sub.edge_index1.max()) + 1 == sub.num_hyperedges
+
+
+def test_readout_head_split_and_model_loss_fallback():
+    """Host logic of the fused readout head: `MLP(x, upto_last=True)` is exactly the input of the
+    last Linear, and `train.model_loss` takes the plain path (predictions -> F.mse_loss over the first n rows) for a
+    module whose forward has no `loss_target` keyword -- here on CPU, where the fused kernel does not exist."""
+    from equihgnn_b200.train import model_loss
+    torch.manual_seed(3)
+    mlp = MLP(in_channels=32, hidden_channels=16, out_channels=1, num_layers=3, dropout=0.0, Normalization="ln")
+    x = torch.randn(9, 32)
+    z = mlp(x, upto_last=True)
+    assert z.shape == (9, 16)
+    assert torch.equal(mlp.lins[-1](z), mlp(x))
+
+    class Plain(torch.nn.Module):
+        def forward(self, data):
+            return mlp(data.x).view(-1)
+
+    class D:
+        pass
+
+    d = D()
+    d.x, d.y = x, torch.randn(9)
+    want = torch.nn.functional.mse_loss(mlp(x).view(-1)[:7], d.y[:7])
+    assert torch.allclose(model_loss(Plain(), d, 7), want)
