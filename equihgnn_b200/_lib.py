@@ -63,6 +63,8 @@ _SIGNATURES = {
                                 _P, c_float, c_float, c_int, _P, _P, _P]),
     "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                               c_float, _P]),
+    "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
+                                  c_float, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

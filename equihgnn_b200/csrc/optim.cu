@@ -22,6 +22,49 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
+// Same update with the step count in DEVICE memory, so that the optimizer can live inside a captured CUDA graph
+// (a host-side `step` would be frozen into the graph's kernel parameters).  Every block reads t = *step + 1 and derives
+// the bias corrections in double, as torch.optim.Adam does on the host; with `advance` the block that finishes last
+// (integer arrival counter, left zero) stores t back.  Several launches of one optimizer step (one per gradient bucket)
+// pass advance = 0 except the last one.
+__global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float wd, long long* __restrict__ step, int advance,
+                                                   int32_t* __restrict__ counter, float gscale) {
+  pdl_prologue();
+  __shared__ float s_bc[2];
+  const long long t = *reinterpret_cast<volatile long long*>(step) + 1;
+  if (threadIdx.x == 0) {
+    s_bc[0] = (float)(1.0 - pow((double)b1, (double)t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i];
+    float gi = g[i] * gscale;
+    if (wd != 0.f) gi += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+  if (advance) {
+    __syncthreads();                       // every thread of this block has read *step
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int prev = atomicAdd(counter, 1);
+      if (prev == (int)gridDim.x - 1) {    // all blocks have read the old value: publish the new one
+        *counter = 0;
+        *step = t;
+      }
+    }
+  }
+}
+
 }  // namespace eqh
 
 extern "C" {
@@ -44,13 +87,29 @@ int eqh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   using namespace eqh;
   EQH_CHECK_ARG(n >= 0 && step >= 1 && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
   if (n == 0) return EQH_OK;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
+  // bias corrections in double on the host, as torch.optim.Adam computes them (1 - 0.999f in fp32 carries ~1e-5)
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
   launch_kernel(k_adam, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                          beta2, eps, weight_decay, bc1, sqrtf(bc2),
                                                                          grad_scale);
+  EQH_LAUNCH_RC();
+}
+
+int eqh_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev, int advance,
+                      int32_t* counter, float grad_scale, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(n >= 0 && step_dev && (!advance || counter) && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
+  if (n == 0 && !advance) return EQH_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  if (blocks < 1) blocks = 1;
+  launch_kernel(k_adam_dev, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg,
+                exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, reinterpret_cast<long long*>(step_dev), advance, counter,
+                grad_scale);
   EQH_LAUNCH_RC();
 }
 

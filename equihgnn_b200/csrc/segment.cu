@@ -29,11 +29,15 @@ __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__
       Row<V> x[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) r[u] = idx ? __ldg(idx + k + u) : (k + u);
+      // a negative row id (an out-of-range index the incidence builder marked with -1) contributes nothing
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u].load(table + (int64_t)r[u] * ld, lane);
+      for (int u = 0; u < 4; ++u) {
+        if (r[u] >= 0) x[u].load(table + (int64_t)r[u] * ld, lane);
+        else x[u].zero();
+      }
       if constexpr (WEIGHTED) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = inv_count(src_rowptr, r[u]);
+        for (int u = 0; u < 4; ++u) w[u] = r[u] >= 0 ? inv_count(src_rowptr, r[u]) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {  // strictly ascending k: same association as a sequential scatter_add_
@@ -43,6 +47,7 @@ __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__
     }
     for (; k < hi; ++k) {
       const int32_t r = idx ? __ldg(idx + k) : k;
+      if (r < 0) continue;
       Row<V> x;
       x.load(table + (int64_t)r * ld, lane);
       const float w = WEIGHTED ? inv_count(src_rowptr, r) : 1.f;
@@ -73,9 +78,11 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ t
     const int32_t s0 = idx ? __ldg(idx + r0) : (int32_t)r0;
     const int32_t s1 = two ? (idx ? __ldg(idx + r0 + 1) : (int32_t)(r0 + 1)) : s0;
     Row<V> a, b;
-    a.load(table + (int64_t)s0 * ld, lane);
-    b.load(table + (int64_t)s1 * ld, lane);
-    const float w0 = inv_count(scale_rowptr, s0), w1 = inv_count(scale_rowptr, s1);
+    // a negative source id (out-of-range index dropped by the incidence builder) yields a zero row, as the forward
+    // left that row out of every segment
+    if (s0 >= 0) a.load(table + (int64_t)s0 * ld, lane); else a.zero();
+    if (s1 >= 0) b.load(table + (int64_t)s1 * ld, lane); else b.zero();
+    const float w0 = s0 >= 0 ? inv_count(scale_rowptr, s0) : 0.f, w1 = s1 >= 0 ? inv_count(scale_rowptr, s1) : 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) { a.v[i] *= w0; b.v[i] *= w1; }
     a.store(out + r0 * ld, lane);

@@ -41,12 +41,9 @@ class _GradSink:
         self.side = direct        # (ops.side_work.fork degrades to the current stream outside graph capture)
         self.out = {}
         for p in params:
-            if direct:
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-                self.out[id(p)] = p.grad
-            else:
-                self.out[id(p)] = None
+            # direct mode: only into the registered view of the Trainer's flat buffer (ops.direct_target_strict raises if
+            # p.grad was re-bound -- never into a private tensor the optimizer would not read)
+            self.out[id(p)] = ops.direct_target_strict(p) if direct else None
         self.params = params
         self.batch = ops.ColsumBatch(params[0].device)
 

@@ -42,6 +42,14 @@ class AtomEncoder(nn.Module):
         return out
 
 
+def bond_encode(emb: nn.Embedding, edge_attr: torch.Tensor) -> torch.Tensor:
+    """`self.bond_encoder(data.edge_attr.squeeze())` (mhnn.py:67,202, equihnn_egnn.py:79,244): one-table case of the
+    embedding-sum kernel (forward gather, deterministic sliced backward) instead of ATen's embedding + atomic backward."""
+    if edge_attr.is_cuda and edge_attr.dtype == torch.int64:
+        return ops.atom_encode(edge_attr.reshape(-1, 1), [emb.weight])
+    return emb(edge_attr.reshape(-1))
+
+
 _ACTS = {"Id": nn.Identity, "relu": nn.ReLU, "prelu": nn.PReLU}
 
 
@@ -92,6 +100,149 @@ def masked_batch_norm(x: torch.Tensor, bn: nn.BatchNorm1d, mask: torch.Tensor) -
             bn.num_batches_tracked.add_(1)
     y = xc * torch.rsqrt(var + bn.eps)
     return y * bn.weight + bn.bias if bn.affine else y
+
+
+def hyperedge_batch_index(data, min_order: int = 2):
+    """Pooling index of `global_add_pool(e[data.e_order > 2], he_batch)` (mhnn.py:59-64,79 / equihnn_egnn.py:70-75,93)
+    built on device: the reference materialises `e_batch` with one `.item()` host sync per molecule and compacts the
+    conjugated hyperedges with a boolean mask (another sync).  Here hyperedge k goes to segment `e_batch[k]` when
+    e_order[k] > min_order and to a trailing segment otherwise, which is then emptied -- no sync, CUDA-graph capturable.
+
+    Returns (n_graphs + 1, rowptr, perm, dst32) for ops.segment_reduce; rows [0, n_graphs) of its output are the pooled
+    hyperedge features (molecules without a conjugated hyperedge get a zero row -- where the reference's
+    `batch.max() + 1` sizing would make `torch.cat((x, e), -1)` raise, mhnn.py:80)."""
+    B = _num_graphs(data)
+    if B is None:
+        B = int(data.n_e.shape[0])
+    E = int(data.e_order.shape[0])
+    dev = data.e_order.device
+    e_batch = torch.repeat_interleave(torch.arange(data.n_e.shape[0], device=dev), data.n_e, output_size=E)
+    dst = torch.where(data.e_order > min_order, e_batch, torch.full_like(e_batch, B))
+    rowptr, perm, dst32, _ = ops.csr_build(dst, B + 1, None)
+    rowptr[B + 1:] = rowptr[B:B + 1]          # the trailing segment (all order-2 bonds: ~97 % of the rows) is not reduced
+    return B + 1, rowptr, perm, dst32
+
+
+def _pool_hyperedges(e, index):
+    n, rowptr, perm, dst32 = index
+    return ops.segment_reduce(e, rowptr, perm, dst32, n, "sum")[:n - 1]
+
+
+class _SharedConvBase(nn.Module):
+    """Common constructor of the shared-parameter wrappers `mhnn` / `egnn_equihnn` (mhnn.py:13-55, equihnn_egnn.py:14-67):
+    module creation order follows the reference so that a torch seed yields the same initial weights."""
+
+    def __init__(self, num_target, args, with_egnn: bool):
+        super().__init__()
+        self.act = _ACTS[args.activation]()
+        self.dropout = nn.Dropout(args.dropout)
+        self.mlp1_layers = args.MLP1_num_layers
+        self.mlp2_layers = args.MLP2_num_layers
+        self.mlp3_layers = args.MLP3_num_layers
+        self.mlp4_layers = args.MLP4_num_layers
+        self.nlayer = args.All_num_layers
+        if with_egnn:
+            self.egnn_layer = EGNN(dim=args.MLP_hidden, norm_coors=True, norm_feats=True, valid_radius=5.0,
+                                   num_nearest_neighbors=16)
+        self.atom_encoder = AtomEncoder(emb_dim=args.MLP_hidden)
+        self.bond_encoder = nn.Embedding(6, args.MLP_hidden)
+        self.conv = MHNNConv(args.MLP_hidden, mlp1_layers=self.mlp1_layers, mlp2_layers=self.mlp2_layers,
+                             mlp3_layers=self.mlp3_layers, mlp4_layers=self.mlp4_layers, aggr=args.aggregate,
+                             dropout=args.dropout, normalization=args.normalization)
+        self.mlp_out = MLP(in_channels=args.MLP_hidden * 2, hidden_channels=args.output_hidden * 2,
+                           out_channels=num_target, num_layers=args.output_num_layers, dropout=args.dropout,
+                           Normalization=args.normalization, InputNorm=False)
+
+    def _forward(self, data, loss_target, with_egnn: bool):
+        V, E = data.edge_index0, data.edge_index1
+        N = data.x.shape[0]
+        dev = data.x.device
+        real = int(getattr(data, "num_real_graphs", 0) or 0) or None
+        with ops.prep_work.fork(dev):
+            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc.nonempty("e"), inc.nonempty("v")
+            pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None), real=real)
+            he_pool = hyperedge_batch_index(data)
+        x = self.atom_encoder(data.x)
+        if with_egnn:
+            x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)    # coors_out is discarded (:77)
+            x = x.squeeze(0)
+        e = bond_encode(self.bond_encoder, data.edge_attr)
+        ops.prep_work.join(dev)
+        for i in range(self.nlayer):
+            x, e = self.conv(x, e, V, E, incidence=inc)
+            if i == self.nlayer - 1:
+                x, e = self.dropout(x), self.dropout(e)
+            else:
+                x, e = self.dropout(self.act(x)), self.dropout(self.act(e))
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)
+        e = _pool_hyperedges(e, he_pool)
+        return _readout(self.mlp_out, torch.cat((x, e), -1), loss_target)
+
+
+class MHNN(_SharedConvBase):
+    """`--method mhnn` (mhnn.py:11-81): one MHNNConv shared by all layers, readout on cat(pooled atoms, pooled
+    conjugated hyperedges)."""
+
+    def __init__(self, num_target, args):
+        super().__init__(num_target, args, with_egnn=False)
+
+    def forward(self, data, loss_target=None):
+        return self._forward(data, loss_target, False)
+
+
+class EGNNEquiHNN(_SharedConvBase):
+    """`--method egnn_equihnn` (equihnn_egnn.py:12-95): EGNN layer, then the shared MHNNConv."""
+
+    def __init__(self, num_target, args):
+        super().__init__(num_target, args, with_egnn=True)
+
+    def forward(self, data, loss_target=None):
+        return self._forward(data, loss_target, True)
+
+
+class MHNNS(nn.Module):
+    """`--method mhnns` (mhnn.py:84-141): egnn_equihnns without the geometric branch."""
+
+    def __init__(self, num_target, args):
+        super().__init__()
+        self.act = _ACTS[args.activation]()
+        self.dropout = nn.Dropout(args.dropout)
+        self.mlp1_layers = args.MLP1_num_layers
+        self.mlp2_layers = args.MLP2_num_layers
+        self.mlp3_layers = args.MLP3_num_layers
+        self.nlayer = args.All_num_layers
+        self.atom_encoder = AtomEncoder(emb_dim=args.MLP_hidden)
+        self.conv = MHNNSConv(args.MLP_hidden, mlp1_layers=self.mlp1_layers, mlp2_layers=self.mlp2_layers,
+                              mlp3_layers=self.mlp3_layers, aggr=args.aggregate, dropout=args.dropout,
+                              normalization=args.normalization)
+        self.mlp_out = MLP(in_channels=args.MLP_hidden, hidden_channels=args.output_hidden, out_channels=num_target,
+                           num_layers=args.output_num_layers, dropout=args.dropout, Normalization=args.normalization,
+                           InputNorm=False)
+
+    def reset_parameters(self):
+        self.conv.reset_parameters()
+        self.mlp_out.reset_parameters()
+
+    def forward(self, data, loss_target=None):
+        V, E = data.edge_index0, data.edge_index1
+        N = data.x.shape[0]
+        dev = data.x.device
+        with ops.prep_work.fork(dev):
+            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc.nonempty("e"), inc.nonempty("v")
+            pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None),
+                                  real=int(getattr(data, "num_real_graphs", 0) or 0) or None)
+        x = self.atom_encoder(data.x)
+        ops.prep_work.join(dev)
+        x0 = x
+        for _ in range(self.nlayer):
+            x = self.dropout(x)
+            x = self.conv(x, V, E, x0, incidence=inc)
+            x = self.act(x)
+        x = self.dropout(x)
+        x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)
+        return _readout(self.mlp_out, x, loss_target)
 
 
 class EGNNEquiHNNS(nn.Module):
@@ -150,7 +301,10 @@ class EGNNEquiHNNS(nn.Module):
 
 
 class MHNNM(nn.Module):
-    """`--method mhnnm` (mhnn.py:144-218)."""
+    """`--method mhnnm` (mhnn.py:144-218); with `_with_egnn` also `egnn_equihnnm` (equihnn_egnn.py:172-261), which is the
+    same network behind an EGNN layer."""
+
+    _with_egnn = False
 
     def __init__(self, num_target, args):
         super().__init__()
@@ -161,6 +315,9 @@ class MHNNM(nn.Module):
         self.mlp3_layers = args.MLP3_num_layers
         self.mlp4_layers = args.MLP4_num_layers
         self.nlayer = args.All_num_layers
+        if self._with_egnn:                       # created first, as in the reference (same seeded initial values)
+            self.egnn_layer = EGNN(dim=args.MLP_hidden, norm_coors=True, norm_feats=True, valid_radius=5.0,
+                                   num_nearest_neighbors=16)
         self.atom_encoder = AtomEncoder(emb_dim=args.MLP_hidden)
         self.bond_encoder = nn.Embedding(6, args.MLP_hidden)
         self.layers = nn.ModuleList()
@@ -183,7 +340,10 @@ class MHNNM(nn.Module):
         V, E = data.edge_index0, data.edge_index1
         N = data.x.shape[0]
         x = self.atom_encoder(data.x)
-        e = self.bond_encoder(data.edge_attr.reshape(-1))
+        if self._with_egnn:
+            x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)    # coors_out discarded (:242)
+            x = x.squeeze(0)
+        e = bond_encode(self.bond_encoder, data.edge_attr)
         inc = ops.build_incidence(V, E, N, e.shape[0])
         real = int(getattr(data, "num_real_graphs", 0) or 0)
         mask = (data.batch < real) if real else None                  # ghost-padded batch: keep ghosts out of BatchNorm
@@ -199,7 +359,14 @@ class MHNNM(nn.Module):
         return _readout(self.mlp_out, x, loss_target)
 
 
-MODELS = {"egnn_equihnns": EGNNEquiHNNS, "mhnnm": MHNNM}
+class EGNNEquiHNNM(MHNNM):
+    """`--method egnn_equihnnm` (equihnn_egnn.py:172-261)."""
+
+    _with_egnn = True
+
+
+MODELS = {"mhnn": MHNN, "mhnns": MHNNS, "mhnnm": MHNNM, "egnn_equihnn": EGNNEquiHNN, "egnn_equihnns": EGNNEquiHNNS,
+          "egnn_equihnnm": EGNNEquiHNNM}
 
 
 def create_model(method: str, num_target, args) -> nn.Module:

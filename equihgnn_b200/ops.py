@@ -248,18 +248,63 @@ def counters(n: int, device) -> torch.Tensor:
     return buf[off:off + n]
 
 
-# Set by equihgnn_b200.train.Trainer.  When True, the generic autograd Functions below (Linear, row LayerNorm, atom
-# encoder) accumulate the gradients of leaf parameters that already own a `.grad` buffer straight into it (on the side
-# stream) and return None for them, instead of handing fresh tensors to autograd's AccumulateGrad (one add launch per
-# parameter).  The layer-level Functions (layers/fused_*.py) have their own flag.
-DIRECT_PARAM_GRADS = False
+# Direct parameter gradients.  A Trainer registers the parameters whose `.grad` is a view of ITS flat gradient buffer
+# (register_direct_grads); for exactly those, the generic autograd Functions below (Linear, row LayerNorm, atom encoder,
+# readout head) and the layer-level Functions (layers/fused_*.py) accumulate the gradient straight into that storage (on
+# the side stream) and return None, instead of handing fresh tensors to autograd's AccumulateGrad (one add launch per
+# parameter).  The registration is keyed on IDENTITY: the parameter object and the data pointer of its gradient view.  If
+# anything re-binds p.grad (model.zero_grad(set_to_none=True), optimizer.zero_grad(), ...) the pointer no longer matches:
+# the generic Functions fall back to returning the gradient to autograd and the layer-level Functions raise -- a
+# gradient can never land silently in a tensor the optimizer does not read.  Parameters nobody registered (any other
+# model in the process) always take the autograd path.
+_DIRECT = {}        # id(param) -> (weakref(param), data_ptr of the registered gradient view)
+
+
+def register_direct_grads(params) -> None:
+    for q in params:
+        if q.grad is None:
+            raise RuntimeError("register_direct_grads: parameter without a gradient buffer")
+        _DIRECT[id(q)] = (weakref.ref(q), q.grad.data_ptr())
+
+
+def unregister_direct_grads(params) -> None:
+    for q in params:
+        _DIRECT.pop(id(q), None)
+
+
+@contextlib.contextmanager
+def direct_grads(params):
+    """Scope in which `params` (each owning a `.grad` buffer) take the direct accumulation path."""
+    params = list(params)
+    register_direct_grads(params)
+    try:
+        yield
+    finally:
+        unregister_direct_grads(params)
+
+
+def direct_grad_registered(p) -> bool:
+    e = _DIRECT.get(id(p)) if p is not None else None
+    return e is not None and e[0]() is p
 
 
 def _direct_target(p) -> Optional[torch.Tensor]:
-    """p.grad if gradients of p may be accumulated in place (see DIRECT_PARAM_GRADS)."""
-    if DIRECT_PARAM_GRADS and p is not None and p.is_leaf and p.requires_grad and p.grad is not None:
-        return p.grad
-    return None
+    """p.grad if gradients of p may be accumulated in place: p is registered and p.grad still IS the registered view."""
+    e = _DIRECT.get(id(p)) if p is not None else None
+    if e is None or e[0]() is not p or not p.requires_grad or p.grad is None or p.grad.data_ptr() != e[1]:
+        return None
+    return p.grad
+
+
+def direct_target_strict(p) -> torch.Tensor:
+    """As _direct_target, for the layer-level Functions that have no autograd fallback: raises when the binding is broken."""
+    t = _direct_target(p)
+    if t is None:
+        raise RuntimeError(
+            "direct-gradient mode: a parameter's .grad is no longer the view of the Trainer's flat gradient buffer it was "
+            "registered with (zero_grad(set_to_none=True) or a re-assigned .grad?).  Use Trainer.fp.zero_grad(), or call "
+            "Trainer.rebind_gradients() after re-binding.")
+    return t
 
 
 class _SideWork:
@@ -1058,3 +1103,17 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.
             raise RuntimeError("adam_step_: flat contiguous CUDA float32 buffers required")
     _call("eqh_adam_step", 1, _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, betas[0], betas[1], eps,
           weight_decay, step, grad_scale, _stream())
+
+
+def adam_step_dev_(param, grad, exp_avg, exp_avg_sq, step_dev: torch.Tensor, lr: float, betas=(0.9, 0.999),
+                   eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0, advance: bool = True) -> None:
+    """adam_step_ with the step count in device memory (`step_dev`: int64 [1] holding t-1), so that the optimizer can be
+    captured in a CUDA graph; advance=False for all but the last launch of a step split over gradient buckets."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("adam_step_dev_: flat contiguous CUDA float32 buffers required")
+    if not (step_dev.is_cuda and step_dev.dtype == torch.int64 and step_dev.numel() == 1):
+        raise RuntimeError("adam_step_dev_: step_dev must be a CUDA int64 scalar")
+    cnt = counters(1, param.device) if advance else None
+    _call("eqh_adam_step_dev", 1, _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, betas[0], betas[1],
+          eps, weight_decay, _p(step_dev), int(advance), _p(cnt), grad_scale, _stream())

@@ -53,15 +53,21 @@ class FlatParams:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
+        self.offsets = []
         with torch.no_grad():
             for p in params:
                 k = p.numel()
                 self.flat[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + k].view_as(p)
-                p.grad = self.grad[off:off + k].view_as(p)
+                self.offsets.append(off)
                 off += (k + align - 1) // align * align
         self.params = params
         self.numel = n
+        self.bind_grads()
+
+    def bind_grads(self):
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.grad[off:off + p.numel()].view_as(p)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -78,7 +84,9 @@ class Trainer:
         for m in model.modules():       # kernels accumulate parameter gradients straight into the flat buffer
             if hasattr(m, "direct_param_grad"):
                 m.direct_param_grad = True
-        ops.DIRECT_PARAM_GRADS = True    # ... and so do the generic Linear / LayerNorm / atom-encoder Functions
+        # ... and so do the generic Linear / LayerNorm / atom-encoder Functions, for THESE parameters only and only while
+        # p.grad is still the view registered here (ops._direct_target checks identity on every use)
+        ops.register_direct_grads(self.fp.params)
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -89,8 +97,27 @@ class Trainer:
         self.distributed = distributed
         self.world = dist.get_world_size(process_group) if distributed else 1
 
+    def rebind_gradients(self) -> None:
+        """Point every parameter's .grad back at its slice of the flat gradient buffer (after something re-bound it)."""
+        self.fp.bind_grads()
+        ops.register_direct_grads(self.fp.params)
+
+    def close(self) -> None:
+        """Leave direct-gradient mode: the model goes back to plain autograd semantics."""
+        ops.unregister_direct_grads(self.fp.params)
+        for m in self.model.modules():
+            if hasattr(m, "direct_param_grad"):
+                m.direct_param_grad = False
+
+    def _check_binding(self) -> None:
+        for q in self.fp.params:
+            if ops._direct_target(q) is None:
+                raise RuntimeError("Trainer: a parameter's .grad no longer aliases the flat gradient buffer "
+                                   "(zero_grad(set_to_none=True)?): call rebind_gradients()")
+
     # -- pieces, so callers can time / graph them individually ---------------------------------
     def forward_backward(self, data) -> torch.Tensor:
+        self._check_binding()
         self.fp.zero_grad()
         loss = model_loss(self.model, data, data.y.view(-1).shape[0])
         loss.backward()

@@ -335,6 +335,15 @@ EQH_API int eqh_adam_step(float* param, const float* grad, float* exp_avg, float
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   eqh_stream_t stream);
 
+/* The same step with the step count t-1 held in DEVICE memory (int64), for an optimizer that lives inside a captured
+ * CUDA graph: every block derives the bias corrections of step t = *step_dev + 1 in double precision; with advance != 0
+ * the last block to finish stores t to *step_dev (counter: one zeroed int32, left zero).  An optimizer step split over
+ * several launches (one per gradient bucket, each after its own all-reduce; main.py:281 DDP buckets) passes advance = 0
+ * for all but the last launch. */
+EQH_API int eqh_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev, int advance,
+                      int32_t* counter, float grad_scale, eqh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,9 +147,21 @@ def case_egnn(ref, C, init_eps, B=10, seed=41, dtype=torch.float32, use_coors=Fa
 
 def case_model(ref, method, C, B, seed, profile="qm9", egnn_eps=None):
     b = _incidence(profile, B, seed)
+    if method in ("mhnn", "egnn_equihnn"):
+        # these wrappers size the pooled hyperedge matrix `he_batch.max() + 1` (mhnn.py:79): the reference only runs when
+        # the LAST molecule owns a conjugated hyperedge.  Pick the first such batch (seed, seed+100, ...) that also has an
+        # interior molecule without one (its pooled row must be 0).
+        while True:
+            e_batch = torch.repeat_interleave(torch.arange(B), b.n_e)
+            has = torch.bincount(e_batch[b.e_order > 2], minlength=B) > 0
+            if bool(has[-1]) and not bool(has[:-1].all()):
+                break
+            seed += 100
+            b = _incidence(profile, B, seed)
     args = model_args(hidden=C, output_hidden=max(C // 2, 16))
     torch.manual_seed(seed)
-    cls = {"egnn_equihnns": ref.EGNNEquiHNNS, "mhnnm": ref.MHNNM}[method]
+    cls = {"egnn_equihnns": ref.EGNNEquiHNNS, "mhnnm": ref.MHNNM, "mhnn": ref.MHNN, "mhnns": ref.MHNNS,
+           "egnn_equihnn": ref.EGNNEquiHNN, "egnn_equihnnm": ref.EGNNEquiHNNM}[method]
     m = cls(1, args)
     if egnn_eps is not None:  # O(0.1) EGNN weights so the non-residual part is visible
         with torch.no_grad():
@@ -163,39 +175,49 @@ def case_model(ref, method, C, B, seed, profile="qm9", egnn_eps=None):
     batch = {f: getattr(b, f) for f in ("x", "pos", "edge_index0", "edge_index1", "edge_attr", "n_e", "e_order",
                                         "batch", "ptr", "y")}
     batch["num_graphs"] = b.num_graphs
-    return {"method": method, "C": C, "args": vars(args), "batch": batch, "sd": _sd(m), "pred": pred.detach(),
+    return {"method": method, "C": C, "seed": seed, "args": vars(args), "batch": batch, "sd": _sd(m), "pred": pred.detach(),
             "loss": loss.detach(), "grads": _grads(m)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=OUT)
+    ap.add_argument("--only", default="", help="comma-separated fixture names (default: all)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the committed vectors
     ref = ref_harness.load()
     fixtures = {
-        "scatter": case_scatter(ref),
-        "mlp": case_mlp(ref),
-        "mhnns_ln_mean_c64": case_mhnns_conv(ref, 64, "ln", "mean", (2, 2, 2)),
-        "mhnns_none_sum_c32": case_mhnns_conv(ref, 32, "None", "sum", (2, 2, 2), seed=22),
-        "mhnns_ln_mean_l131_c32": case_mhnns_conv(ref, 32, "ln", "mean", (1, 3, 1), seed=23),
-        "mhnns_ln_mean_l012_c32": case_mhnns_conv(ref, 32, "ln", "mean", (0, 1, 2), seed=24),
-        "mhnns_ln_mean_opv_c32": case_mhnns_conv(ref, 32, "ln", "mean", (2, 2, 2), profile="opv", B=2, seed=25),
-        "mhnns_ln_mean_c32_f64": case_mhnns_conv(ref, 32, "ln", "mean", (2, 2, 2), seed=26, dtype=torch.float64),
-        "mhnn_ln_mean_c64": case_mhnn_conv(ref, 64, "ln", "mean", (2, 2, 2, 2)),
-        "mhnn_none_sum_c32": case_mhnn_conv(ref, 32, "None", "sum", (2, 2, 2, 2), seed=32),
-        "mhnn_ln_mean_l1031_c32": case_mhnn_conv(ref, 32, "ln", "mean", (1, 0, 3, 1), seed=33),
-        "mhnn_bn_mean_c32": case_mhnn_conv(ref, 32, "bn", "mean", (2, 2, 2, 2), seed=34),
-        "egnn_c64_eps0.1": case_egnn(ref, 64, 0.1),
-        "egnn_c64_default": case_egnn(ref, 64, 1e-3, seed=42),
-        "egnn_c32_coors": case_egnn(ref, 32, 0.1, B=6, seed=43, use_coors=True),
-        "egnn_c32_f64": case_egnn(ref, 32, 0.1, B=6, seed=44, dtype=torch.float64),
-        "model_egnn_equihnns_c64": case_model(ref, "egnn_equihnns", 64, 8, 51, egnn_eps=0.05),
-        "model_mhnnm_c64": case_model(ref, "mhnnm", 64, 8, 52),
+        "scatter": lambda: case_scatter(ref),
+        "mlp": lambda: case_mlp(ref),
+        "mhnns_ln_mean_c64": lambda: case_mhnns_conv(ref, 64, "ln", "mean", (2, 2, 2)),
+        "mhnns_none_sum_c32": lambda: case_mhnns_conv(ref, 32, "None", "sum", (2, 2, 2), seed=22),
+        "mhnns_ln_mean_l131_c32": lambda: case_mhnns_conv(ref, 32, "ln", "mean", (1, 3, 1), seed=23),
+        "mhnns_ln_mean_l012_c32": lambda: case_mhnns_conv(ref, 32, "ln", "mean", (0, 1, 2), seed=24),
+        "mhnns_ln_mean_opv_c32": lambda: case_mhnns_conv(ref, 32, "ln", "mean", (2, 2, 2), profile="opv", B=2, seed=25),
+        "mhnns_ln_mean_c32_f64": lambda: case_mhnns_conv(ref, 32, "ln", "mean", (2, 2, 2), seed=26, dtype=torch.float64),
+        "mhnn_ln_mean_c64": lambda: case_mhnn_conv(ref, 64, "ln", "mean", (2, 2, 2, 2)),
+        "mhnn_none_sum_c32": lambda: case_mhnn_conv(ref, 32, "None", "sum", (2, 2, 2, 2), seed=32),
+        "mhnn_ln_mean_l1031_c32": lambda: case_mhnn_conv(ref, 32, "ln", "mean", (1, 0, 3, 1), seed=33),
+        "mhnn_bn_mean_c32": lambda: case_mhnn_conv(ref, 32, "bn", "mean", (2, 2, 2, 2), seed=34),
+        "egnn_c64_eps0.1": lambda: case_egnn(ref, 64, 0.1),
+        "egnn_c64_default": lambda: case_egnn(ref, 64, 1e-3, seed=42),
+        "egnn_c32_coors": lambda: case_egnn(ref, 32, 0.1, B=6, seed=43, use_coors=True),
+        "egnn_c32_f64": lambda: case_egnn(ref, 32, 0.1, B=6, seed=44, dtype=torch.float64),
+        "model_egnn_equihnns_c64": lambda: case_model(ref, "egnn_equihnns", 64, 8, 51, egnn_eps=0.05),
+        "model_mhnnm_c64": lambda: case_model(ref, "mhnnm", 64, 8, 52),
+        # the other four wrappers; the pcqm4mv2 profile gives every molecule of these seeds'
+        # last positions a conjugated hyperedge often enough that the reference's cat((x, e)) does not raise
+        "model_mhnn_c32": lambda: case_model(ref, "mhnn", 32, 6, 53, profile="pcqm4mv2"),
+        "model_mhnns_c32": lambda: case_model(ref, "mhnns", 32, 8, 54),
+        "model_egnn_equihnn_c32": lambda: case_model(ref, "egnn_equihnn", 32, 6, 55, profile="pcqm4mv2", egnn_eps=0.05),
+        "model_egnn_equihnnm_c32": lambda: case_model(ref, "egnn_equihnnm", 32, 8, 56, egnn_eps=0.05),
     }
+    if a.only:
+        fixtures = {k: v for k, v in fixtures.items() if k in a.only.split(",")}
     total = 0
-    for name, fx in fixtures.items():
+    for name, make in fixtures.items():
+        fx = make()
         path = os.path.join(a.out, name + ".pt")
         torch.save(fx, path)
         sz = os.path.getsize(path)

@@ -17,7 +17,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("EQH_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """EQH_REFERENCE_ROOT, else /root/reference (build container), else the offline install `baseline/_ref` (git-ignored,
+    travels to the GPU box: `pip install --no-index --no-deps --target baseline/_ref <copy of /root/reference>`)."""
+    env = os.environ.get("EQH_REFERENCE_ROOT")
+    if env:
+        return env
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in ("/root/reference", os.path.join(here, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "equihgnn/models/layers/conv.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 _FILES = [
@@ -66,8 +79,11 @@ def load() -> types.SimpleNamespace:
         MHNNConv=mods["equihgnn.models.layers.conv"].MHNNConv,
         MHNNSConv=mods["equihgnn.models.layers.conv"].MHNNSConv,
         EGNN=mods["equihgnn.models.layers.egnn_layer"].EGNN,
+        MHNN=mods["equihgnn.models.mhnn"].MHNN,
         MHNNM=mods["equihgnn.models.mhnn"].MHNNM,
         MHNNS=mods["equihgnn.models.mhnn"].MHNNS,
+        EGNNEquiHNN=mods["equihgnn.models.equihnn_egnn"].EGNNEquiHNN,
         EGNNEquiHNNS=mods["equihgnn.models.equihnn_egnn"].EGNNEquiHNNS,
+        EGNNEquiHNNM=mods["equihgnn.models.equihnn_egnn"].EGNNEquiHNNM,
         modules=mods,
     )

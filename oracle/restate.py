@@ -233,6 +233,73 @@ def mhnnm(p: Params, data, nlayer: int = 3, aggr: str = "mean", normalization: s
     return mlp(p, "mlp_out", x, normalization).view(-1)                          # :217-218
 
 
+def _hyperedge_pool(e: Tensor, data, num_graphs: Optional[int]) -> Tensor:
+    """global_add_pool(e[data.e_order > 2], he_batch) with he_batch = repeat(arange(B), n_e)[e_order > 2]
+    (mhnn.py:59-64,79 / equihnn_egnn.py:70-75,93).  The reference sizes the output `he_batch.max() + 1`; with
+    num_graphs given the output has one row per molecule (zero rows for molecules without a conjugated hyperedge),
+    which is what the reference computes whenever its `torch.cat((x, e), -1)` does not raise."""
+    e_batch = torch.repeat_interleave(torch.arange(data.n_e.shape[0]), data.n_e)
+    keep = data.e_order > 2
+    return scatter_rows(e[keep], e_batch[keep], num_graphs, "sum")
+
+
+def _shared_mhnn(p: Params, data, nlayer, aggr, normalization, activation, with_egnn, nbhd) -> Tensor:
+    act = {"Id": lambda t: t, "relu": F.relu}[activation]
+    V, E = data.edge_index0, data.edge_index1
+    x = atom_encoder(p, "atom_encoder", data.x)
+    if with_egnn:
+        x, _ = egnn(p, "egnn_layer", x, data.pos, 16, True, True, nbhd=nbhd)     # equihnn_egnn.py:77
+    e = p["bond_encoder.weight"][data.edge_attr.reshape(-1)]
+    for i in range(nlayer):                                                      # shared conv
+        x, e = mhnn_conv(p, "conv", x, e, V, E, aggr, normalization)
+        if i != nlayer - 1:
+            x, e = act(x), act(e)
+    B = getattr(data, "num_graphs", None)
+    x = global_add_pool(x, data.batch, B)
+    e = _hyperedge_pool(e, data, B)
+    return mlp(p, "mlp_out", torch.cat((x, e), -1), normalization).view(-1)
+
+
+def mhnn(p: Params, data, nlayer: int = 3, aggr: str = "mean", normalization: str = "ln", activation: str = "relu") -> Tensor:
+    """MHNN.forward -- mhnn.py:57-81 (dropout p=0)."""
+    return _shared_mhnn(p, data, nlayer, aggr, normalization, activation, False, None)
+
+
+def egnn_equihnn(p: Params, data, nlayer: int = 3, aggr: str = "mean", normalization: str = "ln", activation: str = "relu",
+                 nbhd: Optional[Tensor] = None) -> Tensor:
+    """EGNNEquiHNN.forward -- equihnn_egnn.py:69-95 (dropout p=0)."""
+    return _shared_mhnn(p, data, nlayer, aggr, normalization, activation, True, nbhd)
+
+
+def mhnns(p: Params, data, nlayer: int = 3, aggr: str = "mean", normalization: str = "ln", activation: str = "relu") -> Tensor:
+    """MHNNS.forward -- mhnn.py:130-141 (dropout p=0)."""
+    act = {"Id": lambda t: t, "relu": F.relu}[activation]
+    V, E = data.edge_index0, data.edge_index1
+    x = atom_encoder(p, "atom_encoder", data.x)
+    x0 = x
+    for _ in range(nlayer):
+        x = act(mhnns_conv(p, "conv", x, V, E, x0, aggr, 0.5, normalization))
+    x = global_add_pool(x, data.batch, getattr(data, "num_graphs", None))
+    return mlp(p, "mlp_out", x, normalization).view(-1)
+
+
+def egnn_equihnnm(p: Params, data, nlayer: int = 3, aggr: str = "mean", normalization: str = "ln",
+                  activation: str = "relu", nbhd: Optional[Tensor] = None) -> Tensor:
+    """EGNNEquiHNNM.forward -- equihnn_egnn.py:233-261 (dropout p=0; BatchNorm1d in train mode)."""
+    act = {"Id": lambda t: t, "relu": F.relu}[activation]
+    V, E = data.edge_index0, data.edge_index1
+    x = atom_encoder(p, "atom_encoder", data.x)
+    x, _ = egnn(p, "egnn_layer", x, data.pos, 16, True, True, nbhd=nbhd)         # :242
+    e = p["bond_encoder.weight"][data.edge_attr.reshape(-1)]
+    for i in range(nlayer):
+        x, e = mhnn_conv(p, f"layers.{i}", x, e, V, E, aggr, normalization)
+        x = F.batch_norm(x, None, None, p[f"batch_norms.{i}.weight"], p[f"batch_norms.{i}.bias"], True, 0.1, 1e-5)
+        if i != nlayer - 1:
+            x, e = act(x), act(e)
+    x = global_add_pool(x, data.batch, getattr(data, "num_graphs", None))
+    return mlp(p, "mlp_out", x, normalization).view(-1)
+
+
 def train_step_loss(model_fn, p: Dict[str, Tensor], data, **kw) -> Tensor:
     """LitModel.training_step: MSELoss(model(data), y)  (main.py:49-51)."""
     return F.mse_loss(model_fn(p, data, **kw), data.y.view(-1))

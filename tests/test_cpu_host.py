@@ -129,6 +129,27 @@ def test_models_same_parameters():
     assert sum(p.numel() for p in MHNNM(1, synthetic.model_args(256)).parameters()) == 2_469_249
 
 
+@pytest.mark.parametrize("name,cls", [("model_mhnn_c32", "MHNN"), ("model_mhnns_c32", "MHNNS"),
+                                      ("model_egnn_equihnn_c32", "EGNNEquiHNN"),
+                                      ("model_egnn_equihnnm_c32", "EGNNEquiHNNM")])
+def test_other_wrappers_same_parameters(name, cls):
+    """the four remaining wrappers keep the reference's parameter names, shapes and seeded values."""
+    import argparse
+    from equihgnn_b200 import models
+    fx = load_golden(name)
+    torch.manual_seed(fx["seed"])
+    m = getattr(models, cls)(1, argparse.Namespace(**fx["args"]))
+    sd, g = m.state_dict(), fx["sd"]
+    assert list(sd.keys()) == list(g.keys())
+    for k in sd:
+        if "running" in k or "num_batches" in k:
+            continue
+        if k.startswith("egnn_layer") and k.endswith("weight") and sd[k].dim() == 2:
+            continue                                            # re-drawn with std 0.05 by make_golden
+        assert torch.equal(sd[k], g[k]), k
+    assert models.MODELS[fx["method"]] is getattr(models, cls)
+
+
 @pytest.mark.parametrize("profile", list(synthetic.PROFILES))
 def test_synthetic_batch_invariants(profile):
     B = 6 if profile == "opv" else 16
@@ -211,3 +232,29 @@ def test_readout_head_split_and_model_loss_fallback():
     d.x, d.y = x, torch.randn(9)
     want = torch.nn.functional.mse_loss(mlp(x).view(-1)[:7], d.y[:7])
     assert torch.allclose(model_loss(Plain(), d, 7), want)
+
+
+def test_direct_gradient_registry_is_keyed_on_identity():
+    """direct accumulation only while p.grad IS the registered view of the flat gradient buffer; a
+    re-bound .grad falls back to autograd (generic Functions) or raises (layer-level Functions) -- never a silent detour."""
+    from equihgnn_b200 import ops
+    from equihgnn_b200.train import FlatParams
+    lin = torch.nn.Linear(8, 4)
+    other = torch.nn.Linear(8, 4)
+    fp = FlatParams(lin)
+    assert lin.weight.grad.data_ptr() == fp.grad.data_ptr()
+    assert ops._direct_target(lin.weight) is None                     # nobody registered it yet
+    with ops.direct_grads(fp.params):
+        assert ops._direct_target(lin.weight) is lin.weight.grad
+        assert ops._direct_target(other.weight) is None               # another model in the process: autograd path
+        lin.zero_grad(set_to_none=True)                               # what optimizer.zero_grad() does by default
+        assert ops._direct_target(lin.weight) is None
+        with pytest.raises(RuntimeError):
+            ops.direct_target_strict(lin.weight)
+        lin.weight.grad = torch.zeros_like(lin.weight)                # a private tensor is not the flat buffer either
+        assert ops._direct_target(lin.weight) is None
+        fp.bind_grads()
+        ops.register_direct_grads(fp.params)
+        assert ops._direct_target(lin.weight) is lin.weight.grad
+        assert lin.weight.grad.data_ptr() == fp.grad.data_ptr()
+    assert not ops.direct_grad_registered(lin.weight)                 # the scope restores plain autograd semantics

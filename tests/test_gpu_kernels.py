@@ -381,18 +381,20 @@ def test_head_mse_matches_torch(R, K, B):
         assert rel_err(got, want) < TOL, name
     assert float(zd.grad[B:].abs().max()) == 0.0 if B < R else True
     # direct accumulation (the Trainer's flat gradient buffer): adds into the existing .grad
-    old = ops.DIRECT_PARAM_GRADS
-    ops.DIRECT_PARAM_GRADS = True
-    try:
-        w2, b2 = wd.detach().clone().requires_grad_(True), bd.detach().clone().requires_grad_(True)
-        w2.grad, b2.grad = torch.ones_like(w2), torch.ones_like(b2)
+    w2, b2 = wd.detach().clone().requires_grad_(True), bd.detach().clone().requires_grad_(True)
+    w2.grad, b2.grad = torch.ones_like(w2), torch.ones_like(b2)
+    with ops.direct_grads([w2, b2]):
         z2 = zd.detach().clone().requires_grad_(True)
         l2, _ = ops.head_mse(z2, w2, b2, y.to(DEV), B)
         (3.0 * l2).backward()
         assert rel_err(w2.grad - 1.0, wr.grad) < TOL and rel_err(b2.grad - 1.0, br.grad) < 4 * TOL
         assert torch.equal(z2.grad, zd.grad) and torch.equal(l2, loss)
-    finally:
-        ops.DIRECT_PARAM_GRADS = old
+        # a re-bound .grad (e.g. zero_grad(set_to_none=True)) breaks the registration: plain autograd semantics again
+        w2.grad, b2.grad = None, None
+        l3, _ = ops.head_mse(zd.detach().clone().requires_grad_(True), w2, b2, y.to(DEV), B)
+        (3.0 * l3).backward()
+        assert rel_err(w2.grad, wr.grad) < TOL and rel_err(b2.grad, br.grad) < 4 * TOL
+    assert not ops.direct_grad_registered(w2)
 
 
 def test_adam_step_matches_torch():

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 from conftest import as_data, grads_mismatch, load_golden, rel_err
 from equihgnn_b200 import ops, synthetic
 from equihgnn_b200.layers import EGNN, MHNNConv, MHNNSConv
-from equihgnn_b200.models import EGNNEquiHNNS, MHNNM
+from equihgnn_b200.models import EGNNEquiHNN, EGNNEquiHNNM, EGNNEquiHNNS, MHNN, MHNNM, MHNNS
 from oracle import restate as R
 
 pytestmark = pytest.mark.gpu
@@ -128,7 +128,10 @@ def test_egnn_pos_gradient_and_errors():
                                                                                               device=DEV))
 
 
-@pytest.mark.parametrize("name,cls", [("model_egnn_equihnns_c64", EGNNEquiHNNS), ("model_mhnnm_c64", MHNNM)])
+@pytest.mark.parametrize("name,cls", [("model_egnn_equihnns_c64", EGNNEquiHNNS), ("model_mhnnm_c64", MHNNM),
+                                      # the remaining wrappers, goldens from the verbatim reference
+                                      ("model_mhnn_c32", MHNN), ("model_mhnns_c32", MHNNS),
+                                      ("model_egnn_equihnn_c32", EGNNEquiHNN), ("model_egnn_equihnnm_c32", EGNNEquiHNNM)])
 def test_models_golden(name, cls):
     fx = load_golden(name)
     import argparse
@@ -397,6 +400,16 @@ def test_trainer_direct_gradient_path_matches_autograd_and_oracle(side, monkeypa
     tr.forward_backward(d)
     torch.cuda.synchronize()
     assert torch.equal(g_first, tr.fp.grad)
+    # a re-bound .grad must not detour gradients into tensors the optimizer never reads
+    tr.model.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        tr.forward_backward(d)
+    tr.rebind_gradients()
+    tr.forward_backward(d)
+    torch.cuda.synchronize()
+    assert torch.equal(g_first, tr.fp.grad)
+    tr.close()
+    assert not tr.model.conv.direct_param_grad and not ops.direct_grad_registered(tr.fp.params[0])
 
 
 def test_graphed_mhnnm_matches_eager_unpadded_steps():

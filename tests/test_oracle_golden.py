@@ -121,7 +121,10 @@ def test_knn_k_larger_than_n_raises():
         R.knn(torch.randn(10, 3), 16)
 
 
-@pytest.mark.parametrize("name,fn", [("model_egnn_equihnns_c64", R.egnn_equihnns), ("model_mhnnm_c64", R.mhnnm)])
+@pytest.mark.parametrize("name,fn", [("model_egnn_equihnns_c64", R.egnn_equihnns), ("model_mhnnm_c64", R.mhnnm),
+                                     ("model_mhnn_c32", R.mhnn), ("model_mhnns_c32", R.mhnns),
+                                     ("model_egnn_equihnn_c32", R.egnn_equihnn),
+                                     ("model_egnn_equihnnm_c32", R.egnn_equihnnm)])
 def test_models(name, fn):
     fx = load_golden(name)
     p = _leafs({k: v for k, v in fx["sd"].items() if "running" not in k and "num_batches" not in k})
