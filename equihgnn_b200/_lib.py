@@ -42,6 +42,8 @@ _SIGNATURES = {
     "eqh_knn16_grid_workspace_bytes": (c_size_t, [c_int64]),
     "eqh_knn16_grid": (c_int, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
     "eqh_knn16_grid_ordered": (c_int, [_P, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "eqh_knn": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
+    "eqh_radius": (c_int, [_P, c_int64, c_float, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     "eqh_egnn_pack": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "eqh_egnn_edge_fwd_smem_bytes": (c_size_t, [c_int64]),
     "eqh_egnn_edge_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),

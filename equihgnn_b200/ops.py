@@ -821,6 +821,73 @@ def knn16(pos: torch.Tensor, method: Optional[str] = None, return_order: bool = 
     return (idx, d2, order) if return_order else (idx, d2)
 
 
+def _segments(N: int, batch: Optional[torch.Tensor], ptr: Optional[torch.Tensor], device):
+    """(seg_ptr int32 [S+1], seg_of int32 [N]) of a collated batch: from PyG's `ptr` when given, else from the sorted
+    `batch` vector (bincount + cumsum on device, no host sync beyond the segment count)."""
+    if batch is None and ptr is None:
+        return None, None
+    if ptr is None:
+        if batch.numel() != N:
+            raise RuntimeError("neighbour search: batch vector length must match the number of atoms")
+        S = int(batch.max().item()) + 1 if N else 0
+        cnt = torch.bincount(batch, minlength=S)
+        ptr = torch.zeros(S + 1, dtype=torch.int64, device=device)
+        ptr[1:] = torch.cumsum(cnt, 0)
+    seg_ptr = ptr.to(torch.int32).contiguous()
+    if batch is None:
+        S = seg_ptr.numel() - 1
+        batch = torch.repeat_interleave(torch.arange(S, device=device), (seg_ptr[1:] - seg_ptr[:-1]).long(), output_size=N)
+    return seg_ptr, batch.to(torch.int32).contiguous()
+
+
+def knn(pos: torch.Tensor, k: int, batch: Optional[torch.Tensor] = None, ptr: Optional[torch.Tensor] = None,
+        exclude_self: bool = False):
+    """General exact k-NN on squared distance (eqh_knn): pos [N,3] float32 -> (idx [N,k] int32, d2 [N,k] float32),
+    ascending, ties by smaller index.  With `batch` (sorted molecule id per atom) or `ptr` every atom searches its own
+    molecule only (FAFormer / Equiformer / SE(3)-Transformer dense-batch semantics); missing slots hold -1 / +inf."""
+    pos = _f32(pos.detach(), "knn pos")
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise RuntimeError(f"knn: expected [N,3] coordinates, got {tuple(pos.shape)}")
+    if not 1 <= k <= 32:
+        raise NotImplementedError(f"knn: k={k} outside the implemented range [1, 32]")
+    N = pos.shape[0]
+    seg_ptr, seg_of = _segments(N, batch, ptr, pos.device)
+    if seg_ptr is None and N < k + int(exclude_self):
+        raise RuntimeError(f"selected index k out of range (k={k} > n={N - int(exclude_self)})")      # torch.topk's error
+    idx = torch.empty((N, k), dtype=torch.int32, device=pos.device)
+    d2 = torch.empty((N, k), dtype=torch.float32, device=pos.device)
+    _call("eqh_knn", 1 if N else 0, _p(pos), N, k, _p(seg_ptr), _p(seg_of), int(exclude_self), _p(idx), _p(d2), _stream())
+    return idx, d2
+
+
+def radius(pos: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, ptr: Optional[torch.Tensor] = None,
+           max_num_neighbors: int = 32, loop: bool = False, return_d2: bool = False):
+    """Fixed-width radius search (eqh_radius): (idx [N, max_num_neighbors] int32 padded with -1, count [N] int32
+    [, d2]) -- for each atom the first max_num_neighbors atoms of its molecule, ascending index, with d2 < r*r."""
+    pos = _f32(pos.detach(), "radius pos")
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise RuntimeError(f"radius: expected [N,3] coordinates, got {tuple(pos.shape)}")
+    N = pos.shape[0]
+    seg_ptr, seg_of = _segments(N, batch, ptr, pos.device)
+    idx = torch.empty((N, max_num_neighbors), dtype=torch.int32, device=pos.device)
+    cnt = torch.empty(N, dtype=torch.int32, device=pos.device)
+    d2 = torch.empty((N, max_num_neighbors), dtype=torch.float32, device=pos.device) if return_d2 else None
+    _call("eqh_radius", 1 if N else 0, _p(pos), N, float(r), _p(seg_ptr), _p(seg_of), int(loop), int(max_num_neighbors),
+          _p(idx), _p(cnt), _p(d2), _stream())
+    return (idx, cnt, d2) if return_d2 else (idx, cnt)
+
+
+def radius_graph(pos: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, loop: bool = False,
+                 max_num_neighbors: int = 32) -> torch.Tensor:
+    """Drop-in for `torch_cluster.radius_graph(pos, r, batch, loop, max_num_neighbors)` as ViSNet calls it
+    (visnet_layer.py:336; flow source_to_target): edge_index [2, M] int64 with row 0 = neighbour j, row 1 = centre i,
+    grouped by i, j ascending.  The compaction to M edges is the one host sync (the reference's op syncs too)."""
+    idx, cnt = radius(pos, r, batch, None, max_num_neighbors, loop)
+    keep = idx >= 0
+    centre = torch.arange(idx.shape[0], device=idx.device).unsqueeze(1).expand_as(idx)
+    return torch.stack((idx[keep].long(), centre[keep]), 0)
+
+
 @dataclass
 class KnnGraph:
     """kNN edges (i -> idx[i,k]) plus the transposed incidence (grouped by neighbour j) that the

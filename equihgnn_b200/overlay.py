@@ -77,3 +77,50 @@ def install():
 def uninstall():
     while _installed:
         sys.modules.pop(_installed.pop(), None)
+
+
+def load_reference_models(reference_root: str):
+    """Execute the reference's OWN wrapper files (`equihgnn/models/mhnn.py`, `equihnn_egnn.py`, unmodified, read from
+    `reference_root`: a checkout or the offline install `baseline/_ref`) on top of the overlay, i.e. what
+    `python main.py --method mhnnm|egnn_equihnns ...` resolves to once `install()` has run: their imports
+    (mhnn.py:3-8, equihnn_egnn.py:3-9) bind to this package's layers, scatter, pooling and encoder.
+
+    The package's `equihgnn/models/__init__.py` is not executed (it imports every model family, including the ones
+    whose third-party dependencies / weight blobs are absent); the two files are loaded by path
+    under their real dotted names, as is `equihgnn/common/registry.py`.  Returns {method name: class}."""
+    import os
+    install()
+    out = {}
+    _ensure_stub("equihgnn")
+    _ensure_stub("equihgnn.common")
+    _ensure_stub("equihgnn.models")
+    for name, rel in (("equihgnn.common.registry", "equihgnn/common/registry.py"),
+                      ("equihgnn.models.mhnn", "equihgnn/models/mhnn.py"),
+                      ("equihgnn.models.equihnn_egnn", "equihgnn/models/equihnn_egnn.py")):
+        path = os.path.join(reference_root, rel)
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        _installed.append(name)
+        spec.loader.exec_module(mod)
+        parent, _, leaf = name.rpartition(".")
+        setattr(sys.modules[parent], leaf, mod)
+        out[name] = mod
+    reg = out["equihgnn.common.registry"].registry
+    return {m: reg.get_model_class(m) for m in ("mhnn", "mhnns", "mhnnm", "egnn_equihnn", "egnn_equihnns", "egnn_equihnnm")}
+
+
+def _ensure_stub(name: str):
+    """A bare package object under `name` (never imports the real one: see load_reference_models)."""
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = types.ModuleType(name)
+    pkg.__path__ = []
+    sys.modules[name] = pkg
+    _installed.append(name)
+    if "." in name:
+        parent, _, leaf = name.rpartition(".")
+        setattr(_ensure_stub(parent), leaf, pkg)
+    return pkg

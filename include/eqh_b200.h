@@ -204,6 +204,25 @@ EQH_API size_t eqh_egnn_edge_fwd_smem_bytes(int64_t H);
 EQH_API int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                          const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij /* optional */,
                          float* Mi, eqh_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Shared neighbour-search primitive for the other geometric encoders.
+ *
+ * eqh_knn: exact k nearest neighbours on squared distance, k in [1, 32], ascending, ties by smaller index.
+ *   seg_ptr / seg_of NULL: the whole cloud is one range (EGNN, egnn_layer.py:281-283; self is rank 0 unless
+ *   exclude_self).  Otherwise atoms are grouped in contiguous ranges [seg_ptr[s], seg_ptr[s+1]) (a collated batch:
+ *   PyG Batch.ptr) and seg_of[i] is atom i's range: each atom searches its own molecule only -- the dense-batch
+ *   semantics of FAFormer's _build_graph (fa_former_layer.py:650-667, exclude_self = 1), Equiformer
+ *   (equiformer_layer.py:1326) and the SE(3)-Transformer (se3_transformer_layer.py:1577).  Slots beyond the number of
+ *   candidates hold idx = -1, d2 = +inf (the references fill them with masked 1e9 / max_value distances).
+ * eqh_radius: torch_cluster.radius_graph semantics (visnet_layer.py:336): for atom i the first max_num_neighbors atoms
+ *   j of its range, in ascending j, with d2(i,j) < r*r (strict); loop != 0 keeps j == i.  idx [N, max_num_neighbors]
+ *   (-1 padded), count [N], optional d2 [N, max_num_neighbors].
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_knn(const float* pos /*[N,3]*/, int64_t N, int k, const int32_t* seg_ptr, const int32_t* seg_of,
+            int exclude_self, int32_t* idx /*[N,k]*/, float* d2 /*[N,k]*/, eqh_stream_t stream);
+EQH_API int eqh_radius(const float* pos /*[N,3]*/, int64_t N, float r, const int32_t* seg_ptr, const int32_t* seg_of, int loop,
+               int max_num_neighbors, int32_t* idx, int32_t* count /*[N]*/, float* d2 /*optional*/, eqh_stream_t stream);
+
 /* eqh_egnn_edge_fwd_tc visiting the atoms in `order` (a permutation of [0,N), e.g. from eqh_knn16_grid_ordered; NULL =
  * natural order).  Outputs are identical; only the memory access pattern changes. */
 EQH_API int eqh_egnn_edge_fwd_tc_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,

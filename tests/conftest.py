@@ -68,3 +68,43 @@ def grads_mismatch(got, golden, tol, floor_frac=5e-2):
         if not e < tol:
             bad[k] = e
     return bad
+
+
+def rebuild_headline_case(fx):
+    """Regenerate the batch and the initial weights of a `headline_*` fixture from its seeds (oracle/make_golden.py
+    case_model_headline) and verify them against the stored checksums."""
+    import argparse
+    from equihgnn_b200 import synthetic
+    from equihgnn_b200.models import MODELS
+    b = synthetic.make_batch(fx["profile"], fx["B"], fx["seed"])
+    torch.manual_seed(fx["seed"])
+    m = MODELS[fx["method"]](1, argparse.Namespace(**fx["args"]))
+    if fx["egnn_eps"] is not None:
+        g = torch.Generator().manual_seed(fx["seed"] + 1)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if k.startswith("egnn_layer") and k.endswith("weight") and p.dim() == 2:
+                    p.copy_(torch.randn(p.shape, generator=g) * fx["egnn_eps"])
+    c = fx["check"]
+    assert (b.num_atoms, b.num_hyperedges, b.num_incidences) == (c["N"], c["E"], c["Z"])
+    assert float(b.pos.double().sum()) == c["pos_sum"] and int(b.x.sum()) == c["x_sum"]
+    assert float(b.y.double().sum()) == c["y_sum"]
+    assert float(sum(p.detach().double().sum() for p in m.parameters())) == c["w_sum"]
+    assert float(sum(p.detach().double().abs().sum() for p in m.parameters())) == c["w_abs"]
+    return b, m
+
+
+def headline_grad_errors(named_grads, fx):
+    """Per parameter: (error of `named_grads` against the verbatim reference's fp64 gradient on the stored slice,
+    the verbatim fp32 reference's own error on the same slice), both relative to max(|g|_max, 5 % of the largest)."""
+    scale = max(g["maxabs"] for g in fx["grads"].values() if g)
+    out = {}
+    for k, g in fx["grads"].items():
+        got = named_grads.get(k)
+        if g is None:
+            assert got is None or float(got.abs().max()) == 0.0, k
+            continue
+        den = max(g["maxabs"], 0.05 * scale)
+        sel = got.detach().reshape(-1).cpu()[g["sel"]].double()
+        out[k] = (float((sel - g["val64"]).abs().max()) / den, float((g["val"].double() - g["val64"]).abs().max()) / den)
+    return out

@@ -524,3 +524,96 @@ def test_edge_kernels_in_cell_order_give_the_same_results():
     for a_, b_ in zip(res["natural"][:4], res["cell"][:4]):
         assert torch.equal(a_, b_)
     assert rel_err(res["cell"][4], res["natural"][4].double()) < 2e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# shared neighbour-search primitive: eqh_knn / eqh_radius
+# ----------------------------------------------------------------------------------------------------------------------
+def _ref_dense_topk(pos, batch, k, exclude_self):
+    """FAFormer._build_graph (fa_former_layer.py:650-667) on squared distance: pairs outside the molecule (and the
+    diagonal) are masked out, then topk(largest=False); masked slots are reported as -1 / +inf."""
+    rel = pos[:, None, :] - pos[None, :, :]
+    d2 = (rel ** 2).sum(-1)
+    mask = torch.zeros_like(d2, dtype=torch.bool)
+    if batch is not None:
+        mask |= batch[:, None] != batch[None, :]
+    if exclude_self:
+        mask |= torch.eye(pos.shape[0], dtype=torch.bool)
+    d2 = d2.masked_fill(mask, float("inf"))
+    v, i = d2.topk(k, dim=-1, largest=False)
+    return torch.where(torch.isinf(v), torch.full_like(i, -1), i), v
+
+
+@pytest.mark.parametrize("k", [1, 8, 16, 24, 32])
+@pytest.mark.parametrize("mode", ["cloud", "cloud_noself", "molecules", "molecules_noself", "molecules_ptr"])
+def test_knn_general_bit_exact_vs_topk(k, mode):
+    """k in [8, 32] (and 1), whole cloud or per molecule, with / without self: indices and squared distances are
+    bit-identical to torch.topk on the masked all-pairs matrix for tie-free coordinates."""
+    b = synthetic.make_batch("pcqm4mv2", 24, 300 + k)          # molecules of 6..51 atoms: some smaller than k
+    pos, batch = b.pos, b.batch
+    seg = mode.startswith("molecules")
+    noself = mode.endswith("noself")
+    if mode == "molecules_ptr":
+        idx, d2 = ops.knn(pos.to(DEV), k, ptr=b.ptr.to(DEV))
+    else:
+        idx, d2 = ops.knn(pos.to(DEV), k, batch=batch.to(DEV) if seg else None, exclude_self=noself)
+    ridx, rd2 = _ref_dense_topk(pos, batch if seg else None, k, noself)
+    assert torch.equal(d2.cpu(), rd2)
+    assert torch.equal(idx.cpu().long(), ridx)
+    if not noself:
+        assert torch.equal(idx[:, 0].cpu().long(), torch.arange(pos.shape[0]))
+    if seg:        # neighbours never leave the molecule
+        ok = idx.cpu() >= 0
+        assert bool((batch[idx.cpu().long().clamp(min=0)] == batch[:, None])[ok].all())
+        assert bool((idx.cpu() < 0).any()) == bool((torch.bincount(batch) - int(noself) < k).any())
+
+
+def test_knn_general_agrees_with_knn16_and_rejects_bad_arguments():
+    b = synthetic.make_batch("qm9", 64, 5)
+    i16, d16 = ops.knn16(b.pos.to(DEV))
+    ig, dg = ops.knn(b.pos.to(DEV), 16)
+    assert torch.equal(i16, ig) and torch.equal(d16, dg)
+    big = synthetic.make_batch("molecule3d", 600, 6)             # N > 16384: the 8-lanes-per-query variant
+    i16, d16 = ops.knn16(big.pos.to(DEV), method="scan")
+    ig, dg = ops.knn(big.pos.to(DEV), 16)
+    assert torch.equal(i16, ig) and torch.equal(d16, dg)
+    with pytest.raises(NotImplementedError):
+        ops.knn(b.pos.to(DEV), 33)
+    with pytest.raises(RuntimeError):
+        ops.knn(torch.randn(10, 3, device=DEV), 16)              # torch.topk raises for k > n
+    with pytest.raises(RuntimeError):
+        ops.knn(torch.randn(16, 3, device=DEV), 16, exclude_self=True)
+
+
+@pytest.mark.parametrize("r,max_nb,loop", [(1.7, 32, False), (3.0, 8, False), (2.5, 32, True), (0.0, 4, False)])
+def test_radius_graph_matches_torch_cluster_semantics(r, max_nb, loop):
+    """torch_cluster.radius_graph (third-party, not installed; semantics restated): per molecule, for centre i the first
+    max_num_neighbors atoms j in ascending index with |x_i - x_j|^2 < r^2, self excluded unless loop; edge_index rows
+    (j, i), grouped by i."""
+    b = synthetic.make_batch("molecule3d", 40, 77)
+    pos, batch = b.pos, b.batch
+    N = pos.shape[0]
+    d2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    ok = (d2 < torch.tensor(r, dtype=torch.float32) ** 2) & (batch[:, None] == batch[None, :])
+    if not loop:
+        ok &= ~torch.eye(N, dtype=torch.bool)
+    rows, cols = [], []
+    for i in range(N):
+        js = torch.nonzero(ok[i]).view(-1)[:max_nb]
+        rows.append(js)
+        cols.append(torch.full_like(js, i))
+    want = torch.stack((torch.cat(rows), torch.cat(cols)), 0)
+    got = ops.radius_graph(pos.to(DEV), r, batch.to(DEV), loop=loop, max_num_neighbors=max_nb)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), want)
+    idx, cnt, dd = ops.radius(pos.to(DEV), r, batch.to(DEV), None, max_nb, loop, return_d2=True)
+    assert torch.equal(cnt.cpu().long(), torch.tensor([len(x) for x in rows]))
+    keep = idx.cpu() >= 0
+    assert torch.equal(dd.cpu()[keep], d2[torch.arange(N)[:, None].expand_as(idx)[keep], idx.cpu().long()[keep]])
+    # no batch vector: one cloud
+    got1 = ops.radius_graph(pos.to(DEV), r, None, loop=loop, max_num_neighbors=max_nb)
+    ok1 = d2 < torch.tensor(r, dtype=torch.float32) ** 2
+    if not loop:
+        ok1 &= ~torch.eye(N, dtype=torch.bool)
+    want1 = torch.cat([torch.stack((torch.nonzero(ok1[i]).view(-1)[:max_nb],
+                                    torch.full((min(int(ok1[i].sum()), max_nb),), i)), 0) for i in range(N)], 1)
+    assert torch.equal(got1.cpu(), want1)

@@ -441,3 +441,96 @@ def test_graphed_mhnnm_matches_eager_unpadded_steps():
             assert rel_err(bg[k], be[k]) < 2e-2, k
         if "num_batches" in k:
             assert int(bg[k]) == int(be[k]) == 4
+
+
+def _reference_root():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("EQH_REFERENCE_ROOT"), os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "equihgnn", "models", "equihnn_egnn.py")):
+            return cand
+    return None
+
+
+@pytest.mark.parametrize("name", ["model_egnn_equihnns_c64", "model_mhnnm_c64", "model_mhnn_c32", "model_mhnns_c32",
+                                  "model_egnn_equihnn_c32", "model_egnn_equihnnm_c32"])
+def test_reference_wrappers_run_unchanged_on_the_overlay(name):
+    """The drop-in executed end to end: the reference's OWN wrapper files (equihnn_egnn.py, mhnn.py; read unmodified
+    from the offline install baseline/_ref or EQH_REFERENCE_ROOT) are loaded on top of overlay.install() -- what
+    `main.py --method ...` resolves to -- and must reproduce the goldens of the verbatim reference on the CUDA path:
+    their MHNNConv / MHNNSConv / EGNN / MLP / scatter / global_add_pool / AtomEncoder are this package's."""
+    import argparse
+    import sys
+    from equihgnn_b200 import overlay
+    root = _reference_root()
+    if root is None:
+        pytest.skip("no reference tree (baseline/_ref or EQH_REFERENCE_ROOT)")
+    fx = load_golden(name)
+    shim_paths = [p for p in sys.path if p.replace("\\", "/").endswith("oracle/shims")]
+    for p in shim_paths:                       # the CPU stand-ins of the oracle must not shadow the overlay
+        sys.path.remove(p)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k.split(".")[0] in ("equihgnn", "torch_scatter", "torch_geometric", "ogb")}
+    try:
+        classes = overlay.load_reference_models(root)
+        assert sys.modules["torch_scatter"].scatter is ops.scatter
+        assert sys.modules["equihgnn.models.layers.conv"].MHNNSConv is MHNNSConv
+        cls = classes[fx["method"]]
+        assert cls.__module__ in ("equihgnn.models.mhnn", "equihgnn.models.equihnn_egnn")      # the reference's class
+        m = cls(1, argparse.Namespace(**fx["args"])).to(DEV)
+        sd = dict(fx["sd"])
+        for k in sd:
+            if k.endswith("running_mean"):
+                sd[k] = torch.zeros_like(sd[k])
+            elif k.endswith("running_var"):
+                sd[k] = torch.ones_like(sd[k])
+        m.load_state_dict(sd)
+        m.train()
+        before = ops.STATS["launches"]
+        data = as_data(fx["batch"], device=DEV)
+        pred = m(data)
+        loss = F.mse_loss(pred, data.y)
+        loss.backward()
+        assert ops.STATS["launches"] - before > 20            # the CUDA library did the work
+        assert rel_err(pred, fx["pred"]) < TOL_MODEL
+        assert abs(float(loss.detach()) - float(fx["loss"])) < TOL_MODEL * max(1.0, abs(float(fx["loss"])))
+        assert not grads_mismatch(_named_grads(m), fx["grads"], TOL_MODEL)
+    finally:
+        overlay.uninstall()
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("equihgnn", "torch_scatter", "torch_geometric", "ogb"):
+                sys.modules.pop(k, None)
+        sys.modules.update(saved)
+        sys.path[:0] = shim_paths
+
+
+def test_headline_shape_matches_the_verbatim_reference():
+    """BASELINE configs[1] (the bench workload: QM9-shaped batch 128, C=256, L=3) against the VERBATIM reference run at
+    that shape.  Predictions and loss to 5e-5 / 1e-5.  Gradients: the fixture also holds the verbatim
+    files' fp64 gradients; the fp32 reference itself is 1e-4..1e-3 away from them wherever a ReLU follows (gates within
+    rounding of zero flip), and ~3e-7 above the last gate.  The CUDA path must be as close to the fp64 truth as the
+    reference's own fp32 arithmetic up to a factor 4, floor 2e-5 -- i.e. the strict bar wherever no gate is involved."""
+    from conftest import headline_grad_errors, rebuild_headline_case
+    fx = load_golden("headline_egnn_equihnns_c256_qm9b128")
+    b, m = rebuild_headline_case(fx)
+    m = m.to(DEV).train()
+    d = b.to(DEV)
+    pred = m(d)
+    loss = F.mse_loss(pred, d.y)
+    loss.backward()
+    assert rel_err(pred, fx["pred64"]) < TOL_MODEL and rel_err(pred, fx["pred"]) < TOL_MODEL
+    assert abs(float(loss.detach()) - float(fx["loss64"])) < 1e-5 * abs(float(fx["loss64"]))
+    errs = headline_grad_errors(_named_grads(m), fx)
+    bad = {k: v for k, v in errs.items() if v[0] > max(2e-5, 4 * v[1])}
+    assert not bad, bad
+    # ... and through the Trainer's hand-scheduled layer Functions (the path the bench times)
+    from equihgnn_b200.train import Trainer
+    b2, m2 = rebuild_headline_case(fx)
+    tr = Trainer(m2.to(DEV).train(), lr=1e-3)
+    loss2 = tr.forward_backward(d)
+    torch.cuda.synchronize()
+    assert abs(float(loss2) - float(fx["loss64"])) < 1e-5 * abs(float(fx["loss64"]))
+    errs2 = headline_grad_errors({k: q.grad for k, q in tr.model.named_parameters()}, fx)
+    bad2 = {k: v for k, v in errs2.items() if v[0] > max(2e-5, 4 * v[1])}
+    assert not bad2, bad2
+    tr.close()
