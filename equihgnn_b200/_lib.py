@@ -65,6 +65,15 @@ _SIGNATURES = {
                                 _P, c_float, c_float, c_int, _P, _P, _P]),
     "eqh_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                               c_float, _P]),
+    "eqh_rowln_fwd_ld": (c_int, [_P, c_int64, _P, _P, c_float, c_int, c_int64, c_int64, _P, c_int64, _P]),
+    "eqh_rowln_bwd_ld": (c_int, [_P, c_int64, _P, c_float, c_int, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, _P]),
+    "eqh_gather_reduce_ld": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, _P, c_int64, _P]),
+    "eqh_egnn_edge_fwd_tc_ld": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P]),
+    "eqh_egnn_edge_bwd_tc_ld": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P,
+                                        _P, _P, _P]),
+    "eqh_egnn_unpack_grads": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
+    "eqh_gemm_tf32x3_ex": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
+                                   c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P]),
     "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
                                   c_float, _P]),
 }

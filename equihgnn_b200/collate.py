@@ -100,16 +100,19 @@ def collate_device(store: MoleculeStore, ids: Sequence[int], bucket: Optional[Tu
 
 
 class StoreTrainer(GraphedTrainer):
-    """GraphedTrainer fed by molecule ids: collation happens on the device, straight into the graph's static inputs."""
+    """GraphedTrainer fed by molecule ids: collation happens on the device, straight into the graph's static inputs.
+    fixed_bucket: pad every batch to this (N_pad, E_pad, Z_pad) instead of its own bucket (uniform shapes over ranks)."""
 
-    def __init__(self, model, store: MoleculeStore, real_graphs: int, **kw):
+    def __init__(self, model, store: MoleculeStore, real_graphs: int, fixed_bucket: Optional[Tuple[int, int, int]] = None,
+                 **kw):
         super().__init__(model, real_graphs, **kw)
         self.store = store
+        self.fixed_bucket = fixed_bucket
 
-    def step_from_ids(self, ids: Sequence[int], step_inputs: Optional[torch.Tensor] = None) -> float:
+    def step_from_ids(self, ids: Sequence[int], step_inputs: Optional[torch.Tensor] = None, sync: bool = True):
         shape = self.store.shape_of(ids)
         N, E, Z = shape
-        bucket = ((N + 1 + 255) // 256 * 256, (E + 1 + 255) // 256 * 256, (Z + 511) // 512 * 512)
+        bucket = self.fixed_bucket or ((N + 1 + 255) // 256 * 256, (E + 1 + 255) // 256 * 256, (Z + 511) // 512 * 512)
         key = (bucket[0], bucket[1], bucket[2], len(ids) + 1)
         bk = self.buckets.get(key)
         if bk is None:
@@ -119,6 +122,8 @@ class StoreTrainer(GraphedTrainer):
         bk.graph.replay()
         self.replays += 1
         self.own_launches += bk.launches + 1
-        self.sync_gradients()
-        self.optimizer_step()
-        return float(bk.loss.item())
+        if self.in_graph_step:
+            self.t += 1
+        self._finish_outside()
+        self._queue_loss(bk.loss)
+        return self._read_loss(1) if sync else self._read_loss(2)

@@ -312,9 +312,47 @@ __global__ void __launch_bounds__(256) k_egnn_pack(const float* __restrict__ W1,
   }
 }
 
+// The inverse re-layout for the gradients, accumulating: T [2 Hp, C] = [dP | dQ]^T . h (rows 0..Hp-1: d W1a, rows Hp..: d W1b)
+// and red = (dW2 [16, Hp] | dwc [Hp] | db2 [16]) are added into the parameters' own gradient tensors
+// gW1 [H0, 2C+1], gW2 [16, H0], gb2 [16] (one launch instead of four strided ATen adds).
+__global__ void __launch_bounds__(256) k_egnn_unpack_grads(const float* __restrict__ T, const float* __restrict__ red, int H0,
+                                                            int C, int Hp, float* __restrict__ gW1, float* __restrict__ gW2,
+                                                            float* __restrict__ gb2) {
+  pdl_prologue();
+  const int64_t ld = 2 * (int64_t)C + 1;
+  const int64_t n1 = (int64_t)H0 * ld, n2 = n1 + (int64_t)kM * H0, n3 = n2 + kM;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < n1) {
+      const int64_t r = t / ld, c = t - r * ld;
+      float v;
+      if (c < C) v = __ldg(T + r * C + c);
+      else if (c < 2 * C) v = __ldg(T + ((int64_t)Hp + r) * C + (c - C));
+      else v = __ldg(red + (int64_t)kM * Hp + r);
+      gW1[t] += v;
+    } else if (t < n2) {
+      const int64_t u = t - n1, o = u / H0, h = u - o * H0;
+      gW2[u] += __ldg(red + o * Hp + h);
+    } else {
+      gb2[t - n2] += __ldg(red + (int64_t)(kM + 1) * Hp + (t - n2));
+    }
+  }
+}
+
 }  // namespace eqh
 
 extern "C" {
+
+int eqh_egnn_unpack_grads(const float* T, const float* red, int64_t H0, int64_t C, int64_t Hp, float* gW1, float* gW2,
+                          float* gb2, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(T && red && gW1 && gW2 && gb2 && H0 > 0 && C > 0 && Hp >= H0);
+  const int64_t n = H0 * (2 * C + 1) + (int64_t)kM * H0 + kM;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  launch_kernel(k_egnn_unpack_grads, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), T, red, (int)H0,
+                (int)C, (int)Hp, gW1, gW2, gb2);
+  EQH_LAUNCH_RC();
+}
 
 int eqh_egnn_pack(const float* W1, const float* b1, const float* W2, int64_t H0, int64_t C, int64_t Hp, float* W1a, float* W1b,
                   float* wc, float* b1p, float* W2p, eqh_stream_t stream) {

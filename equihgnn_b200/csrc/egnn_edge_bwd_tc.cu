@@ -135,7 +135,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
               const float* __restrict__ W2, const int32_t* __restrict__ idx, const float* __restrict__ d2,
               const float* __restrict__ S2, const float* __restrict__ dMi, int64_t N, int H, int ngroups, int nslices,
               float* __restrict__ dP, float* __restrict__ dPre, float* __restrict__ part, int64_t part_cols,
-              const int32_t* __restrict__ order) {
+              const int32_t* __restrict__ order, int64_t ldpq, int64_t lddp, int64_t lddmi) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* ds_full = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [DSLOT] dS2 tiles + meta written
@@ -240,7 +240,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       if (atom >= 0) {
         const int64_t e = (int64_t)atom * kNbr + (el & 15);
         v.s2 = __ldg(reinterpret_cast<const float4*>(S2 + e * kM) + oq);
-        v.gm = __ldg(reinterpret_cast<const float4*>(dMi + (int64_t)atom * kM) + oq);
+        v.gm = __ldg(reinterpret_cast<const float4*>(dMi + (int64_t)atom * lddmi) + oq);
         if (oq == 0) {
           v.jj = __ldg(idx + e);
           v.dd = __ldg(d2 + e);
@@ -387,10 +387,10 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         // warp q copies rows q, q+4, ..., q+28 of Q and (q < 2) the P row of atom q: all row ids first, then the copies
         const float* src[9];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) src[i] = Q + (int64_t)mm->j[q + 4 * i] * ld;
+        for (int i = 0; i < 8; ++i) src[i] = Q + (int64_t)mm->j[q + 4 * i] * ldpq;
         {
           const int32_t a = mm->atom[q & 1];
-          src[8] = P + (int64_t)(a >= 0 ? a : 0) * ld;
+          src[8] = P + (int64_t)(a >= 0 ? a : 0) * ldpq;
         }
         const uint32_t d = smem_u32(qring + stage * kQStageBytes + lane * 16 + q * (GC * 4));
 #pragma unroll
@@ -447,7 +447,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
           float* dprow = dPre + ((int64_t)at * kNbr) * ld + col;
 #pragma unroll
           for (int k = 0; k < kNbr; ++k, dprow += ld) *dprow = dh[k];
-          dP[(int64_t)at * ld + col] = dpa;
+          dP[(int64_t)at * lddp + col] = dpa;
         }
         tmem_st16(a2 + half * 16, hv);                    // hi: the tensor core ignores the low 13 bits
 #pragma unroll
@@ -513,17 +513,27 @@ int eqh_egnn_edge_bwd_tc_rows(int64_t H) { return H > 0 ? eqh::edge_bwd_tc::slic
 int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const int32_t* idx,
                          const float* d2, const float* S2, const float* dMi, int64_t N, int64_t H, float* dP, float* dPre,
                          float* part, const int32_t* order, eqh_stream_t stream) {
+  return eqh_egnn_edge_bwd_tc_ld(P, Q, H, wc, W2, idx, d2, S2, dMi, EQH_M_DIM, N, H, dP, H, dPre, part, order, stream);
+}
+
+// Strided variant (see eqh_egnn_edge_fwd_tc_ld): P / Q row stride ldpq, dP written with row stride lddp (a column block of
+// the merged [dP | dQ] matrix), dMi read with row stride lddmi (a column block of the node MLP's input gradient).
+int eqh_egnn_edge_bwd_tc_ld(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                            const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi, int64_t N,
+                            int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
+                            eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::edge_bwd_tc;
   EQH_CHECK_ARG(P && Q && wc && W2 && idx && d2 && S2 && dMi && dP && dPre && part && N >= 0);
-  EQH_CHECK_ARG(aligned16(S2) && aligned16(dMi));
+  EQH_CHECK_ARG(aligned16(S2) && aligned16(dMi) && aligned16(P) && aligned16(Q));
+  EQH_CHECK_ARG(ldpq >= H && ldpq % 4 == 0 && lddp >= H && lddmi >= kM && lddmi % 4 == 0);
   if (H <= 0 || H % 64 != 0 || groups_of(H) > kSMs) return EQH_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   if (e != cudaSuccess) return (int)e;
   const int gr = groups_of(H), sl = slices_of(H);
   const int64_t part_cols = (int64_t)(kM + 1) * H + kM;
   launch_kernel(k_edge_bwd_tc, dim3((unsigned)(gr * sl)), dim3(kThreads), (size_t)kSmem, static_cast<cudaStream_t>(stream), P, Q, wc,
-                W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order);
+                W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order, ldpq, lddp, lddmi);
   EQH_LAUNCH_RC();
 }
 

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ wc,
               const float* __restrict__ W2, const float* __restrict__ b2, const int32_t* __restrict__ idx,
               const float* __restrict__ d2, int64_t N, int H, int64_t ldpq, float* __restrict__ S2,
-              float* __restrict__ Mij, float* __restrict__ Mi, const int32_t* __restrict__ order) {
+              float* __restrict__ Mij, float* __restrict__ Mi, int64_t ldmi, const int32_t* __restrict__ order) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * kStageBytes);
@@ -251,7 +251,7 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         m[o] = x;
       }
       if ((lane & 15) == 0 && ok) {
-        float4* mip = reinterpret_cast<float4*>(Mi + (e >> 4) * kM);
+        float4* mip = reinterpret_cast<float4*>(Mi + (e >> 4) * ldmi);
 #pragma unroll
         for (int o = 0; o < kM; o += 4) mip[o >> 2] = make_float4(m[o], m[o + 1], m[o + 2], m[o + 3]);
       }
@@ -265,12 +265,13 @@ k_edge_fwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
 }  // namespace edge_tc
 }  // namespace eqh
 
-static int edge_fwd_tc_impl(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
+static int edge_fwd_tc_impl(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2, const float* b2,
                             const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij, float* Mi,
-                            const int32_t* order, eqh_stream_t stream) {
+                            int64_t ldmi, const int32_t* order, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::edge_tc;
   EQH_CHECK_ARG(P && Q && wc && W2 && b2 && idx && d2 && S2 && Mi && N >= 0);
+  EQH_CHECK_ARG(ldpq >= H && ldpq % 4 == 0 && ldmi >= kM && ldmi % 4 == 0);
   EQH_CHECK_ARG(aligned16(P) && aligned16(Q) && aligned16(wc) && aligned16(W2) && aligned16(S2) && aligned16(Mi) &&
                 aligned16(Mij));
   if (H <= 0 || H % 64 != 0) return EQH_ERR_UNSUPPORTED;
@@ -281,19 +282,27 @@ static int edge_fwd_tc_impl(const float* P, const float* Q, const float* wc, con
   auto kern = N >= 8192 ? k_edge_fwd_tc<2> : k_edge_fwd_tc<1>;      // measured: QM9-128 45 vs 53 us, Molecule3D-1024 821 vs 668 us
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  launch_kernel(kern, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), P, Q, wc, W2, b2, idx, d2, N, (int)H, H, S2,
-                Mij, Mi, order);
+  launch_kernel(kern, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), P, Q, wc, W2, b2, idx, d2, N, (int)H, ldpq, S2,
+                Mij, Mi, ldmi, order);
   EQH_LAUNCH_RC();
 }
 
 extern "C" int eqh_egnn_edge_fwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                                     const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
                                     float* Mi, eqh_stream_t stream) {
-  return edge_fwd_tc_impl(P, Q, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, nullptr, stream);
+  return edge_fwd_tc_impl(P, Q, H, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, EQH_M_DIM, nullptr, stream);
 }
 
 extern "C" int eqh_egnn_edge_fwd_tc_ordered(const float* P, const float* Q, const float* wc, const float* W2, const float* b2,
                                             const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
                                             float* Mi, const int32_t* order, eqh_stream_t stream) {
-  return edge_fwd_tc_impl(P, Q, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, order, stream);
+  return edge_fwd_tc_impl(P, Q, H, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, EQH_M_DIM, order, stream);
+}
+
+// Strided variant: P / Q are column blocks of one [N, ldpq] matrix (the merged h.[W1a|W1b]^T GEMM) and m_i is written
+// into a column block of a wider row (the node MLP's input cat(LN(h), m_i), egnn_layer.py:360: row stride ldmi).
+extern "C" int eqh_egnn_edge_fwd_tc_ld(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                                       const float* b2, const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2,
+                                       float* Mij, float* Mi, int64_t ldmi, const int32_t* order, eqh_stream_t stream) {
+  return edge_fwd_tc_impl(P, Q, ldpq, wc, W2, b2, idx, d2, N, H, S2, Mij, Mi, ldmi, order, stream);
 }

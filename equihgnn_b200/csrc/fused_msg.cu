@@ -336,9 +336,8 @@ __global__ void __launch_bounds__(256, 2) k_fused_bwd_dgb(
 template <int V, bool RELU>
 __global__ void __launch_bounds__(256) k_rowln_fwd(const float* __restrict__ x, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float eps, int64_t rows,
-                                                    float* __restrict__ y) {
+                                                    float* __restrict__ y, int64_t ldx, int64_t ldy) {
   pdl_prologue();
-  constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(256) k_rowln_fwd(const float* __restrict__ x, 
   bt.load(beta, lane);
   for (int64_t r = warp; r < rows; r += nwarps) {
     Row<V> t;
-    t.load(x + r * C, lane);
+    t.load(x + r * ldx, lane);
     if (RELU) {
 #pragma unroll
       for (int i = 0; i < V; ++i) t.v[i] = fmaxf(t.v[i], 0.f);
@@ -356,14 +355,15 @@ __global__ void __launch_bounds__(256) k_rowln_fwd(const float* __restrict__ x, 
     ln_stats<V>(t, eps, mean, rstd);
 #pragma unroll
     for (int i = 0; i < V; ++i) t.v[i] = (t.v[i] - mean) * rstd * g.v[i] + bt.v[i];
-    t.store(y + r * C, lane);
+    t.store(y + r * ldy, lane);
   }
 }
 
 template <int V, bool RELU>
 __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, const float* __restrict__ gamma, float eps,
                                                     const float* __restrict__ dy, int64_t rows, float* __restrict__ dx,
-                                                    float* __restrict__ dgb_partial) {
+                                                    float* __restrict__ dgb_partial, int64_t ldx, int64_t lddy, int64_t lddx,
+                                                    const float* __restrict__ add) {
   pdl_prologue();
   constexpr int C = 32 * V;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, 
   db.zero();
   for (int64_t r = warp; r < rows; r += nwarps) {
     Row<V> pre, t, gy;
-    pre.load(x + r * C, lane);
-    gy.load(dy + r * C, lane);
+    pre.load(x + r * ldx, lane);
+    gy.load(dy + r * lddy, lane);
 #pragma unroll
     for (int i = 0; i < V; ++i) t.v[i] = RELU ? fmaxf(pre.v[i], 0.f) : pre.v[i];
     float mean, rstd;
@@ -401,7 +401,13 @@ __global__ void __launch_bounds__(256) k_rowln_bwd(const float* __restrict__ x, 
       const float dt = rstd * (dxh.v[i] - s1 - xh.v[i] * s2);
       o.v[i] = (!RELU || pre.v[i] > 0.f) ? dt : 0.f;
     }
-    o.store(dx + r * C, lane);
+    if (add) {                       // dx = add + LayerNorm backward (a gradient that reaches x on a second path)
+      Row<V> a;
+      a.load_plain(add + r * lddx, lane);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.v[i] += a.v[i];
+    }
+    o.store(dx + r * lddx, lane);
   }
   __shared__ __align__(16) float sm[8][2 * C];
   dg.store(&sm[wib][0], lane);
@@ -558,31 +564,44 @@ int eqh_fused_msg_bwd(const float* A, const float* B, const int32_t* ia, const i
 
 int eqh_rowln_fwd(const float* x, const float* gamma, const float* beta, float eps, int relu, int64_t rows, int64_t C,
                   float* y, eqh_stream_t stream) {
+  return eqh_rowln_fwd_ld(x, C, gamma, beta, eps, relu, rows, C, y, C, stream);
+}
+
+int eqh_rowln_fwd_ld(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int relu, int64_t rows,
+                     int64_t C, float* y, int64_t ldy, eqh_stream_t stream) {
   using namespace eqh;
   EQH_CHECK_ARG(rows >= 0 && gamma && beta && (rows == 0 || (x && y)));
   EQH_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta));
+  EQH_CHECK_ARG(ldx >= C && ldy >= C && ldx % 4 == 0 && ldy % 4 == 0);
   if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
   if (rows == 0) return EQH_OK;
   int64_t blocks = (rows + 7) / 8;
   if (blocks > (int64_t)kSMs * 16) blocks = (int64_t)kSMs * 16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EQH_DISPATCH_V(C, {
-    if (relu) launch_kernel(k_rowln_fwd<V, true>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y);
-    else launch_kernel(k_rowln_fwd<V, false>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y);
+    if (relu) launch_kernel(k_rowln_fwd<V, true>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y, ldx, ldy);
+    else launch_kernel(k_rowln_fwd<V, false>, dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, beta, eps, rows, y, ldx, ldy);
   });
   EQH_LAUNCH_RC();
 }
 
 int eqh_rowln_bwd(const float* x, const float* gamma, float eps, int relu, const float* dy, int64_t rows, int64_t C,
                   float* dx, float* dgb_partial, eqh_stream_t stream) {
+  return eqh_rowln_bwd_ld(x, C, gamma, eps, relu, dy, C, rows, C, dx, C, nullptr, dgb_partial, stream);
+}
+
+int eqh_rowln_bwd_ld(const float* x, int64_t ldx, const float* gamma, float eps, int relu, const float* dy, int64_t lddy,
+                     int64_t rows, int64_t C, float* dx, int64_t lddx, const float* add, float* dgb_partial,
+                     eqh_stream_t stream) {
   using namespace eqh;
   EQH_CHECK_ARG(rows >= 0 && gamma && dgb_partial && (rows == 0 || (x && dy && dx)));
-  EQH_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) && aligned16(dgb_partial));
+  EQH_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) && aligned16(dgb_partial) && aligned16(add));
+  EQH_CHECK_ARG(ldx >= C && lddy >= C && lddx >= C && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0);
   if (!supported_C(C)) return EQH_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EQH_DISPATCH_V(C, {
-    if (relu) launch_kernel(k_rowln_bwd<V, true>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial);
-    else launch_kernel(k_rowln_bwd<V, false>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial);
+    if (relu) launch_kernel(k_rowln_bwd<V, true>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial, ldx, lddy, lddx, add);
+    else launch_kernel(k_rowln_bwd<V, false>, dim3(kPartialRows), dim3(256), 0, st, x, gamma, eps, dy, rows, dx, dgb_partial, ldx, lddy, lddx, add);
   });
   EQH_LAUNCH_RC();
 }

@@ -56,6 +56,12 @@ struct Params {
   int M, N, K;
   int act;            // 0 none, 1 relu, 2 silu
   int kb_per_split;   // K blocks of 32 per split
+  // optional epilogue extras (no split-K): `stash` [M, ldd] receives the pre-activation A.B^T + bias (what the backward of
+  // SiLU needs, so act = silu costs no separate elementwise launch); `dsilu_aux` [M, ld_aux]: the result is multiplied by
+  // SiLU'(dsilu_aux[m, n]) before the residual is added (the backward of SiLU fused into the dgrad GEMM).
+  float* stash;
+  const float* dsilu_aux;
+  int64_t ld_aux;
 };
 
 
@@ -125,6 +131,18 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
         const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);   // warp-uniform address: broadcast
         v[j] += b4.x * rs; v[j + 1] += b4.y * rs; v[j + 2] += b4.z * rs; v[j + 3] += b4.w * rs;
       }
+      if (final_out && p.stash != nullptr && m0 + row < p.M) {
+        // pre-activation stash: each thread owns 32 consecutive columns of its row (a full 128-byte line per thread)
+        float* sp = p.stash + (int64_t)(m0 + row) * p.ldd + n0 + c0;
+        if ((p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.stash) & 15) == 0) && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(sp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) sp[j] = v[j];
+        }
+      }
       if (act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -147,6 +165,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
     const int64_t ld = final_out ? p.ldd : p.N;
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool has_res = final_out && p.residual != nullptr;
+    const bool has_aux = final_out && p.dsilu_aux != nullptr;
     // a warp instruction covers 128 / BN rows of the tile as float4s; four such groups in flight per warp
     constexpr int LPR = BN / 4;                          // lanes per row
     constexpr int RPI = 32 / LPR;                        // rows per warp instruction
@@ -164,6 +183,13 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
             x[u] = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
             // plain (coherent) load: the residual may be D itself
             if (has_res) rr[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n);
+            if (has_aux) {
+              const float* ap = p.dsilu_aux + (int64_t)(m0 + r) * p.ld_aux + n;
+              float4 a4;
+              if ((p.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dsilu_aux) & 15) == 0)) a4 = __ldg(reinterpret_cast<const float4*>(ap));
+              else a4 = make_float4(__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3));
+              x[u].x *= dsilu_f(a4.x); x[u].y *= dsilu_f(a4.y); x[u].z *= dsilu_f(a4.z); x[u].w *= dsilu_f(a4.w);
+            }
           }
         }
 #pragma unroll
@@ -188,6 +214,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
           for (int j = 0; j < 4; ++j) {
             if (n + j < p.N) {
               float x = src[j];
+              if (has_aux) x *= dsilu_f(__ldg(p.dsilu_aux + (int64_t)(m0 + r) * p.ld_aux + n + j));
               if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
               dst[j] = x;
             }

@@ -11,7 +11,7 @@ template <int V, bool WEIGHTED>
 __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__ table, const int32_t* __restrict__ idx,
                                                         const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ src_rowptr, int64_t n_out, int mode,
-                                                        float* __restrict__ out, int64_t ld) {
+                                                        float* __restrict__ out, int64_t ld, int64_t ld_out) {
   pdl_prologue();
   table += (int64_t)blockIdx.y * (32 * V);  // column block of a wider row (row stride ld)
   out += (int64_t)blockIdx.y * (32 * V);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < V; ++i) acc.v[i] = acc.v[i] / cnt;  // true division, as torch_scatter's true_divide_
     }
-    acc.store(out + s * ld, lane);
+    acc.store(out + s * ld_out, lane);
   }
 }
 
@@ -112,7 +112,14 @@ extern "C" {
 
 int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* rowptr, const int32_t* src_rowptr,
                       int64_t n_out, int64_t C, int mode, float* out, eqh_stream_t stream) {
+  return eqh_gather_reduce_ld(table, C, idx, rowptr, src_rowptr, n_out, C, mode, out, C, stream);
+}
+
+int eqh_gather_reduce_ld(const float* table, int64_t ld_table, const int32_t* idx, const int32_t* rowptr,
+                         const int32_t* src_rowptr, int64_t n_out, int64_t C, int mode, float* out, int64_t ld_out,
+                         eqh_stream_t stream) {
   using namespace eqh;
+  EQH_CHECK_ARG(ld_table >= C && ld_out >= C && ld_table % 4 == 0 && ld_out % 4 == 0);
   EQH_CHECK_ARG(n_out >= 0 && rowptr && (n_out == 0 || out));  // table may be NULL when every segment is empty
   EQH_CHECK_ARG(mode == EQH_REDUCE_SUM || mode == EQH_REDUCE_MEAN);
   EQH_CHECK_ARG(aligned16(table) && aligned16(out));
@@ -123,9 +130,9 @@ int eqh_gather_reduce(const float* table, const int32_t* idx, const int32_t* row
   const dim3 grid(grid_for_warps(n_out, 256), (unsigned)(C / CB));
   EQH_DISPATCH_V(CB, {
     if (src_rowptr)
-      launch_kernel(k_gather_reduce<V, true>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, src_rowptr, n_out, mode, out, C);
+      launch_kernel(k_gather_reduce<V, true>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, src_rowptr, n_out, mode, out, ld_table, ld_out);
     else
-      launch_kernel(k_gather_reduce<V, false>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, nullptr, n_out, mode, out, C);
+      launch_kernel(k_gather_reduce<V, false>, dim3(grid), dim3(256), 0, st, table, idx, rowptr, nullptr, n_out, mode, out, ld_table, ld_out);
   });
   EQH_LAUNCH_RC();
 }

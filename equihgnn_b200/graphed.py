@@ -22,7 +22,7 @@ result depends on every row: MHNNM evaluates it with the ghost rows masked out o
 from __future__ import annotations
 
 import os
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -85,20 +85,53 @@ class _Bucket:
         self.static, self.graph, self.loss, self.launches = static, graph, loss, launches
 
 
-class GraphedTrainer(Trainer):
-    """Trainer whose forward+loss+backward is one CUDA-graph replay per step.
+def common_bucket(batches, gran: Tuple[int, int, int] = (256, 256, 512), process_group=None) -> Tuple[int, int, int]:
+    """One bucket that fits every batch of `batches` -- and, in a distributed run, every batch of every rank (element-wise
+    MAX all-reduce).  Padding all batches to it makes every rank replay a graph of the same shape at every step: no rank
+    waits for a peer that drew a larger bucket, and the in-graph gradient exchange is legal (see GraphedTrainer)."""
+    import torch.distributed as dist
+    dims = [max(bucket_of(b, gran)[k] for b in batches) for k in range(3)]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dev = "cuda" if dist.get_backend(process_group) == "nccl" else "cpu"
+        t = torch.tensor(dims, dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=process_group)
+        dims = [int(v) for v in t.tolist()]
+    return tuple(dims)
 
-    step(padded_device_batch) / step_from_host(padded_pinned_batch, device): the batch must have
-    been padded with `pad_batch(batch, bucket_of(batch))` (host side, part of collation).
+
+class GraphedTrainer(Trainer):
+    """Trainer whose step is one CUDA-graph replay.
+
+    step(padded_device_batch) / step_from_host(padded_pinned_batch, device): the batch must have been padded with
+    `pad_batch(batch, bucket)` (host side, part of collation).
+
+    in_graph_step (default: on whenever it is legal) puts the WHOLE step into the captured graph -- zeroing the flat
+    gradient buffer, forward, loss, backward, the bucketed gradient all-reduce (NCCL calls captured on a forked stream, the
+    conv + readout bucket under the EGNN backward: Trainer.fused_step) and the fused Adam with a device-side step counter.
+    Per step the host then only copies the inputs into the static buffers and replays.  With more than one rank this needs
+    `uniform_shapes=True`: the caller guarantees that all ranks see the same sequence of batch shapes (pad to
+    `common_bucket`), because a rank that captures a new bucket (three eager warm-up steps, then the capture) while its
+    peers replay an old one would issue a different number of collectives.  Otherwise the graph holds forward + loss +
+    backward and the exchange + Adam follow outside, as in round 1.
     """
 
-    def __init__(self, model, real_graphs: int, **kw):
+    def __init__(self, model, real_graphs: int, in_graph_step: Optional[bool] = None, uniform_shapes: bool = False, **kw):
         super().__init__(model, **kw)
         self.B = real_graphs
         self.buckets: Dict[Tuple[int, int, int, int], _Bucket] = {}
         self._pool = None
         self.replays = 0
         self.own_launches = 0
+        legal = (not self.distributed) or uniform_shapes
+        if in_graph_step is None:
+            in_graph_step = legal and os.environ.get("EQH_INGRAPH_STEP", "1") != "0"
+        if in_graph_step and not legal:
+            raise ValueError("in_graph_step with several ranks needs uniform_shapes=True (see the class docstring)")
+        self.in_graph_step = bool(in_graph_step)
+        # loss read-back ring of step_from_host(sync=False): the loss of step k is read while step k+1 is in flight
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory() if self.fp.flat.is_cuda else torch.zeros(2)
+        self._loss_evt = [None, None]
+        self._issued = 0
 
     def _fwd_bwd(self, data) -> torch.Tensor:
         self.fp.zero_grad()
@@ -107,19 +140,26 @@ class GraphedTrainer(Trainer):
         ops.side_work.join()        # the side-stream branch rejoins before the capture ends
         return loss.detach()
 
+    def _body(self, data) -> torch.Tensor:
+        return self.fused_step(data, self.B) if self.in_graph_step else self._fwd_bwd(data)
+
     def _capture(self, like: HBatch) -> _Bucket:
         dev = self.fp.flat.device
+        self._check_binding()
         # static inputs: one contiguous buffer with every field a view into it (HBatch.pack), so a packed batch of the
         # same shapes arrives with a single copy
         static = like.pack(device=dev)
-        # warm-up on a side stream (cuBLAS workspaces, autograd buffers), then capture.  The warm-up steps must leave
-        # no trace: module buffers (BatchNorm running statistics of mhnnm) are restored afterwards.
+        # warm-up on a side stream (NCCL / autograd buffers), then capture.  The warm-up steps must leave no trace: module
+        # buffers (BatchNorm running statistics of mhnnm) and -- when the optimizer is part of the body -- parameters,
+        # Adam moments and the step counter are restored afterwards.
         buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
+        if self.in_graph_step:
+            buffers += [(t, t.detach().clone()) for t in (self.fp.flat, self.exp_avg, self.exp_avg_sq, self.step_dev)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
-                self._fwd_bwd(static)
+                self._body(static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -141,8 +181,11 @@ class GraphedTrainer(Trainer):
         prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "0"))
         if prio != 0:
             kw["stream"] = torch.cuda.Stream(priority=prio)
+        if self.distributed and self.in_graph_step:
+            kw["capture_error_mode"] = "thread_local"      # NCCL's own threads may touch the CUDA API during the capture
         with torch.cuda.graph(g, **kw):
-            loss = self._fwd_bwd(static)
+            loss = self._body(static)
+        torch.cuda.synchronize()
         return _Bucket(static, g, loss, ops.STATS["launches"] - before)
 
     def _bucket(self, data: HBatch) -> _Bucket:
@@ -152,7 +195,7 @@ class GraphedTrainer(Trainer):
             bk = self.buckets[key] = self._capture(data)
         return bk
 
-    def forward_backward(self, data: HBatch) -> torch.Tensor:
+    def _replay(self, data: HBatch) -> _Bucket:
         bk = self._bucket(data)
         flat = getattr(data, "_flat", None)
         if flat is not None and flat.numel() == bk.static._flat.numel():
@@ -163,10 +206,54 @@ class GraphedTrainer(Trainer):
         bk.graph.replay()
         self.replays += 1
         self.own_launches += bk.launches
-        return bk.loss
+        if self.in_graph_step:
+            self.t += 1
+        return bk
 
-    def step_from_host(self, host_batch: HBatch, device=None) -> float:
-        loss = self.forward_backward(host_batch)           # H2D straight into the graph's static inputs
+    def forward_backward(self, data: HBatch) -> torch.Tensor:
+        """Replay on `data`.  NOTE: with in_graph_step the replay is the whole step (optimizer included).  The returned
+        tensor is a copy: the graph's own loss tensor is overwritten by the next replay of that bucket."""
+        return self._replay(data).loss.clone()
+
+    def step(self, data: HBatch) -> torch.Tensor:
+        if self.in_graph_step:
+            return self._replay(data).loss.clone()
+        loss = self.forward_backward(data)
         self.sync_gradients()
         self.optimizer_step()
-        return float(loss.item())
+        return loss
+
+    # -- host-facing step ------------------------------------------------------------------------
+    def _finish_outside(self):
+        if not self.in_graph_step:
+            self.sync_gradients()
+            self.optimizer_step()
+
+    def _queue_loss(self, loss: torch.Tensor) -> None:
+        k = self._issued % 2
+        self._loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
+        if self._loss_evt[k] is None:
+            self._loss_evt[k] = torch.cuda.Event()
+        self._loss_evt[k].record()
+        self._issued += 1
+
+    def _read_loss(self, back: int) -> Optional[float]:
+        """Loss of the step issued `back` steps ago (1 = the latest), waiting for exactly that step."""
+        if self._issued < back:
+            return None
+        k = (self._issued - back) % 2
+        self._loss_evt[k].synchronize()
+        return float(self._loss_host[k])
+
+    def step_from_host(self, host_batch: HBatch, device=None, sync: bool = True) -> Optional[float]:
+        """Pinned host batch in (H2D straight into the graph's static inputs), replay, loss out (D2H into pinned memory).
+        sync=True returns this step's loss (the host waits for the step).  sync=False returns the PREVIOUS step's loss
+        (None on the first call): the host reads loss k-1 after it has queued step k, so the GPU never waits for the host
+        between steps; `flush_loss()` returns the last one."""
+        bk = self._replay(host_batch)
+        self._finish_outside()
+        self._queue_loss(bk.loss)
+        return self._read_loss(1) if sync else self._read_loss(2)
+
+    def flush_loss(self) -> Optional[float]:
+        return self._read_loss(1)

@@ -113,7 +113,9 @@ class EGNN(nn.Module):
             H0 = self.edge_mlp[0].weight.shape[0]
             Hp = _round_up(H0, 64)
             z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
-            self._packed = {"W1a": z(Hp, C), "W1b": z(Hp, C), "wc": z(Hp), "b1": z(Hp), "W2": z(ops.M_DIM, Hp)}
+            W1ab, b1ab = z(2 * Hp, C), z(2 * Hp)        # [W1a ; W1b] as ONE matrix: P | Q is a single GEMM (b1 | 0)
+            self._packed = {"W1ab": W1ab, "b1ab": b1ab, "W1a": W1ab[:Hp], "W1b": W1ab[Hp:], "wc": z(Hp), "b1": b1ab[:Hp],
+                            "W2": z(ops.M_DIM, Hp)}
         return self._packed
 
     def init_(self, module):

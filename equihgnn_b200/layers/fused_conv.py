@@ -104,12 +104,16 @@ class MHNNSConvFused(torch.autograd.Function):
         X0 = ops._f32(X0, "MHNNSConv X0")
         N, C = X.shape
         mode = _MODES[aggr]
+        # A = X . W2a^T needs only X: a parallel branch of the captured graph next to the W1 -> V2E -> W2b chain
+        A = torch.empty((N, C), dtype=torch.float32, device=X.device)
+        with ops.branch_work.fork(X.device, keep=(X, A)):
+            gemm_raw(X, True, w20[:, :C], True, N, C, C, out=A)
         h1 = gemm_raw(X, True, w10, True, N, C, C, bias=b10)
         y1 = _rowln_fwd(h1, g1, t1, eps[0])
         Y = gemm_raw(y1, True, w11, True, N, C, C, bias=b11)
         Xe = gather_reduce_raw(Y, inc.vtx_by_e, inc.rowptr_e, None, inc.E, mode)                    # conv.py:172-173
-        A = gemm_raw(X, True, w20[:, :C], True, N, C, C)
         Bm = gemm_raw(Xe, True, w20[:, C:], True, inc.E, C, C, bias=b20)
+        ops.branch_work.join(X.device)
         U = torch.empty((N, C), dtype=torch.float32, device=X.device)
         _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
               mode, _p(U), _stream(), nbytes=4.0 * C * (2 * N + inc.E) + 4.0 * (inc.Z + N + 1))      # conv.py:175-177
@@ -164,7 +168,10 @@ class MHNNSConvFused(torch.autograd.Function):
               _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream(),
               nbytes=4.0 * C * (2 * N + 2 * E) + 4.0 * (2 * inc.Z + E + 1))
         sink.affine(g2, t2, part)
-        dX = gemm_raw(dA, True, w20[:, :C], False, N, C, C)
+        # dX = dA . W2a is needed only by the last GEMM of this backward: a parallel branch next to dXe -> dY -> dh1
+        dX = torch.empty((N, C), dtype=torch.float32, device=X.device)
+        with ops.branch_work.fork(X.device, keep=(dA, dX)):
+            gemm_raw(dA, True, w20[:, :C], False, N, C, C, out=dX)
         dXe = gemm_raw(dBm, True, w20[:, C:], False, E, C, C)
         sink.weight(w20, dA, X, cols=slice(0, C))
         sink.weight(w20, dBm, Xe, cols=slice(C, 2 * C))
@@ -176,6 +183,7 @@ class MHNNSConvFused(torch.autograd.Function):
         sink.bias(b11, dY)
         dh1, part = _rowln_bwd(h1, g1, eps[0], dy1)
         sink.affine(g1, t1, part)
+        ops.branch_work.join(X.device)
         gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX)          # dX += dh1 . W1_0 (in-place epilogue)
         sink.weight(w10, dh1, X)
         sink.bias(b10, dh1)

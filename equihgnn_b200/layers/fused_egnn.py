@@ -18,7 +18,9 @@ from .fused_conv import _GradSink, _rowln_bwd
 
 
 def pack_phi_e(bufs, w1, b1, w2, C: int) -> None:
-    """Refresh the packed, zero-padded copies of phi_e's weights (TMA needs 16-byte row strides; 2C+1 floats is not)."""
+    """Refresh the packed, zero-padded copies of phi_e's weights (TMA needs 16-byte row strides; 2C+1 floats is not).
+    W1a and W1b are the two halves of ONE [2 Hp, C] matrix, so that P | Q, their gradient w.r.t. h and the weight
+    gradient are one GEMM each."""
     H0, Hp = w1.shape[0], bufs["W1a"].shape[0]
     _call("eqh_egnn_pack", 1, _p(ops._f32(w1, "edge_mlp.0.weight")), _p(ops._f32(b1, "edge_mlp.0.bias")),
           _p(ops._f32(w2, "edge_mlp.3.weight")), H0, C, Hp, _p(bufs["W1a"]), _p(bufs["W1b"]), _p(bufs["wc"]), _p(bufs["b1"]),
@@ -26,85 +28,96 @@ def pack_phi_e(bufs, w1, b1, w2, C: int) -> None:
 
 
 class EGNNFused(torch.autograd.Function):
-    """(h [N,C]) -> node_mlp(cat(LN(h), sum_j phi_e(h_i, h_j, d2_ij))) + h"""
+    """(h [N,C]) -> node_mlp(cat(LN(h), sum_j phi_e(h_i, h_j, d2_ij))) + h
+
+    Forward: 3 GEMMs (P | Q merged; node MLP layer 1 with the SiLU and its pre-activation stash in the epilogue; layer 2
+    with the residual), one row LayerNorm writing straight into the node MLP's input, the edge kernel writing m_i next to
+    it.  Backward: 3 dgrad GEMMs (SiLU' in the epilogue of the first, dP | dQ -> dh merged and added to the LayerNorm /
+    residual gradient in the last), the edge kernel, the dQ reduction, 3 weight-gradient GEMMs on the side branch.  No
+    ATen kernel in between (the reference's graph: egnn_layer.py:298-310,357-362)."""
 
     @staticmethod
     def forward(ctx, h, graph, bufs, eps, w1, b1, w2, b2, g, t, w5, b5, w6, b6):
         h = ops._f32(h, "EGNN feats")
         N, C = h.shape
-        H0 = w1.shape[0]
         Hp = bufs["W1a"].shape[0]
-        # the packed copies of phi_e's weights were refreshed by the caller (pack_phi_e, possibly on a parallel branch)
-        W1a, W1b, wc, b1p, W2p = bufs["W1a"], bufs["W1b"], bufs["wc"], bufs["b1"], bufs["W2"]
-        P = gemm_raw(h, True, W1a, True, N, Hp, C, bias=b1p)
-        Q = gemm_raw(h, True, W1b, True, N, Hp, C)
         dev = h.device
+        # the packed copies of phi_e's weights were refreshed by the caller (pack_phi_e, possibly on a parallel branch)
+        W1ab, b1ab, wc, W2p = bufs["W1ab"], bufs["b1ab"], bufs["wc"], bufs["W2"]
+        PQ = gemm_raw(h, True, W1ab, True, N, 2 * Hp, C, bias=b1ab)                  # P = PQ[:, :Hp], Q = PQ[:, Hp:]
         S2 = torch.empty((N * KNN_K, M_DIM), dtype=torch.float32, device=dev)
-        Mi = torch.empty((N, M_DIM), dtype=torch.float32, device=dev)
+        ldn = C + M_DIM
+        node_in = torch.empty((N, ldn), dtype=torch.float32, device=dev)             # cat(LN(h), m_i): egnn_layer.py:360
+        _call("eqh_rowln_fwd_ld", 1, _p(h), C, _p(g), _p(t), eps, 0, N, C, _p(node_in), ldn, _stream())
         ops.prep_work_b.join(dev)                        # the kNN graph may have been built on a parallel branch
-        _call("eqh_egnn_edge_fwd_tc_ordered", 1, _p(P), _p(Q), _p(wc), _p(W2p), _p(b2), _p(graph.idx), _p(graph.d2), N, Hp,
-              _p(S2), None, _p(Mi), _p(graph.order), _stream(), nbytes=2.0 * N * KNN_K * Hp * M_DIM)
-        hn = torch.empty_like(h)
-        _call("eqh_rowln_fwd", 1, _p(h), _p(g), _p(t), eps, 0, N, C, _p(hn), _stream())
-        node_in = torch.cat((hn, Mi), dim=-1)                                        # egnn_layer.py:360
-        t_pre = gemm_raw(node_in, True, w5, True, N, 2 * C, C + M_DIM, bias=b5)
-        tt = torch.nn.functional.silu(t_pre)
+        _call("eqh_egnn_edge_fwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2p), _p(b2), _p(graph.idx),
+              _p(graph.d2), N, Hp, _p(S2), None, node_in.data_ptr() + 4 * C, ldn, _p(graph.order), _stream(),
+              nbytes=2.0 * N * KNN_K * Hp * M_DIM)
+        t_pre = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
+        tt = gemm_raw(node_in, True, w5, True, N, 2 * C, ldn, bias=b5, act="silu", stash=t_pre)
         out = gemm_raw(tt, True, w6, True, N, C, 2 * C, bias=b6, residual=h)         # egnn_layer.py:361-362
-        ctx.save_for_backward(h, P, Q, S2, node_in, t_pre, tt, w1, b1, w2, b2, g, t, w5, b5, w6, b6)
+        ctx.save_for_backward(h, PQ, S2, node_in, t_pre, tt, w1, b1, w2, b2, g, t, w5, b5, w6, b6)
         ctx.graph, ctx.bufs, ctx.eps = graph, bufs, eps
         return out
 
     @staticmethod
     def backward(ctx, dOut):
-        h, P, Q, S2, node_in, t_pre, tt, w1, b1, w2, b2, g, t, w5, b5, w6, b6 = ctx.saved_tensors
+        h, PQ, S2, node_in, t_pre, tt, w1, b1, w2, b2, g, t, w5, b5, w6, b6 = ctx.saved_tensors
         graph, bufs, eps = ctx.graph, ctx.bufs, ctx.eps
-        W1a, W1b, wc, W2p = bufs["W1a"], bufs["W1b"], bufs["wc"], bufs["W2"]
+        W1ab, wc, W2p = bufs["W1ab"], bufs["wc"], bufs["W2"]
         dOut = ops._f32(dOut, "EGNN grad")
         N, C = h.shape
-        H0, Hp = w1.shape[0], W1a.shape[0]
+        H0, Hp = w1.shape[0], bufs["W1a"].shape[0]
+        ldn = C + M_DIM
         dev = h.device
         sink = _GradSink((w1, b1, w2, b2, g, t, w5, b5, w6, b6), True)
-        # ---- node update
-        dt = gemm_raw(dOut, True, w6, False, N, 2 * C, C)
+        # ---- node update: dt_pre = (dOut . W6) * SiLU'(t_pre) in the GEMM epilogue
+        dt_pre = gemm_raw(dOut, True, w6, False, N, 2 * C, C, dsilu_aux=t_pre)
         sink.weight(w6, dOut, tt)
         sink.bias(b6, dOut)
-        dt_pre = torch.ops.aten.silu_backward(dt, t_pre)
-        dni = gemm_raw(dt_pre, True, w5, False, N, C + M_DIM, 2 * C)
+        dni = gemm_raw(dt_pre, True, w5, False, N, ldn, 2 * C)                       # [d LN(h) | d m_i]
         sink.weight(w5, dt_pre, node_in)
         sink.bias(b5, dt_pre)
-        dhn = dni[:, :C].contiguous()
-        dMi = dni[:, C:].contiguous()
-        dh_ln, part_ln = _rowln_bwd(h, g, eps, dhn, relu=0)
+        # dh0 = dOut (residual) + LayerNorm backward of dni[:, :C]
+        dh0 = torch.empty_like(h)
+        part_ln = torch.empty((ops.partial_rows(), 2 * C), dtype=torch.float32, device=dev)
+        _call("eqh_rowln_bwd_ld", 1, _p(h), C, _p(g), eps, 0, _p(dni), ldn, N, C, _p(dh0), C, _p(dOut), _p(part_ln),
+              _stream())
         sink.affine(g, t, part_ln)
         sink.flush()                                # bias / LayerNorm-affine column sums: every input exists already
         # ---- phi_e
         if graph.rowptr_j is None:
             graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
         cols = (M_DIM + 1) * Hp + M_DIM
-        dP, dPre, _, part = ops.egnn_edge_bwd_raw(P, Q, wc, W2p, b2, graph, graph.d2, S2, dMi, None, False)
+        dPQ = torch.empty((N, 2 * Hp), dtype=torch.float32, device=dev)              # [dP | dQ]
+        dPre = torch.empty((N * KNN_K, Hp), dtype=torch.float32, device=dev)
+        rows = _lib_rows(Hp)
+        part = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        _call("eqh_egnn_edge_bwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2p), _p(graph.idx),
+              _p(graph.d2), _p(S2), dni.data_ptr() + 4 * C, ldn, N, Hp, _p(dPQ), 2 * Hp, _p(dPre), _p(part), _p(graph.order),
+              _stream(), nbytes=4.0 * N * KNN_K * Hp * M_DIM)
         # phi_e parameter gradients on the side stream (a parallel branch of the captured graph), forked as soon as their
-        # inputs exist -- this layer's backward is the tail of the step, nothing later can hide them: what needs only dP /
-        # the partial sums starts next to the dQ reduction, the dQ part next to the dh GEMMs.
-        gw1 = sink.out[id(w1)]
-        # into a 16-byte-aligned staging matrix (vector stores, vector split-K finish), then one add into the
-        # [H0, 2C+1] gradient whose odd row stride would force the scalar epilogue
-        tmp = torch.empty((H0, 2 * C), dtype=torch.float32, device=dev)
-        with ops.side_work.fork(dev, keep=(dP, h, part, tmp)):
-            gemm_raw(dP, False, h, False, H0, C, N, splits=0, out=tmp[:, :C])
-            red = torch.empty(cols, dtype=torch.float32, device=dev)
+        # inputs exist -- this layer's backward is the tail of the step, nothing later can hide them: the partial sums
+        # and db1 start next to the dQ reduction, the merged weight gradient [dP | dQ]^T . h next to the dh GEMM.
+        red = torch.empty(cols, dtype=torch.float32, device=dev)
+        with ops.side_work.fork(dev, keep=(dPQ, part, red)):
             batch = ops.ColsumBatch(dev)
             batch.add(part, red)
-            batch.add(dP, sink.out[id(b1)], accumulate=True, cols=H0)          # db1 = column sums of dP (= d pre)
+            batch.add(dPQ, sink.out[id(b1)], accumulate=True, cols=H0)          # db1 = column sums of dP (= d pre)
             batch.run()
-            sink.out[id(w2)].add_(red[:M_DIM * Hp].view(M_DIM, Hp)[:, :H0])
-            gw1[:, 2 * C].add_(red[M_DIM * Hp:M_DIM * Hp + H0])
-            sink.out[id(b2)].add_(red[(M_DIM + 1) * Hp:])
-        dQ = gather_reduce_raw(dPre, graph.perm_j, graph.rowptr_j, None, N, SUM)
-        with ops.side_work.fork(dev, keep=(dQ, h, tmp)):
-            gemm_raw(dQ, False, h, False, H0, C, N, splits=0, out=tmp[:, C:])
-            gw1[:, :2 * C].add_(tmp)
-        # dh = dOut (residual) + dP.W1a + dQ.W1b + LayerNorm backward
-        dh = gemm_raw(dP, True, W1a, False, N, C, Hp, residual=dOut)
-        gemm_raw(dQ, True, W1b, False, N, C, Hp, out=dh, residual=dh)
-        dh = dh + dh_ln
+        # dQ[j] = sum over the edges (i, k) with idx[i, k] == j, ascending edge order (deterministic)
+        _call("eqh_gather_reduce_ld", 1, _p(dPre), Hp, _p(graph.perm_j), _p(graph.rowptr_j), None, N, Hp, SUM,
+              dPQ.data_ptr() + 4 * Hp, 2 * Hp, _stream(), nbytes=4.0 * Hp * (N * KNN_K + N) + 4.0 * (N * KNN_K + N + 1))
+        T = torch.empty((2 * Hp, C), dtype=torch.float32, device=dev)
+        with ops.side_work.fork(dev, keep=(dPQ, h, T, red)):
+            gemm_raw(dPQ, False, h, False, 2 * Hp, C, N, splits=0, out=T)
+            _call("eqh_egnn_unpack_grads", 1, _p(T), _p(red), H0, C, Hp, _p(sink.out[id(w1)]), _p(sink.out[id(w2)]),
+                  _p(sink.out[id(b2)]), _stream())
+        # dh = dh0 + [dP | dQ] . [W1a ; W1b]   (K = 2 Hp: split-K chosen by the planner, residual added by its finish)
+        dh = gemm_raw(dPQ, True, W1ab, False, N, C, 2 * Hp, residual=dh0, splits=0)
         return (dh, None, None, None) + (None,) * 10
+
+
+def _lib_rows(Hp: int) -> int:
+    from .. import _lib
+    return _lib.load().eqh_egnn_edge_bwd_tc_rows(Hp)

@@ -248,6 +248,9 @@ class MHNNS(nn.Module):
 class EGNNEquiHNNS(nn.Module):
     """`--method egnn_equihnns` (equihnn_egnn.py:98-169)."""
 
+    # gradients of these sub-modules are complete once the backward reaches ops.grad_boundary (the EGNN output)
+    early_gradient_modules = ("conv", "mlp_out")
+
     def __init__(self, num_target, args):
         super().__init__()
         self.act = _ACTS[args.activation]()
@@ -290,6 +293,7 @@ class EGNNEquiHNNS(nn.Module):
         x = x.squeeze(0)
         ops.prep_work.join(data.x.device)
         ops.prep_work_b.join(data.x.device)
+        x = ops.grad_boundary(x)       # backward: conv / readout gradients are final here -> their bucket's exchange starts
         x0 = x
         for _ in range(self.nlayer):
             x = self.dropout(x)

@@ -375,7 +375,35 @@ side_work = _SideWork()
 # forward-time index / packing work that nothing on the critical path needs yet (incidence CSR next to the atom encoder
 # and the kNN search, the transposed kNN incidence next to the phi_e GEMMs): a second parallel branch of the captured graph
 prep_work = _SideWork()
+# independent GEMMs of a layer whose result the critical chain needs only later (X.W2a^T of MHNNSConv next to the W1 chain,
+# its dX next to the dXe -> dY -> dh1 chain): a third parallel branch
+branch_work = _SideWork()
 prep_work_b = _SideWork()     # second branch: the kNN search (needs only the coordinates) next to the atom encoder and the phi_e GEMMs
+
+
+# Gradient-bucket boundary (DDP overlaps its bucketed all-reduce with the backward, main.py:281): a model marks the point
+# of its forward below which no gradient of the modules listed in `model.early_gradient_modules` is produced any more
+# (egnn_equihnns: the EGNN output -- once its gradient exists, the conv and readout gradients are final).  In backward the
+# marker calls BOUNDARY_HOOK (set by the Trainer for the duration of its backward), which starts that bucket's
+# all-reduce + optimizer update on a forked stream, i.e. under the rest of the backward.
+BOUNDARY_HOOK = None
+
+
+class _GradBoundary(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        hook = BOUNDARY_HOOK
+        if hook is not None:
+            hook()
+        return g
+
+
+def grad_boundary(x: torch.Tensor) -> torch.Tensor:
+    return _GradBoundary.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else x
 
 
 class ColsumBatch:
@@ -620,11 +648,14 @@ def gemm_plan(M: int, N: int, K: int, splits: int = 1, flags: int = 0):
 
 def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
              splits: int = 1, write_hi: bool = False, rowscale=None, out: Optional[torch.Tensor] = None,
-             out_scale: float = 1.0, res_scale: float = 1.0, flags: Optional[int] = None) -> torch.Tensor:
+             out_scale: float = 1.0, res_scale: float = 1.0, flags: Optional[int] = None,
+             stash: Optional[torch.Tensor] = None, dsilu_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = out_scale * act(A.B^T + bias * rowscale) + res_scale * residual with A logical [M,K], B logical [N,K]; an
     operand flagged k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3).  `out` may be a row-strided
     view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation).
-    splits: 1 = no split-K, 0 = let the kernel's planner choose (weight gradients), >1 = at most that many."""
+    splits: 1 = no split-K, 0 = let the kernel's planner choose (weight gradients), >1 = at most that many.
+    stash: [M, N] tensor with D's row stride that receives the pre-activation (act = 'silu' keeps what its backward needs);
+    dsilu_aux: [M, >=N] tensor, the result is multiplied by SiLU'(dsilu_aux) before the residual (SiLU backward fused)."""
     dev = A.device
     D = torch.empty((M, N), dtype=torch.float32, device=dev) if out is None else out
     ldd = D.stride(0)
@@ -640,6 +671,15 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
             ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
             cnt = counters(tiles, dev)
     flops = 2.0 * M * N * K
+    if stash is not None or dsilu_aux is not None:
+        if splits != 1:
+            raise RuntimeError("gemm_raw: stash / dsilu_aux need splits == 1")
+        if stash is not None and stash.stride(0) != ldd:
+            raise RuntimeError("gemm_raw: stash must have the row stride of the output")
+        _call("eqh_gemm_tf32x3_ex", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
+              _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
+              _p(stash), _p(dsilu_aux), dsilu_aux.stride(0) if dsilu_aux is not None else 0, _stream(), nbytes=flops)
+        return D
     _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
           _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
           _stream(), nbytes=flops)

@@ -74,7 +74,17 @@ class FlatParams:
 
 
 class Trainer:
-    """fwd + loss + bwd + (all-reduce) + Adam for one of the model wrappers."""
+    """fwd + loss + bwd + (all-reduce) + Adam for one of the model wrappers.
+
+    Two ways to run a step:
+      * `step()`: forward_backward / sync_gradients / optimizer_step as separate host-driven pieces (one all-reduce of the
+        whole flat buffer after the backward, Adam with the step count as a host argument);
+      * `fused_step()`: everything as ONE stream-ordered sequence with no host decision in it, so that it can be captured
+        in a CUDA graph (graphed.GraphedTrainer): the step count lives in device memory (eqh_adam_step_dev) and the gradient
+        exchange is bucketed like DDP's (main.py:281): the bucket of the modules the model lists in `early_gradient_modules`
+        (egnn_equihnns: conv + readout, 15 % of the step before its end) is all-reduced and applied on a forked stream
+        under the remaining backward, the rest at the end.
+    """
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.0,
                  betas=(0.9, 0.999), eps: float = 1e-8, process_group: Optional[dist.ProcessGroup] = None,
@@ -96,6 +106,38 @@ class Trainer:
             distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.distributed = distributed
         self.world = dist.get_world_size(process_group) if distributed else 1
+        self.split = self._plan_buckets()
+        dev = self.fp.flat.device
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)      # t - 1 of the fused step (device-side counter)
+        self._comm = None
+        self._early_done = False
+        self.timing = {}                 # filled by bench.py: measured all-reduce time etc.
+
+    # -- gradient buckets -----------------------------------------------------------------------
+    def _plan_buckets(self) -> Optional[int]:
+        """Offset (in floats) that splits the flat buffers into [0, split) -- final only at the end of the backward -- and
+        [split, n): the parameters of `model.early_gradient_modules`, final at the model's ops.grad_boundary.  None when
+        the model declares no such modules or they are not a suffix of the parameter order (single bucket)."""
+        early = tuple(getattr(self.model, "early_gradient_modules", ()) or ())
+        if not early:
+            return None
+        ids = set()
+        for name in early:
+            sub = getattr(self.model, name, None)
+            if sub is None:
+                return None
+            ids.update(id(q) for q in sub.parameters())
+        flags = [id(q) in ids for q in self.fp.params]
+        if not any(flags) or all(flags):
+            return None
+        first = flags.index(True)
+        if not all(flags[first:]):
+            return None
+        return self.fp.offsets[first]
+
+    def bucket_ranges(self):
+        n = self.fp.numel
+        return [(0, n)] if self.split is None else [(0, self.split), (self.split, n)]
 
     def rebind_gradients(self) -> None:
         """Point every parameter's .grad back at its slice of the flat gradient buffer (after something re-bound it)."""
@@ -146,3 +188,47 @@ class Trainer:
         (H2D copy of the inputs, the step, D2H read of the loss)."""
         data = host_batch.to(device, non_blocking=True)
         return float(self.step(data).item())
+
+    # -- the fused, capturable step -------------------------------------------------------------
+    def _exchange_and_update(self, lo: int, hi: int, advance: bool) -> None:
+        """all-reduce(sum) of grad[lo:hi] over the ranks, then Adam on that slice with grad_scale = 1/world (DDP's mean)."""
+        g = self.fp.grad[lo:hi]
+        if self.distributed:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+        ops.adam_step_dev_(self.fp.flat[lo:hi], g, self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_dev, self.lr,
+                           self.betas, self.eps, self.wd, grad_scale=1.0 / self.world, advance=advance)
+
+    def _on_boundary(self) -> None:
+        """Called from the backward at the model's ops.grad_boundary: the early bucket is final (its weight-gradient work
+        sits on the side stream): exchange + update it on the communication stream, under the rest of the backward."""
+        if self.split is None or self._early_done:
+            return
+        dev = self.fp.flat.device
+        main = torch.cuda.current_stream(dev)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+        self._comm.wait_stream(main)
+        side = ops.side_work.streams.get(dev.index if dev.index is not None else torch.cuda.current_device())
+        if side is not None:
+            self._comm.wait_stream(side)
+        with torch.cuda.stream(self._comm):
+            self._exchange_and_update(self.split, self.fp.numel, advance=False)
+        self._early_done = True
+
+    def fused_step(self, data, n_loss: Optional[int] = None) -> torch.Tensor:
+        """zero grads, forward, loss, backward, bucketed gradient exchange, Adam: one stream-ordered sequence."""
+        self.fp.zero_grad()
+        self._early_done = False
+        ops.BOUNDARY_HOOK = self._on_boundary if (self.split is not None and self.fp.flat.is_cuda) else None
+        try:
+            loss = model_loss(self.model, data, data.y.view(-1).shape[0] if n_loss is None else n_loss)
+            loss.backward()
+        finally:
+            ops.BOUNDARY_HOOK = None
+        ops.side_work.join()
+        if self._early_done:
+            self._exchange_and_update(0, self.split, advance=True)
+            torch.cuda.current_stream(self.fp.flat.device).wait_stream(self._comm)
+        else:
+            self._exchange_and_update(0, self.fp.numel, advance=True)
+        return loss.detach()

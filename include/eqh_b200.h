@@ -354,6 +354,39 @@ EQH_API int eqh_adam_step(float* param, const float* grad, float* exp_avg, float
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   eqh_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Strided / fused-epilogue variants used by the hand-scheduled layer Functions (layers/fused_*.py), so that concat,
+ * slice, activation and residual-add launches of the reference's autograd graph (egnn_layer.py:357-362, mlp.py:94-96)
+ * never exist as separate kernels.  Row strides are in floats and must be multiples of 4.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_rowln_fwd_ld(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int relu, int64_t rows,
+                     int64_t C, float* y, int64_t ldy, eqh_stream_t stream);
+/* dx = (add ? add : 0) + LayerNorm/ReLU backward; add has the row stride of dx and may alias it */
+EQH_API int eqh_rowln_bwd_ld(const float* x, int64_t ldx, const float* gamma, float eps, int relu, const float* dy, int64_t lddy,
+                     int64_t rows, int64_t C, float* dx, int64_t lddx, const float* add, float* dgb_partial,
+                     eqh_stream_t stream);
+EQH_API int eqh_gather_reduce_ld(const float* table, int64_t ld_table, const int32_t* idx, const int32_t* rowptr,
+                         const int32_t* src_rowptr, int64_t n_out, int64_t C, int mode, float* out, int64_t ld_out,
+                         eqh_stream_t stream);
+EQH_API int eqh_egnn_edge_fwd_tc_ld(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                            const float* b2, const int32_t* idx, const float* d2, int64_t N, int64_t H, float* S2, float* Mij,
+                            float* Mi, int64_t ldmi, const int32_t* order, eqh_stream_t stream);
+EQH_API int eqh_egnn_edge_bwd_tc_ld(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                            const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi, int64_t N,
+                            int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
+                            eqh_stream_t stream);
+/* gradients of phi_e's packed weights back into the parameters' own layout, accumulating (inverse of eqh_egnn_pack):
+ * T [2 Hp, C] = [dP | dQ]^T . h, red = (dW2 [16, Hp] | dwc [Hp] | db2 [16]) */
+EQH_API int eqh_egnn_unpack_grads(const float* T, const float* red, int64_t H0, int64_t C, int64_t Hp, float* gW1, float* gW2,
+                          float* gb2, eqh_stream_t stream);
+/* eqh_gemm_tf32x3 with two optional epilogue extras (splits must be 1): stash [M, ldd] receives the pre-activation
+ * A.B^T + bias * rowscale (act = SiLU keeps what its backward needs); dsilu_aux [M, ld_aux]: the result is multiplied by
+ * SiLU'(dsilu_aux[m, n]) before the residual is added (SiLU backward fused into the dgrad GEMM). */
+EQH_API int eqh_gemm_tf32x3_ex(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                       int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
+                       const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                       float* stash, const float* dsilu_aux, int64_t ld_aux, eqh_stream_t stream);
+
 /* The same step with the step count t-1 held in DEVICE memory (int64), for an optimizer that lives inside a captured
  * CUDA graph: every block derives the bias corrections of step t = *step_dev + 1 in double precision; with advance != 0
  * the last block to finish stores t to *step_dev (counter: one zeroed int32, left zero).  An optimizer step split over

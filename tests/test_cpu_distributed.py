@@ -85,6 +85,37 @@ def _worker(rank, world, port, out_dir):
                     p.grad.add_(torch.randn(p.shape, generator=g) / world)
             t2.optimizer_step()
         assert torch.allclose(t2.fp.flat, tr.fp.flat, rtol=1e-5, atol=1e-7)
+        # ---- the bucketed exchange of the fused (CUDA-graph) step: the conv + readout parameters form the suffix of the
+        # flat buffers that is final at the model's grad_boundary; exchanging + updating that bucket first and the rest at
+        # the end must equal ONE all-reduce + ONE Adam over the whole buffer (device-side step counter: advance once)
+        lo_hi = tr.bucket_ranges()
+        assert len(lo_hi) == 2 and lo_hi[0][0] == 0 and lo_hi[0][1] == lo_hi[1][0] == tr.split and lo_hi[1][1] == tr.fp.numel
+        first_early = next(i for i, n in enumerate(names) if n.startswith(("conv.", "mlp_out.")))
+        assert tr.split == tr.fp.offsets[first_early] and tr.split % 32 == 0
+        assert all(n.startswith(("conv.", "mlp_out.")) for n in names[first_early:])
+
+        def adam_dev(param, grad, m, v, step_dev, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0,
+                     advance=True):
+            _adam_reference(param, grad, m, v, int(step_dev) + 1, lr, betas, eps, weight_decay, grad_scale)
+            if advance:
+                step_dev += 1
+        ops.adam_step_dev_ = adam_dev
+        tr.step_dev.fill_(tr.t)                       # continue from the two host-driven steps above
+        g = torch.Generator().manual_seed(777 + rank)
+        tr.fp.zero_grad()
+        for n, p in zip(names, tr.fp.params):
+            if not n.startswith("egnn_layer.coors_"):
+                p.grad.copy_(torch.randn(p.shape, generator=g))
+        want_flat, want_m, want_v = tr.fp.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone()
+        gsum = tr.fp.grad.clone()
+        dist.all_reduce(gsum)
+        _adam_reference(want_flat, gsum, want_m, want_v, tr.t + 1, tr.lr, tr.betas, tr.eps, 0.0, 1.0 / world)
+        tr._exchange_and_update(tr.split, tr.fp.numel, advance=False)      # what the boundary hook does under the backward
+        assert int(tr.step_dev) == tr.t
+        tr._exchange_and_update(0, tr.split, advance=True)                  # the tail of the step
+        assert int(tr.step_dev) == tr.t + 1
+        assert torch.equal(tr.fp.grad, gsum)
+        assert torch.equal(tr.fp.flat, want_flat) and torch.equal(tr.exp_avg, want_m) and torch.equal(tr.exp_avg_sq, want_v)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -116,4 +147,6 @@ def test_bench_reference_arm_under_torchrun_prints_one_line(tmp_path):
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["warmup"] == 1 and d["steps"] == 1
+    assert d["config"]["workload"].startswith("egnn_equihnns qm9-shaped batch 128/GPU, C=32")

@@ -534,3 +534,100 @@ def test_headline_shape_matches_the_verbatim_reference():
     bad2 = {k: v for k, v in errs2.items() if v[0] > max(2e-5, 4 * v[1])}
     assert not bad2, bad2
     tr.close()
+
+
+def test_in_graph_step_matches_host_driven_step():
+    """The whole step inside the captured graph (zero-grad, fwd, bwd, bucketed exchange, Adam with a device-side step
+    counter; conv + readout bucket updated on a forked stream under the EGNN backward) == graph(fwd+bwd) followed by the
+    host-driven exchange + Adam: same losses and bit-identical parameters / moments after several steps; and the loss
+    read one step late (sync=False) is the loss of the previous step."""
+    from equihgnn_b200.graphed import GraphedTrainer, common_bucket, pad_batch
+    C, B = 64, 24
+    batches = [synthetic.make_batch("qm9", B, 500 + i) for i in range(3)]
+    bucket = common_bucket(batches, (64, 64, 128))
+    host = [pad_batch(b, bucket).pack(pin=True) for b in batches]
+    args = synthetic.model_args(hidden=C)
+
+    def fresh():
+        torch.manual_seed(21)
+        m = EGNNEquiHNNS(1, args)
+        with torch.no_grad():
+            for k, p_ in m.named_parameters():
+                if k.startswith("egnn_layer") and k.endswith("weight") and p_.dim() == 2:
+                    p_.normal_(0, 0.05)
+        return m.to(DEV).train()
+
+    a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=True)
+    b = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=False)
+    assert a.in_graph_step and not b.in_graph_step and a.split is not None
+    la, lb = [], []
+    for step in range(5):
+        la.append(a.step_from_host(host[step % 3], DEV, sync=False))
+        lb.append(b.step_from_host(host[step % 3], DEV))
+    la.append(a.flush_loss())
+    assert la[0] is None and la[1:] == lb, (la, lb)
+    torch.cuda.synchronize()
+    assert a.t == b.t == 5 and int(a.step_dev) == 5
+    assert len(a.buckets) == 1                               # one common bucket: one captured graph
+    assert torch.equal(a.fp.flat, b.fp.flat) and torch.equal(a.exp_avg, b.exp_avg) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+    # the returned device loss of step() is a copy, not the graph's static tensor (ADVICE r1)
+    l1 = a.step(host[0].pack(device=DEV))
+    v1 = float(l1)
+    a.step(host[1].pack(device=DEV))
+    assert float(l1) == v1
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from equihgnn_b200.graphed import GraphedTrainer, common_bucket, pad_batch
+        C, B = 64, 24
+        batches = [synthetic.make_batch("qm9", B, 800 + 10 * rank + i) for i in range(3)]      # per-rank data
+        bucket = common_bucket(batches, (64, 64, 128))                                         # MAX over ranks
+        host = [pad_batch(b, bucket).pack(pin=True) for b in batches]
+        args = synthetic.model_args(hidden=C)
+
+        def fresh():
+            torch.manual_seed(33)                                                              # same weights on all ranks
+            m = EGNNEquiHNNS(1, args)
+            with torch.no_grad():
+                for k, p_ in m.named_parameters():
+                    if k.startswith("egnn_layer") and k.endswith("weight") and p_.dim() == 2:
+                        p_.normal_(0, 0.05)
+            return m.to(dev).train()
+
+        a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, uniform_shapes=True)               # exchange inside the graph
+        b = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=False)               # one all-reduce after it
+        assert a.in_graph_step and a.distributed and a.world == world
+        for step in range(4):
+            la = a.step_from_host(host[step % 3], dev)
+            lb = b.step_from_host(host[step % 3], dev)
+            assert la == lb, (rank, step, la, lb)
+        torch.cuda.synchronize()
+        # two bucket all-reduces == one all-reduce of the flat buffer (element-wise sums): bit-identical state
+        assert torch.equal(a.fp.flat, b.fp.flat) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+        flats = [torch.empty_like(a.fp.flat) for _ in range(world)]
+        dist.all_gather(flats, a.fp.flat)
+        assert all(torch.equal(flats[0], f) for f in flats[1:])                                # ranks stay in lock step
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_in_graph_gradient_exchange_two_gpus(tmp_path):
+    """NCCL all-reduces captured inside the step graph (bucketed, the conv + readout bucket overlapped with the EGNN
+    backward) against the plain 'replay, then one all-reduce, then Adam' path on 2 GPUs (needs `gpurun --gpus 2`)."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
