@@ -74,6 +74,8 @@ _SIGNATURES = {
     "eqh_egnn_unpack_grads": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "eqh_gemm_tf32x3_ex": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                    c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "eqh_gemm_grouped_plan": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "eqh_gemm_grouped": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
                                   c_float, _P]),
 }
@@ -87,6 +89,16 @@ class ColsumJob(ctypes.Structure):
 
 
 COLSUM_MAX_JOBS = 32
+
+
+class GemmProblem(ctypes.Structure):
+    """struct eqh_gemm_problem (include/eqh_b200.h)"""
+    _fields_ = [("A", c_void_p), ("lda", c_int64), ("B", c_void_p), ("ldb", c_int64), ("D", c_void_p), ("ldd", c_int64),
+                ("M", c_int64), ("N", c_int64), ("K", c_int64), ("bias", c_void_p), ("rowscale", c_void_p),
+                ("residual", c_void_p), ("out_scale", c_float), ("res_scale", c_float)]
+
+
+GEMM_MAX_GROUP = 8
 
 
 class Store(ctypes.Structure):

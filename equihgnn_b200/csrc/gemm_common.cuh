@@ -64,6 +64,18 @@ struct Params {
   int64_t ld_aux;
 };
 
+// A group of independent problems launched as one grid (gemm_ts.cu: k_gemm_ts_grouped)
+constexpr int kMaxGroup = 8;
+struct GroupParams {
+  CUtensorMap tmA[kMaxGroup];
+  CUtensorMap tmB[kMaxGroup];
+  Params p[kMaxGroup];
+  int cta_start[kMaxGroup + 1];   // first CTA of each problem in the linear grid
+  int tiles[kMaxGroup];           // output tiles (m x n) of each problem; its CTAs = tiles * p.splits
+  int tiles_n[kMaxGroup];
+  int n;
+};
+
 
 // Epilogue of one 128 x BN tile, executed by warps 4-7 (TMEM lane quadrant = warp & 3):
 // TMEM -> registers -> (bias, act, scales) -> padded smem (`smem`, the idle operand ring) -> coalesced stores
@@ -74,7 +86,7 @@ struct Params {
 template <int BN, class AM>
 __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint32_t tmem_base, uint64_t* tmem_full, int warp,
                                               int lane, int nkb, const Params& p, int m0, int n0, int ep_tid = -1,
-                                              uint32_t full_parity = 0, uint64_t* tmem_empty = nullptr) {
+                                              uint32_t full_parity = 0, uint64_t* tmem_empty = nullptr, int split_idx = -1) {
     if (ep_tid < 0) ep_tid = threadIdx.x - 128;
     // ---- epilogue: TMEM -> registers -> (bias, act, residual) -> padded smem -> coalesced stores
     constexpr int PITCH = BN + 4;
@@ -161,7 +173,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
     if (ep_tid == 0) EQH_STAMP(7);
-    float* out = final_out ? p.D : p.ws + (size_t)blockIdx.z * p.M * p.N;
+    float* out = final_out ? p.D : p.ws + (size_t)(split_idx >= 0 ? split_idx : (int)blockIdx.z) * p.M * p.N;
     const int64_t ld = final_out ? p.ldd : p.N;
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool has_res = final_out && p.residual != nullptr;
@@ -226,14 +238,15 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
 
 // Split-K finish, executed by the whole CTA after its partial tile is written (includes the block barriers).
 template <int BN>
-__device__ __forceinline__ void splitk_finish(const Params& p, int m0, int n0, int* s_last) {
+__device__ __forceinline__ void splitk_finish(const Params& p, int m0, int n0, int* s_last, int tile_idx = -1,
+                                              int nsplits = -1) {
   {
     // ---- split-K finish: the CTA that arrives last at this tile's counter adds the partials in split order
     // (the order never depends on which CTA is last: deterministic) and applies the output transform
     if (threadIdx.x == 0) {
-      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      const int tile = tile_idx >= 0 ? tile_idx : (int)(blockIdx.y * gridDim.x + blockIdx.x);
       const int prev = atomicAdd(p.counters + tile, 1);
-      *s_last = (prev == (int)gridDim.z - 1);
+      *s_last = (prev == (nsplits >= 0 ? nsplits : (int)gridDim.z) - 1);
       if (*s_last) p.counters[tile] = 0;         // left zero for the next launch
     }
     __syncthreads();
@@ -241,7 +254,7 @@ __device__ __forceinline__ void splitk_finish(const Params& p, int m0, int n0, i
       __threadfence();
       const int64_t MN = (int64_t)p.M * p.N;
       const int rows_here = min(BM, p.M - m0);
-      const int nz = (int)gridDim.z;
+      const int nz = nsplits >= 0 ? nsplits : (int)gridDim.z;
       const bool vec = ((p.N & 3) == 0) && ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                        (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
       if (vec) {

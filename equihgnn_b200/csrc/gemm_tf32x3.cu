@@ -20,6 +20,9 @@
 // per-split partials; the CTA arriving last at a tile's counter adds them in split order (deterministic)
 // and applies the output transform -- one launch.  The tile width (32/64/128) and the split count are
 // chosen per problem so that small GEMMs still occupy every SM (plan()).
+#include <algorithm>
+#include <mutex>
+
 #include "gemm_common.cuh"
 
 namespace eqh {
@@ -252,6 +255,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
 int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
               dim3 grid, cudaStream_t st);
 
+int launch_ts_grouped(int BN, bool a_kmajor, bool b_kmajor, const GroupParams& g, int ctas, cudaStream_t st);
+
 // gemm_ps.cu: persistent 128 x 64 variant with double-buffered accumulators (multi-wave problems, no split-K)
 int launch_ps(bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t st);
 
@@ -315,6 +320,131 @@ int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits, int flags, int* b
   gemm::plan(M, N, K, splits, (flags & 0x100) ? 128 : (code ? (16 << code) : 0), bn, splits_out, (flags & 0x8000) != 0);
   *tiles = ((M + gemm::BM - 1) / gemm::BM) * ((N + *bn - 1) / *bn);
   return EQH_OK;
+}
+
+// ---- grouped launch: n independent problems with the same operand majors ------------------------------------------
+// Plan: one tile width for the group and, per problem, a split count such that every CTA owns about q K blocks; q and
+// the width minimise rounds x per-CTA cost (the cost model of gemm::plan), rounds = ceil(total CTAs / SMs).
+static void plan_group(const eqh_gemm_problem* pr, int n, int bn_req, int* bn_out, int* splits /*[n]*/) {
+  using namespace eqh;
+  using namespace eqh::gemm;
+  double best = 1e300;
+  int best_bn = 64, best_q = 1 << 30;
+  int64_t kb_max = 1;
+  for (int i = 0; i < n; ++i) kb_max = std::max<int64_t>(kb_max, (pr[i].K + BK - 1) / BK);
+  for (int bn = 128; bn >= 32; bn >>= 1) {
+    if (bn_req && bn != bn_req) continue;
+    for (int s = 1; s <= 32; ++s) {
+      const int64_t q = (kb_max + s - 1) / s;                 // K blocks per CTA of the deepest problem
+      if (s > 1 && q < 2) break;
+      int64_t ctas = 0;
+      double finish = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const int64_t kb = (pr[i].K + BK - 1) / BK;
+        int64_t si = (kb + q - 1) / q;
+        si = si < 1 ? 1 : (si > 32 ? 32 : si);
+        const int64_t kbps = (kb + si - 1) / si, s_eff = (kb + kbps - 1) / kbps;
+        ctas += ((pr[i].M + BM - 1) / BM) * ((pr[i].N + bn - 1) / bn) * s_eff;
+        if (s_eff > 1) finish = std::max(finish, 4.0 * bn * (double)s_eff);
+      }
+      const int64_t rounds = (ctas + kSMs - 1) / kSMs;
+      const double cost = (double)rounds * ((double)q * (300.0 + 6.4 * bn) + 1500.0) + finish;
+      if (cost < best - 1e-9) { best = cost; best_bn = bn; best_q = (int)q; }
+    }
+  }
+  *bn_out = best_bn;
+  for (int i = 0; i < n; ++i) {
+    const int64_t kb = (pr[i].K + BK - 1) / BK;
+    int64_t si = (kb + best_q - 1) / best_q;
+    si = si < 1 ? 1 : (si > 32 ? 32 : si);
+    const int64_t kbps = (kb + si - 1) / si;
+    splits[i] = (int)((kb + kbps - 1) / kbps);
+  }
+}
+
+static int group_check(const eqh_gemm_problem* pr, int n) {
+  if (!pr || n < 1 || n > eqh::gemm::kMaxGroup) return EQH_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    const eqh_gemm_problem& q = pr[i];
+    if (!(q.A && q.B && q.D && q.M > 0 && q.N > 0 && q.K > 0 && q.M < (1 << 30) && q.N < (1 << 30) && q.K < (1 << 30)))
+      return EQH_ERR_ARG;
+    if (!(eqh::aligned16(q.A) && eqh::aligned16(q.B) && q.lda % 4 == 0 && q.ldb % 4 == 0 && q.ldd >= q.N)) return EQH_ERR_ARG;
+  }
+  return EQH_OK;
+}
+
+int eqh_gemm_grouped_plan(const eqh_gemm_problem* problems, int n, int a_kmajor, int b_kmajor, int flags, int* bn,
+                          int* splits, int64_t* ws_floats, int64_t* n_counters) {
+  (void)a_kmajor; (void)b_kmajor;
+  using namespace eqh::gemm;
+  int rc = group_check(problems, n);
+  if (rc) return rc;
+  EQH_CHECK_ARG(bn && splits && ws_floats && n_counters);
+  const int code = (flags >> 9) & 3;
+  plan_group(problems, n, code ? (16 << code) : 0, bn, splits);
+  int64_t ws = 0, cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    if (splits[i] > 1) {
+      ws += (int64_t)splits[i] * problems[i].M * problems[i].N;
+      ws = (ws + 3) / 4 * 4;                                   // every problem's partials start 16-byte aligned
+    }
+    cnt += ((problems[i].M + BM - 1) / BM) * ((problems[i].N + *bn - 1) / *bn);
+  }
+  *ws_floats = ws;
+  *n_counters = cnt;
+  return EQH_OK;
+}
+
+int eqh_gemm_grouped(const eqh_gemm_problem* problems, int n, int a_kmajor, int b_kmajor, int flags, float* ws,
+                     int32_t* counters, eqh_stream_t stream) {
+  using namespace eqh;
+  using namespace eqh::gemm;
+  int rc = group_check(problems, n);
+  if (rc) return rc;
+  int BN, splits[kMaxGroup];
+  const int code = (flags >> 9) & 3;
+  plan_group(problems, n, code ? (16 << code) : 0, &BN, splits);
+  static GroupParams g;                        // ~3 KB: too large for the stack of every caller; filled and launched under a lock
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  g.n = n;
+  int ctas = 0;
+  int64_t ws_off = 0, cnt_off = 0;
+  for (int i = 0; i < n; ++i) {
+    const eqh_gemm_problem& q = problems[i];
+    rc = a_kmajor ? make_map(&g.tmA[i], q.A, q.M, q.K, q.lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_map(&g.tmA[i], q.A, q.K, q.M, q.lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = b_kmajor ? make_map(&g.tmB[i], q.B, q.N, q.K, q.ldb, BK, (uint32_t)BN, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_map(&g.tmB[i], q.B, q.K, q.N, q.ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    Params& p = g.p[i];
+    const int64_t tm = (q.M + BM - 1) / BM, tn = (q.N + BN - 1) / BN;
+    const int kb_total = (int)((q.K + BK - 1) / BK);
+    p.D = q.D; p.ldd = q.ldd; p.residual = q.residual; p.out_scale = q.out_scale; p.res_scale = q.res_scale;
+    p.M = (int)q.M; p.N = (int)q.N; p.K = (int)q.K;
+    p.splits = splits[i];
+    p.kb_per_split = (kb_total + splits[i] - 1) / splits[i];
+    p.stash = nullptr; p.dsilu_aux = nullptr; p.ld_aux = 0;
+    if (splits[i] > 1) {
+      EQH_CHECK_ARG(ws && counters && !q.bias);                // the split-K finish applies scales / residual only
+      p.ws = ws + ws_off;
+      ws_off += (int64_t)splits[i] * q.M * q.N;
+      ws_off = (ws_off + 3) / 4 * 4;
+      p.bias = nullptr; p.rowscale = nullptr; p.act = 0;
+    } else {
+      p.ws = nullptr;
+      p.bias = q.bias; p.rowscale = q.rowscale; p.act = flags & 0xff;
+    }
+    p.counters = counters ? counters + cnt_off : nullptr;
+    cnt_off += tm * tn;
+    g.cta_start[i] = ctas;
+    g.tiles[i] = (int)(tm * tn);
+    g.tiles_n[i] = (int)tn;
+    ctas += (int)(tm * tn) * splits[i];
+  }
+  g.cta_start[n] = ctas;
+  return launch_ts_grouped(BN, a_kmajor != 0, b_kmajor != 0, g, ctas, static_cast<cudaStream_t>(stream));
 }
 
 size_t eqh_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {

@@ -57,9 +57,14 @@ struct TsCfg {
   static_assert(kRing >= (size_t)BM * (BN + 4) * 4, "epilogue staging must fit in the B ring");
 };
 
+// One output tile (bx, by) of one problem, K range of split bz of nz; `tile` indexes the problem's split-K arrival counter.
+// Called by the single-problem kernel (coordinates = blockIdx) and by the grouped kernel (coordinates decoded from a
+// linear CTA index over all problems of the group).
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__ CUtensorMap tmA,
-                                                          const __grid_constant__ CUtensorMap tmB, const Params p) {
+__device__ __forceinline__ void gemm_ts_tile(const CUtensorMap* __restrict__ ptmA, const CUtensorMap* __restrict__ ptmB,
+                                             const Params& p, int bx, int by, int bz, int nz, int tile) {
+  const CUtensorMap& tmA = *ptmA;
+  const CUtensorMap& tmB = *ptmB;
   using Cfg = TsCfg<BN>;
   using AM = AccMap<BN>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB;
@@ -79,10 +84,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int n0 = bx * BN, m0 = by * BM;
   if (threadIdx.x == 0) EQH_STAMP(0);
   const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_begin = bz * p.kb_per_split;
   const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
   const int nkb = max(kb_end - kb_begin, 0);
 
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__
       if (r == 0 && i < 8) EQH_STAMP(40 + i);
     }
     // ===================== epilogue (same warps) =====================
-    epilogue_tile<BN, AM>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0);
+    epilogue_tile<BN, AM>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0, -1, 0, nullptr, bz);
   } else {
     // ===================== B split (hi / lo): warps 2, 3, 8, 9 =====================
     const int t = ((warp < 4 ? warp - 2 : warp - 6) << 5) + lane;      // 0..127
@@ -241,7 +246,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__
   if (p.ws != nullptr) __threadfence();       // this split's partial tile is visible device-wide before the arrival
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
-  if (p.ws != nullptr) splitk_finish<BN>(p, m0, n0, &s_last);
+  if (p.ws != nullptr) splitk_finish<BN>(p, m0, n0, &s_last, tile, nz);
+}
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(kThreads, 1) k_gemm_ts(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB, const Params p) {
+  gemm_ts_tile<BN, A_KMAJOR, B_KMAJOR>(&tmA, &tmB, p, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.z,
+                                       (int)(blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+// Several independent GEMMs of the same operand majors in ONE launch (the weight gradients of a layer: 7 problems of 16
+// tiles each would otherwise be 7 launches of a few CTA rounds each, every one with its own prologue / split-K finish
+// tail).  CTA i of the linear grid belongs to problem g with cta_start[g] <= i < cta_start[g+1]; inside the problem the
+// index decodes to (split, tile_m, tile_n).
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(kThreads, 1) k_gemm_ts_grouped(const __grid_constant__ GroupParams g) {
+  int i = 0;
+  while (i + 1 < g.n && (int)blockIdx.x >= g.cta_start[i + 1]) ++i;
+  const int local = (int)blockIdx.x - g.cta_start[i];
+  const int bz = local / g.tiles[i], t = local - bz * g.tiles[i];
+  const int by = t / g.tiles_n[i], bx = t - by * g.tiles_n[i];
+  gemm_ts_tile<BN, A_KMAJOR, B_KMAJOR>(&g.tmA[i], &g.tmB[i], g.p[i], bx, by, bz, g.p[i].splits, t);
 }
 
 template <int BN, bool AK, bool BK_>
@@ -252,6 +278,29 @@ static int launch_one(const CUtensorMap& a, const CUtensorMap& b, const Params& 
   if (e != cudaSuccess) return (int)e;
   launch_kernel(k_gemm_ts<BN, AK, BK_>, dim3(grid), dim3(kThreads), smem, st, a, b, p);
   EQH_LAUNCH_RC();
+}
+
+template <int BN, bool AK, bool BK_>
+static int launch_group_one(const GroupParams& g, int ctas, cudaStream_t st) {
+  constexpr size_t smem = TsCfg<BN>::kSmem;
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_ts_grouped<BN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  launch_kernel(k_gemm_ts_grouped<BN, AK, BK_>, dim3((unsigned)ctas), dim3(kThreads), smem, st, g);
+  EQH_LAUNCH_RC();
+}
+
+int launch_ts_grouped(int BN, bool a_kmajor, bool b_kmajor, const GroupParams& g, int ctas, cudaStream_t st) {
+#define EQH_TSG_MAJORS(BNV)                                                                  \
+  do {                                                                                       \
+    if (a_kmajor && b_kmajor) return launch_group_one<BNV, true, true>(g, ctas, st);         \
+    if (a_kmajor && !b_kmajor) return launch_group_one<BNV, true, false>(g, ctas, st);       \
+    if (!a_kmajor && !b_kmajor) return launch_group_one<BNV, false, false>(g, ctas, st);     \
+    return launch_group_one<BNV, false, true>(g, ctas, st);                                  \
+  } while (0)
+  if (BN == 32) EQH_TSG_MAJORS(32);
+  if (BN == 64) EQH_TSG_MAJORS(64);
+  EQH_TSG_MAJORS(128);
+#undef EQH_TSG_MAJORS
 }
 
 int launch_ts(int BN, bool a_kmajor, bool b_kmajor, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,

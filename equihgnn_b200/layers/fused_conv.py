@@ -46,6 +46,8 @@ class _GradSink:
             self.out[id(p)] = ops.direct_target_strict(p) if direct else None
         self.params = params
         self.batch = ops.ColsumBatch(params[0].device)
+        # weight gradients dW = dY^T . X are queued and launched as ONE grouped GEMM per flush() (ops.GemmGroup)
+        self.group = ops.GemmGroup(params[0].device, False, False) if ops.WGRAD_GROUPED else None
 
     def weight(self, p, dy, x, cols=None):
         """p.grad[:, cols] (+)= dy^T x   (dy [M, out], x [M, in])"""
@@ -58,6 +60,10 @@ class _GradSink:
             self._fresh_cols = getattr(self, "_fresh_cols", {})
         view = tgt if cols is None else tgt[:, cols]
         acc = self.direct or (not fresh and cols is None)
+        if self.group is not None and ops._gemm_ok(dy) and ops._gemm_ok(x) and view.stride(1) == 1 and view.stride(0) % 4 == 0 \
+                and view.data_ptr() % 16 == 0:
+            self.group.add(dy, x, n_out, n_in, M, view, accumulate=acc)
+            return
         if self.side:
             with ops.side_work.fork(dy.device, keep=(dy, x)):
                 gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view)
@@ -84,10 +90,16 @@ class _GradSink:
                 self.batch.add(part, tgt, col0=c0, cols=C, accumulate=True)
 
     def flush(self):
+        group = self.group if (self.group is not None and self.group.problems) else None
         if self.side:
-            with ops.side_work.fork(self.batch.device, keep=tuple(self.batch.keep)):
+            keep = tuple(self.batch.keep) + (tuple(group.keep) if group else ())
+            with ops.side_work.fork(self.batch.device, keep=keep):
+                if group:
+                    group.run()
                 self.batch.run()
         else:
+            if group:
+                group.run()
             self.batch.run()
 
     def results(self):

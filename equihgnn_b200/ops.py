@@ -686,6 +686,45 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
     return D
 
 
+class GemmGroup:
+    """Collects independent GEMMs with the same operand majors (a layer's weight gradients dW = dY^T . X) and launches them
+    as ONE grid (eqh_gemm_grouped): instead of one launch per parameter -- each a few CTA rounds with its own prologue,
+    split-K finish and tail -- the group fills the GPU once."""
+
+    def __init__(self, device, a_kmajor: bool, b_kmajor: bool):
+        self.device, self.a_kmajor, self.b_kmajor = device, a_kmajor, b_kmajor
+        self.problems, self.keep = [], []
+
+    def add(self, A, B, M: int, N: int, K: int, out: torch.Tensor, accumulate: bool = False, out_scale: float = 1.0) -> None:
+        """out[M,N] (+)= out_scale * A.B^T  (A logical [M,K], B logical [N,K], stored as the group's majors say)"""
+        self.problems.append(_lib.GemmProblem(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
+                                              out.stride(0), M, N, K, None, None, out.data_ptr() if accumulate else None,
+                                              out_scale, 1.0))
+        self.keep += [A, B, out]
+
+    def run(self) -> None:
+        import ctypes
+        lib = _lib.load()
+        for i in range(0, len(self.problems), _lib.GEMM_MAX_GROUP):
+            chunk = self.problems[i:i + _lib.GEMM_MAX_GROUP]
+            arr = (_lib.GemmProblem * len(chunk))(*chunk)
+            bn, ws_f, n_cnt = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+            splits = (ctypes.c_int * len(chunk))()
+            _lib.check(lib.eqh_gemm_grouped_plan(arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), GEMM_FLAGS,
+                                                 ctypes.byref(bn), splits, ctypes.byref(ws_f), ctypes.byref(n_cnt)),
+                       "eqh_gemm_grouped_plan")
+            ws = torch.empty(max(ws_f.value, 4), dtype=torch.float32, device=self.device)
+            cnt = counters(int(n_cnt.value), self.device)
+            flops = sum(2.0 * q.M * q.N * q.K for q in chunk)
+            _call("eqh_gemm_grouped", 1, arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), GEMM_FLAGS, _p(ws), _p(cnt),
+                  _stream(), nbytes=flops)
+            self.keep.append(ws)
+        self.problems = []
+
+
+WGRAD_GROUPED = os.environ.get("EQH_WGRAD_GROUPED", "1") != "0"     # one grouped launch per layer for the weight gradients
+
+
 def _gemm_ok(t: torch.Tensor) -> bool:
     return (t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0
             and t.data_ptr() % 16 == 0)

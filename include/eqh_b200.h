@@ -387,6 +387,26 @@ EQH_API int eqh_gemm_tf32x3_ex(const float* A, int a_kmajor, int64_t lda, const 
                        const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
                        float* stash, const float* dsilu_aux, int64_t ld_aux, eqh_stream_t stream);
 
+/* Several independent GEMMs with the same operand majors as ONE launch (the weight gradients dW = dY^T . X of all the
+ * Linears of a layer, mlp.py:91-99 / conv.py:169-182 backward): D_i = out_scale_i * (A_i . B_i^T [+ bias_i * rowscale_i])
+ * + res_scale_i * residual_i, operand conventions of eqh_gemm_tf32x3.  The planner picks one tile width for the group and
+ * a split-K count per problem (partials in ws, finished in fixed split order by the last-arriving CTA of a tile:
+ * deterministic); a problem that is split must not carry a bias.  eqh_gemm_grouped_plan returns the tile width, the
+ * per-problem split counts (splits[n]) and the workspace (floats) / zeroed int32 counters the launch needs.
+ * n <= 8. */
+typedef struct eqh_gemm_problem {
+  const float* A; int64_t lda;
+  const float* B; int64_t ldb;
+  float* D; int64_t ldd;
+  int64_t M, N, K;
+  const float* bias; const float* rowscale; const float* residual;
+  float out_scale, res_scale;
+} eqh_gemm_problem;
+EQH_API int eqh_gemm_grouped_plan(const eqh_gemm_problem* problems, int n, int a_kmajor, int b_kmajor, int flags, int* bn,
+                          int* splits, int64_t* ws_floats, int64_t* n_counters);
+EQH_API int eqh_gemm_grouped(const eqh_gemm_problem* problems, int n, int a_kmajor, int b_kmajor, int flags, float* ws,
+                     int32_t* counters, eqh_stream_t stream);
+
 /* The same step with the step count t-1 held in DEVICE memory (int64), for an optimizer that lives inside a captured
  * CUDA graph: every block derives the bias corrections of step t = *step_dev + 1 in double precision; with advance != 0
  * the last block to finish stores t to *step_dev (counter: one zeroed int32, left zero).  An optimizer step split over

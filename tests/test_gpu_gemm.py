@@ -186,3 +186,79 @@ def test_gemm_writes_only_its_output(M, N, K, flags):
         full = buf[8 * ld:8 * ld + rows * ld].view(rows, ld)
         assert bool((full[:, N:] == 12345.0).all()), layout                  # columns beyond N in every row
         assert bool((buf[:8 * ld] == 12345.0).all()) and bool((buf[8 * ld + rows * ld:] == 12345.0).all()), layout
+
+
+@pytest.mark.parametrize("rows", [300, 2560, 30000])
+def test_gemm_grouped_weight_gradients(rows):
+    """eqh_gemm_grouped: the weight gradients of a layer (dW_i = dY_i^T . X_i, different shapes, one strided target that is
+    accumulated in place) as ONE launch agree with fp64 and are deterministic; more problems than a group holds are
+    chunked."""
+    g = torch.Generator().manual_seed(rows)
+    shapes = [(256, 256), (256, 256), (512, 272), (64, 256), (256, 128), (1088, 256), (256, 256), (32, 64), (256, 256),
+              (128, 512)]                                                   # (out features, in features): 10 > 8 problems
+    dys = [_mk((rows, o), g) for o, _ in shapes]
+    xs = [_mk((rows, i), g) for _, i in shapes]
+    wide = _mk((256, 512), g)                                               # problem 1 accumulates into wide[:, 256:]
+    wide0 = wide.clone()
+    outs = []
+
+    def run():
+        grp = ops.GemmGroup(DEV, False, False)
+        res = []
+        for k, ((o, i), dy, x) in enumerate(zip(shapes, dys, xs)):
+            if k == 1:
+                wide.copy_(wide0)
+                grp.add(dy, x, o, i, rows, wide[:, 256:], accumulate=True)
+                res.append(wide)
+            else:
+                t = torch.empty(o, i, device=DEV)
+                grp.add(dy, x, o, i, rows, t)
+                res.append(t)
+        grp.run()
+        return [r.clone() for r in res]
+
+    outs = run()
+    for k, ((o, i), dy, x) in enumerate(zip(shapes, dys, xs)):
+        ref = dy.double().t() @ x.double()
+        if k == 1:
+            assert torch.equal(outs[k][:, :256], wide0[:, :256])            # the other half is untouched
+            assert rel_err(outs[k][:, 256:], wide0[:, 256:].double() + ref) < 5e-6
+        else:
+            assert rel_err(outs[k], ref) < 5e-6, (k, o, i)
+    again = run()
+    assert all(torch.equal(a, b) for a, b in zip(outs, again))             # split-K finished in fixed order
+
+
+def test_gemm_grouped_forward_layout_and_epilogue_extras():
+    """Grouped launch with K-major operands (two Linears sharing their input), and the single-launch epilogue extras:
+    the SiLU pre-activation stash and the fused SiLU backward."""
+    g = torch.Generator().manual_seed(5)
+    X = _mk((2341, 256), g)
+    W1, W2 = _mk((256, 256), g, 0.06), _mk((1088, 256), g, 0.06)
+    grp = ops.GemmGroup(DEV, True, True)
+    D1, D2 = torch.empty(2341, 256, device=DEV), torch.empty(2341, 1088, device=DEV)
+    grp.add(X, W1, 2341, 256, 256, D1)
+    grp.add(X, W2, 2341, 1088, 256, D2)
+    grp.run()
+    assert rel_err(D1, X.double() @ W1.double().t()) < 2e-6 and rel_err(D2, X.double() @ W2.double().t()) < 2e-6
+    # act = silu with the pre-activation stashed; rows / columns that do not fill a tile
+    A, B, bias = _mk((1000, 272), g), _mk((520, 272), g, 0.06), _mk((520,), g)
+    pre = A.double() @ B.double().t() + bias.double()
+    stash = torch.empty(1000, 520, device=DEV)
+    D = ops.gemm_raw(A, True, B, True, 1000, 520, 272, bias=bias, act="silu", stash=stash)
+    assert rel_err(stash, pre) < 2e-6 and rel_err(D, torch.nn.functional.silu(pre)) < 2e-6
+    # dgrad with the SiLU derivative of a stored pre-activation in the epilogue: (dY . W) * silu'(aux) + residual
+    dY, W = _mk((1000, 256), g), _mk((256, 520), g, 0.06)
+    aux, res = _mk((1000, 520), g), _mk((1000, 520), g)
+    s = torch.sigmoid(aux.double())
+    want = (dY.double() @ W.double()) * (s * (1 + aux.double() * (1 - s)))
+    D = ops.gemm_raw(dY, True, W, False, 1000, 520, 256, dsilu_aux=aux)
+    assert rel_err(D, want) < 2e-6
+    D = ops.gemm_raw(dY, True, W, False, 1000, 520, 256, dsilu_aux=aux, residual=res)
+    assert rel_err(D, want + res.double()) < 2e-6
+    big = _mk((30000, 256), g)                                                # the persistent variant shares the epilogue
+    Wb = _mk((512, 256), g, 0.06)
+    st = torch.empty(30000, 512, device=DEV)
+    D = ops.gemm_raw(big, True, Wb, True, 30000, 512, 256, act="silu", stash=st)
+    pre = big.double() @ Wb.double().t()
+    assert rel_err(st, pre) < 2e-6 and rel_err(D, torch.nn.functional.silu(pre)) < 2e-6
