@@ -294,21 +294,21 @@ __global__ void __launch_bounds__(256) k_egnn_pack(const float* __restrict__ W1,
                                                     float* __restrict__ W1b, float* __restrict__ wc, float* __restrict__ b1p,
                                                     float* __restrict__ W2p) {
   pdl_prologue();
-  const int64_t ld = 2 * (int64_t)C + 1;
-  const int64_t n1 = (int64_t)H0 * ld, n2 = n1 + H0, n3 = n2 + (int64_t)kM * H0;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
-    if (t < n1) {
-      const int64_t r = t / ld, c = t - r * ld;
-      const float v = __ldg(W1 + t);
-      if (c < C) W1a[r * C + c] = v;
-      else if (c < 2 * C) W1b[r * C + (c - C)] = v;
-      else wc[r] = v;
-    } else if (t < n2) {
-      b1p[t - n1] = __ldg(b1 + (t - n1));
-    } else {
-      const int64_t u = t - n2, o = u / H0, h = u - o * H0;
-      W2p[o * Hp + h] = __ldg(W2 + u);
+  // one block per row of W1 (coalesced reads and writes, no integer division); the last kM blocks copy b1 and W2
+  const int r = blockIdx.x;
+  if (r < H0) {
+    const float* src = W1 + (int64_t)r * (2 * C + 1);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      W1a[(int64_t)r * C + c] = __ldg(src + c);
+      W1b[(int64_t)r * C + c] = __ldg(src + C + c);
     }
+    if (threadIdx.x == 0) {
+      wc[r] = __ldg(src + 2 * C);
+      b1p[r] = __ldg(b1 + r);
+    }
+  } else {
+    const int o = r - H0;
+    for (int h = threadIdx.x; h < H0; h += blockDim.x) W2p[(int64_t)o * Hp + h] = __ldg(W2 + (int64_t)o * H0 + h);
   }
 }
 
@@ -358,10 +358,7 @@ int eqh_egnn_pack(const float* W1, const float* b1, const float* W2, int64_t H0,
                   float* wc, float* b1p, float* W2p, eqh_stream_t stream) {
   using namespace eqh;
   EQH_CHECK_ARG(W1 && b1 && W2 && W1a && W1b && wc && b1p && W2p && H0 > 0 && C > 0 && Hp >= H0);
-  const int64_t n = H0 * (2 * C + 1) + H0 + (int64_t)kM * H0;
-  int64_t blocks = (n + 255) / 256;
-  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
-  launch_kernel(k_egnn_pack, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), W1, b1, W2, (int)H0, (int)C,
+  launch_kernel(k_egnn_pack, dim3((unsigned)(H0 + kM)), dim3(256), 0, static_cast<cudaStream_t>(stream), W1, b1, W2, (int)H0, (int)C,
                 (int)Hp, W1a, W1b, wc, b1p, W2p);
   EQH_LAUNCH_RC();
 }

@@ -99,6 +99,7 @@ class EGNN(nn.Module):
         # are accumulated straight into p.grad (layers/fused_egnn.py)
         self.direct_param_grad = False
         self._packed = None
+        self._packed_fresh = False
         self.apply(self.init_)
 
     def _fusable(self, h, x, need_coors) -> bool:
@@ -117,6 +118,16 @@ class EGNN(nn.Module):
             self._packed = {"W1ab": W1ab, "b1ab": b1ab, "W1a": W1ab[:Hp], "W1b": W1ab[Hp:], "wc": z(Hp), "b1": b1ab[:Hp],
                             "W2": z(ops.M_DIM, Hp)}
         return self._packed
+
+    def prepack(self, device) -> None:
+        """Refresh the packed phi_e weights now (they depend on the parameters only): a model calls this under
+        ops.branch_work.fork at the start of its forward so that the re-layout leaves the critical path."""
+        if not (self.direct_param_grad and torch.is_grad_enabled() and self.node_mlp is not None):
+            return
+        lin0, lin3 = self.edge_mlp[0], self.edge_mlp[3]
+        from .fused_egnn import pack_phi_e
+        pack_phi_e(self._packed_buffers(device, self.dim), lin0.weight, lin0.bias, lin3.weight, self.dim)
+        self._packed_fresh = True
 
     def init_(self, module):
         if type(module) in {nn.Linear}:
@@ -144,11 +155,14 @@ class EGNN(nn.Module):
             # While a CUDA graph is being captured the kNN search and the transposed kNN incidence (they need only the
             # coordinates) run as a parallel branch (ops.prep_work_b) next to the weight packing and the phi_e GEMMs;
             # EGNNFused joins the branch right before the edge kernel.
+            # (the transposed incidence is only needed by the backward: EGNNFused builds it on the branch AFTER the edge
+            # kernel has been issued, so that it does not gate the forward)
             with ops.prep_work_b.fork(h.device):
-                graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=True)
-                if graph.rowptr_j is None:
-                    graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
-            pack_phi_e(bufs, lin0.weight, lin0.bias, lin3.weight, C)
+                graph = knn_graph if knn_graph is not None else ops.build_knn_graph(x, need_transpose=False)
+            if not self._packed_fresh:                # (a caller may have refreshed them on a parallel branch: prepack())
+                pack_phi_e(bufs, lin0.weight, lin0.bias, lin3.weight, C)
+            self._packed_fresh = False
+            ops.branch_work.join(h.device)
             out = EGNNFused.apply(h, graph, bufs, self.node_norm.eps, lin0.weight, lin0.bias,
                                   lin3.weight, lin3.bias, self.node_norm.weight, self.node_norm.bias, n0.weight, n0.bias,
                                   n3.weight, n3.bias)

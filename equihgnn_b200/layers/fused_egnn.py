@@ -53,6 +53,9 @@ class EGNNFused(torch.autograd.Function):
         _call("eqh_egnn_edge_fwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2p), _p(b2), _p(graph.idx),
               _p(graph.d2), N, Hp, _p(S2), None, node_in.data_ptr() + 4 * C, ldn, _p(graph.order), _stream(),
               nbytes=2.0 * N * KNN_K * Hp * M_DIM)
+        if graph.rowptr_j is None:                        # transposed kNN incidence for the backward: a parallel branch
+            with ops.prep_work_b.fork(dev, keep=(graph.idx,)):
+                graph.rowptr_j, graph.perm_j, _, _ = ops.csr_build(graph.idx.view(-1), N, None)
         t_pre = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
         tt = gemm_raw(node_in, True, w5, True, N, 2 * C, ldn, bias=b5, act="silu", stash=t_pre)
         out = gemm_raw(tt, True, w6, True, N, C, 2 * C, bias=b6, residual=h)         # egnn_layer.py:361-362

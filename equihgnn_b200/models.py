@@ -286,7 +286,9 @@ class EGNNEquiHNNS(nn.Module):
         # ... and, on small batches, the kNN graph (coordinates only) next to both; the cell-grid search of large batches
         # fills the GPU by itself (measured: no gain at Molecule3D-1024)
         with (ops.prep_work_b.fork(data.x.device) if N < 8192 else contextlib.nullcontext()):
-            graph = ops.build_knn_graph(data.pos, need_transpose=torch.is_grad_enabled())
+            graph = ops.build_knn_graph(data.pos, need_transpose=False)    # (the EGNN layer builds the transpose it needs)
+        with ops.branch_work.fork(data.x.device):          # phi_e's weight re-layout depends on the parameters only
+            self.egnn_layer.prepack(data.x.device)
         x = self.atom_encoder(data.x)
         x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False,   # coors_out is discarded (:158)
                                knn_graph=graph)
