@@ -76,6 +76,13 @@ _SIGNATURES = {
                                    c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P]),
     "eqh_gemm_grouped_plan": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "eqh_gemm_grouped": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "eqh_egnn_coors_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    "eqh_egnn_coors_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "eqh_egnn_coors_bwd_pos": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
+    "eqh_batchnorm_partial_floats": (c_int, [c_int64]),
+    "eqh_batchnorm_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P]),
+    "eqh_batchnorm_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
                                   c_float, _P]),
 }

@@ -192,12 +192,11 @@ class EGNN(nn.Module):
 
         # --- coordinate branch phi_x (egnn_layer.py:325-340); callers of egnn_equihnns discard it
         if self.coors_mlp is not None and need_coors:
-            cw = self.coors_mlp(m_ij).squeeze(-1)                                  # [N,16]
-            if idx_long is None:
-                idx_long = graph.idx.long()
-            rel = x.unsqueeze(1) - x[idx_long]                                     # [N,16,3]
-            rel = self.coors_norm(rel)
-            coors_out = torch.einsum("ij,ijc->ic", cw, rel) + x
+            # one kernel (eqh_egnn_coors_fwd: 16 -> 64 -> 1 MLP per kNN edge, CoorsNorm, sum over the neighbours) instead
+            # of ~10 ATen / cuBLAS launches on materialised [N,16,*] tensors; its backward is kernels too
+            c0, c3 = self.coors_mlp[0], self.coors_mlp[3]
+            scale = self.coors_norm.scale if isinstance(self.coors_norm, CoorsNorm) else None
+            coors_out = ops.egnn_coors(m_ij, x, c0.weight, c0.bias, c3.weight, c3.bias, scale, graph)
         else:
             coors_out = x
 

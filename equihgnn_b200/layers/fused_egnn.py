@@ -103,7 +103,10 @@ class EGNNFused(torch.autograd.Function):
         # inputs exist -- this layer's backward is the tail of the step, nothing later can hide them: the partial sums
         # and db1 start next to the dQ reduction, the merged weight gradient [dP | dQ]^T . h next to the dh GEMM.
         red = torch.empty(cols, dtype=torch.float32, device=dev)
-        with ops.side_work.fork(dev, keep=(dPQ, part, red)):
+        T = torch.empty((2 * Hp, C), dtype=torch.float32, device=dev)               # [dP | dQ]^T . h = [d W1a ; d W1b]
+        with ops.side_work.fork(dev, keep=(dPQ, part, red, T, h)):
+            # the dP half of the weight gradient runs under the dQ reduction (memory-bound: the tensor pipe is idle)
+            gemm_raw(dPQ, False, h, False, Hp, C, N, splits=0, out=T[:Hp])
             batch = ops.ColsumBatch(dev)
             batch.add(part, red)
             batch.add(dPQ, sink.out[id(b1)], accumulate=True, cols=H0)          # db1 = column sums of dP (= d pre)
@@ -111,9 +114,8 @@ class EGNNFused(torch.autograd.Function):
         # dQ[j] = sum over the edges (i, k) with idx[i, k] == j, ascending edge order (deterministic)
         _call("eqh_gather_reduce_ld", 1, _p(dPre), Hp, _p(graph.perm_j), _p(graph.rowptr_j), None, N, Hp, SUM,
               dPQ.data_ptr() + 4 * Hp, 2 * Hp, _stream(), nbytes=4.0 * Hp * (N * KNN_K + N) + 4.0 * (N * KNN_K + N + 1))
-        T = torch.empty((2 * Hp, C), dtype=torch.float32, device=dev)
         with ops.side_work.fork(dev, keep=(dPQ, h, T, red)):
-            gemm_raw(dPQ, False, h, False, 2 * Hp, C, N, splits=0, out=T)
+            gemm_raw(dPQ[:, Hp:], False, h, False, Hp, C, N, splits=0, out=T[Hp:])     # the dQ half, next to the dh GEMM
             _call("eqh_egnn_unpack_grads", 1, _p(T), _p(red), H0, C, Hp, _p(sink.out[id(w1)]), _p(sink.out[id(w2)]),
                   _p(sink.out[id(b2)]), _stream())
         # dh = dh0 + [dP | dQ] . [W1a ; W1b]   (K = 2 Hp: split-K chosen by the planner, residual added by its finish)

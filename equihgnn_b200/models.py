@@ -245,6 +245,15 @@ class MHNNS(nn.Module):
         return _readout(self.mlp_out, x, loss_target)
 
 
+def _batch_norm(x, bn: nn.BatchNorm1d, n_real_atoms, mask):
+    """BatchNorm1d over the real atom rows (mhnn.py:206): the row kernels when the number of real atoms is known on the
+    host (it always is for batches this package collates), else the masked torch formulation."""
+    if bn.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and n_real_atoms is not None \
+            and bn.momentum is not None:
+        return ops.batch_norm_rows(x, bn, n_real_atoms)
+    return bn(x) if mask is None else masked_batch_norm(x, bn, mask)
+
+
 class EGNNEquiHNNS(nn.Module):
     """`--method egnn_equihnns` (equihnn_egnn.py:98-169)."""
 
@@ -352,10 +361,15 @@ class MHNNM(nn.Module):
         e = bond_encode(self.bond_encoder, data.edge_attr)
         inc = ops.build_incidence(V, E, N, e.shape[0])
         real = int(getattr(data, "num_real_graphs", 0) or 0)
-        mask = (data.batch < real) if real else None                  # ghost-padded batch: keep ghosts out of BatchNorm
+        # ghost-padded batch: the padding atoms follow the real ones and stay out of the BatchNorm statistics; their number
+        # is read on the device (ptr[real]: it changes between replays of one captured graph)
+        ptr = getattr(data, "ptr", None)
+        n_real_atoms = (ptr[real:real + 1] if (ptr is not None and ptr.is_cuda and ptr.dtype == torch.int64) else None) \
+            if real else N
+        mask = (data.batch < real) if (real and n_real_atoms is None) else None
         for i, layer in enumerate(self.layers):
             x, e = layer(x, e, V, E, incidence=inc)
-            x = self.batch_norms[i](x) if mask is None else masked_batch_norm(x, self.batch_norms[i], mask)
+            x = _batch_norm(x, self.batch_norms[i], n_real_atoms, mask)
             if i == self.nlayer - 1:
                 x, e = self.dropout(x), self.dropout(e)
             else:

@@ -1058,6 +1058,120 @@ class _EgnnEdge(torch.autograd.Function):
         return dP, dQ, dwc, dW2, db2, dd2, None
 
 
+class _BatchNormRows(torch.autograd.Function):
+    """nn.BatchNorm1d in training mode over the first n_stat rows of x [rows, C] (eqh_batchnorm_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, num_batches_tracked, n_stat, n_stat_dev, momentum, eps):
+        ctx.w_param, ctx.b_param = weight, bias
+        x = _f32(x, "batch_norm x")
+        rows, C = x.shape
+        dev = x.device
+        w = _f32(weight, "batch_norm weight") if weight is not None else None
+        b = _f32(bias, "batch_norm bias") if bias is not None else None
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        rstd = torch.empty(C, dtype=torch.float32, device=dev)
+        part = torch.empty(_lib.load().eqh_batchnorm_partial_floats(C), dtype=torch.float32, device=dev)
+        _call("eqh_batchnorm_fwd", 2, _p(x), rows, n_stat, C, _p(w), _p(b), eps, momentum, _p(y), _p(mean), _p(rstd),
+              _p(running_mean), _p(running_var), _p(num_batches_tracked), _p(n_stat_dev), _p(part), _stream())
+        ctx.save_for_backward(x, w, mean, rstd)
+        ctx.n_stat, ctx.n_stat_dev = n_stat, n_stat_dev
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dy = _f32(dy, "batch_norm grad")
+        rows, C = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        tg = _direct_target(ctx.w_param) if ctx.w_param is not None else None
+        tb = _direct_target(ctx.b_param) if ctx.b_param is not None else None
+        direct = tg is not None and tb is not None
+        if direct:
+            dg, db = tg, tb
+        else:
+            dg = torch.empty(C, dtype=torch.float32, device=dev) if ctx.w_param is not None else None
+            db = torch.empty(C, dtype=torch.float32, device=dev) if ctx.b_param is not None else None
+        part = torch.empty(_lib.load().eqh_batchnorm_partial_floats(C), dtype=torch.float32, device=dev)
+        _call("eqh_batchnorm_bwd", 2, _p(x), _p(dy), rows, ctx.n_stat, C, _p(w), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
+              int(direct), _p(ctx.n_stat_dev), _p(part), _stream())
+        if direct:
+            return (dx,) + (None,) * 9
+        return (dx, dg, db) + (None,) * 7
+
+
+def batch_norm_rows(x: torch.Tensor, bn: "torch.nn.BatchNorm1d", n_stat=None) -> torch.Tensor:
+    """`bn(x)` for x [rows, C] in training mode with the batch statistics over the first n_stat rows (default: all);
+    running statistics and num_batches_tracked are updated as nn.BatchNorm1d does.  n_stat: an int, or a CUDA int64 scalar
+    tensor read by the kernels (the real-atom count of a ghost-padded batch inside a captured graph)."""
+    rows = x.shape[0]
+    n_stat_dev = None
+    if isinstance(n_stat, torch.Tensor):
+        if not (n_stat.is_cuda and n_stat.dtype == torch.int64 and n_stat.numel() == 1):
+            raise RuntimeError("batch_norm_rows: n_stat tensor must be a CUDA int64 scalar")
+        n_stat_dev, n_stat = n_stat, rows
+    n_stat = rows if n_stat is None else int(n_stat)
+    if bn.track_running_stats:
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+    else:
+        mom, rm, rv, nbt = 0.0, None, None, None
+    if bn.momentum is None and bn.track_running_stats:
+        raise NotImplementedError("batch_norm_rows: momentum=None (cumulative average) is not implemented")
+    return _BatchNormRows.apply(x, bn.weight if bn.affine else None, bn.bias if bn.affine else None, rm, rv, nbt, n_stat,
+                                n_stat_dev, float(mom), float(bn.eps))
+
+
+class _EgnnCoors(torch.autograd.Function):
+    """(m_ij [N,16,16], x [N,3], W3, b3, W4, b4, scale | None) -> coors_out [N,3]: the coordinate branch phi_x
+    (egnn_layer.py:325-340, CoorsNorm :71-81) as one kernel; see csrc/egnn_coors.cu."""
+
+    @staticmethod
+    def forward(ctx, Mij, x, W3, b3, W4, b4, scale, graph: "KnnGraph"):
+        Mij, x, W3, b3, b4 = (_f32(t, "egnn_coors") for t in (Mij, x, W3, b3, b4))
+        W4 = _f32(W4, "egnn_coors").reshape(-1)
+        scale = _f32(scale, "egnn_coors scale") if scale is not None else None
+        N = x.shape[0]
+        if Mij.shape != (N, KNN_K, M_DIM) or W3.shape != (4 * M_DIM, M_DIM) or W4.numel() != 4 * M_DIM:
+            raise NotImplementedError("egnn_coors: coors_mlp must be Linear(16,64) -> SiLU -> Linear(64,1)")
+        out = torch.empty_like(x)
+        _call("eqh_egnn_coors_fwd", 1 if N else 0, _p(Mij), _p(x), _p(graph.idx), _p(W3), _p(b3), _p(W4), _p(b4), _p(scale), N,
+              _p(out), None, _stream())
+        ctx.save_for_backward(Mij, x, W3, b3, W4, b4, scale)
+        ctx.graph = graph
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Mij, x, W3, b3, W4, b4, scale = ctx.saved_tensors
+        g = ctx.graph
+        N = x.shape[0]
+        E = N * KNN_K
+        dev = x.device
+        dout = _f32(dout, "egnn_coors grad")
+        if g.rowptr_j is None:
+            g.rowptr_j, g.perm_j, _, _ = csr_build(g.idx.view(-1), N, None)
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        dMij, dpre3, thid, dw, dsc, grel = f(N, KNN_K, M_DIM), f(E, 4 * M_DIM), f(E, 4 * M_DIM), f(E, 1), f(E, 1), f(E, 3)
+        _call("eqh_egnn_coors_bwd", 1, _p(Mij), _p(x), _p(g.idx), _p(W3), _p(b3), _p(W4), _p(b4), _p(scale), _p(dout), N,
+              _p(dMij), _p(dpre3), _p(thid), _p(dw), _p(dsc), _p(grel), _stream())
+        dx = torch.empty_like(x)
+        _call("eqh_egnn_coors_bwd_pos", 1, _p(dout), _p(grel), _p(g.rowptr_j), _p(g.perm_j), N, _p(dx), _stream())
+        # parameter gradients: contractions over the edges on the deterministic GEMM / column-sum kernels
+        dW3 = gemm_raw(dpre3, False, Mij.view(E, M_DIM), False, 4 * M_DIM, M_DIM, E, splits=0)       # dpre3^T . m
+        db3 = colsum_tall(dpre3)
+        dW4 = colsum_tall(thid, roww=dw.view(-1)).view(1, -1)                                        # t^T . dw
+        db4 = colsum_tall(dw)
+        dscale = colsum_tall(dsc) if scale is not None else None
+        return dMij, dx, dW3, db3, dW4, db4, dscale, None
+
+
+def egnn_coors(Mij, x, W3, b3, W4, b4, scale, graph: "KnnGraph") -> torch.Tensor:
+    return _EgnnCoors.apply(Mij, x, W3, b3, W4, b4, scale, graph)
+
+
 # ----------------------------------------------------------------------------------------------
 # public functional API
 # ----------------------------------------------------------------------------------------------

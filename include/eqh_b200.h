@@ -355,6 +355,43 @@ EQH_API int eqh_adam_step(float* param, const float* grad, float* exp_avg, float
                   eqh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * EGNN coordinate branch phi_x (egnn_layer.py:325-340 + CoorsNorm :71-81):
+ *   coors_out[i] = pos[i] + sum_k w_ik * (pos[i] - pos[j]) * scale / max(|pos[i] - pos[j]|, 1e-8),  j = idx[i,k],
+ *   w_ik = W4 . SiLU(W3 . m_ij[i,k,:] + b3) + b4      (W3 [64,16], b3 [64], W4 [64], b4 [1]; scale NULL = no CoorsNorm)
+ * forward: Mij [N,16,16] (from the edge kernels) -> coors_out [N,3] (+ optional wij [N,16]).
+ * backward (per kNN edge e): dMij [N*16,16], dpre3 / thid [N*16,64], dw / dscale_e [N*16], grel [N*16,3]; the
+ * parameter gradients are dW3 = dpre3^T . Mij, db3 = colsum(dpre3), dW4 = thid^T . dw, db4 = sum(dw),
+ * dscale = sum(dscale_e) (library GEMM / column sums).  eqh_egnn_coors_bwd_pos: dpos = dcoors_out + own-edge minus
+ * incoming-edge sums of grel over the transposed kNN incidence (rowptr_j / perm_j), deterministic.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_egnn_coors_fwd(const float* Mij, const float* pos, const int32_t* idx, const float* W3, const float* b3,
+                       const float* W4, const float* b4, const float* scale, int64_t N, float* coors_out, float* wij,
+                       eqh_stream_t stream);
+EQH_API int eqh_egnn_coors_bwd(const float* Mij, const float* pos, const int32_t* idx, const float* W3, const float* b3,
+                       const float* W4, const float* b4, const float* scale, const float* dcoors_out, int64_t N, float* dMij,
+                       float* dpre3, float* thid, float* dw, float* dscale_e, float* grel, eqh_stream_t stream);
+EQH_API int eqh_egnn_coors_bwd_pos(const float* dcoors_out, const float* grel, const int32_t* rowptr_j, const int32_t* perm_j,
+                           int64_t N, float* dpos, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * nn.BatchNorm1d over atom rows in training mode (mhnn.py:182,206; equihnn_egnn.py:226,246), forward and backward.
+ * Batch statistics over the first n_stat rows (ghost-padded batches keep their padding atoms after the real ones and
+ * out of the statistics), all `rows` rows normalised: y = (x - mean) * rstd * gamma + beta with the biased variance;
+ * running_mean / running_var (optional) are updated with `momentum` and the unbiased variance, num_batches_tracked
+ * (optional int64 scalar) is incremented.  n_stat_dev (optional, device int64) overrides n_stat: the number of real atoms
+ * of a ghost-padded batch changes between replays of one captured graph.  partial: eqh_batchnorm_partial_floats(C) floats.
+ * backward: dx, and dgamma / dbeta (optional; accumulate != 0 adds to their contents).  Deterministic.
+ * ---------------------------------------------------------------------------------------- */
+EQH_API int eqh_batchnorm_partial_floats(int64_t C);
+EQH_API int eqh_batchnorm_fwd(const float* x, int64_t rows, int64_t n_stat, int64_t C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* y, float* save_mean, float* save_rstd, float* running_mean,
+                      float* running_var, int64_t* num_batches_tracked, const int64_t* n_stat_dev, float* partial,
+                      eqh_stream_t stream);
+EQH_API int eqh_batchnorm_bwd(const float* x, const float* dy, int64_t rows, int64_t n_stat, int64_t C, const float* gamma,
+                      const float* save_mean, const float* save_rstd, float* dx, float* dgamma, float* dbeta, int accumulate,
+                      const int64_t* n_stat_dev, float* partial, eqh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Strided / fused-epilogue variants used by the hand-scheduled layer Functions (layers/fused_*.py), so that concat,
  * slice, activation and residual-add launches of the reference's autograd graph (egnn_layer.py:357-362, mlp.py:94-96)
  * never exist as separate kernels.  Row strides are in floats and must be multiples of 4.

@@ -617,3 +617,86 @@ def test_radius_graph_matches_torch_cluster_semantics(r, max_nb, loop):
     want1 = torch.cat([torch.stack((torch.nonzero(ok1[i]).view(-1)[:max_nb],
                                     torch.full((min(int(ok1[i].sum()), max_nb),), i)), 0) for i in range(N)], 1)
     assert torch.equal(got1.cpu(), want1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BatchNorm over atom rows (mhnn.py:206) and the coordinate branch phi_x (egnn_layer.py:325-340) as kernels
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,n_stat,C,as_tensor", [(2330, 2330, 256, False), (2560, 2331, 256, True), (300, 257, 64, True),
+                                                    (70, 70, 32, False)])
+def test_batchnorm_rows_matches_torch(rows, n_stat, C, as_tensor):
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.7)
+    w = torch.randn(rows, C, generator=g)
+    bn_ref = torch.nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.randn(C, generator=g))
+        bn_ref.bias.copy_(torch.randn(C, generator=g))
+        bn_ref.running_mean.copy_(torch.randn(C, generator=g))
+        bn_ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    bn = torch.nn.BatchNorm1d(C)
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn_ref.state_dict().items()})
+    bn = bn.to(DEV).train()
+    bn_ref.train()
+    xr = x[:n_stat].double().requires_grad_(True)
+    yr = bn_ref(xr)
+    (yr * w[:n_stat].double()).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    ns = torch.tensor([n_stat], dtype=torch.int64, device=DEV) if as_tensor else n_stat
+    y = ops.batch_norm_rows(xd, bn, ns)
+    wd = w.to(DEV).clone()
+    wd[n_stat:] = 0                                       # padding rows carry no gradient (they are not in the loss)
+    (y * wd).sum().backward()
+    assert rel_err(y[:n_stat], yr) < TOL
+    assert rel_err(xd.grad[:n_stat], xr.grad) < TOL and float(xd.grad[n_stat:].abs().max() if n_stat < rows else 0.0) == 0.0
+    assert rel_err(bn.weight.grad, bn_ref.weight.grad) < TOL and rel_err(bn.bias.grad, bn_ref.bias.grad) < TOL
+    assert rel_err(bn.running_mean, bn_ref.running_mean) < TOL and rel_err(bn.running_var, bn_ref.running_var) < TOL
+    assert int(bn.num_batches_tracked) == 1
+    # padding rows are normalised with the real rows' statistics
+    if n_stat < rows:
+        mean, var = x[:n_stat].double().mean(0), x[:n_stat].double().var(0, unbiased=False)
+        want = (x[n_stat:].double() - mean) / torch.sqrt(var + bn.eps) * bn_ref.weight.detach() + bn_ref.bias.detach()
+        assert rel_err(y[n_stat:], want) < TOL
+    # direct accumulation into registered gradient buffers (the Trainer's flat buffer)
+    bn.weight.grad.fill_(1.0)
+    bn.bias.grad.fill_(1.0)
+    with ops.direct_grads([bn.weight, bn.bias]):
+        x2 = x.to(DEV).requires_grad_(True)
+        (ops.batch_norm_rows(x2, bn, ns) * wd).sum().backward()
+    assert rel_err(bn.weight.grad - 1.0, bn_ref.weight.grad) < 2 * TOL and torch.equal(x2.grad, xd.grad)
+
+
+@pytest.mark.parametrize("norm_coors", [True, False])
+def test_egnn_coors_kernels_match_oracle(norm_coors):
+    """phi_x forward and backward (every gradient: m_ij, coordinates, coors_mlp, coors_norm.scale) against the fp64
+    restatement of egnn_layer.py:325-340 / :71-81 on a QM9-shaped batch; the self edge (rel = 0) included."""
+    b = synthetic.make_batch("qm9", 12, 31)
+    N = b.num_atoms
+    g = torch.Generator().manual_seed(9)
+    idx, _ = ops.knn16(b.pos.to(DEV))
+    graph = ops.KnnGraph(idx, None, None, None)
+    Mij = torch.randn(N, 16, 16, generator=g)
+    W3, b3 = torch.randn(64, 16, generator=g) * 0.3, torch.randn(64, generator=g) * 0.1
+    W4, b4 = torch.randn(1, 64, generator=g) * 0.3, torch.randn(1, generator=g)
+    scale = torch.tensor([0.37])
+    wout = torch.randn(N, 3, generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (Mij, b.pos, W3, b3, W4, b4, scale)]
+    Mr, xr, W3r, b3r, W4r, b4r, sr = leaves
+    nb = idx.cpu().long()
+    cw = F.linear(F.silu(F.linear(Mr, W3r, b3r)), W4r, b4r).squeeze(-1)                    # [N,16]
+    rel = xr[:, None, :] - xr[nb]
+    if norm_coors:
+        rel = rel / rel.norm(dim=-1, keepdim=True).clamp(min=1e-8) * sr
+    out_r = (cw.unsqueeze(-1) * rel).sum(1) + xr
+    (out_r * wout.double()).sum().backward()
+    dl = [t.to(DEV).requires_grad_(True) for t in (Mij, b.pos, W3, b3, W4, b4, scale)]
+    out = ops.egnn_coors(dl[0], dl[1], dl[2], dl[3], dl[4], dl[5], dl[6] if norm_coors else None, graph)
+    (out * wout.to(DEV)).sum().backward()
+    assert rel_err(out, out_r) < TOL
+    names = ["m_ij", "pos", "W3", "b3", "W4", "b4", "scale"]
+    for nm, got, want in zip(names, dl, leaves):
+        if nm == "scale" and not norm_coors:
+            continue
+        # the reference's own autograd pushes +-1e8-scaled terms through the self edge (rel / clamp(|rel|, 1e-8)); they
+        # cancel exactly in fp64, and the kernel never forms them
+        assert rel_err(got.grad, want.grad) < (2 * TOL), nm

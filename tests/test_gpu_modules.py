@@ -504,6 +504,83 @@ def test_reference_wrappers_run_unchanged_on_the_overlay(name):
         sys.path[:0] = shim_paths
 
 
+def _headline_bad(errs):
+    """errs: {param: (our error vs the verbatim fp64 gradient, the verbatim fp32 run's own error vs it)}.
+    Parameters ABOVE the last ReLU (the reference's fp32 run reproduces fp64 to < 1e-5 there: no gate involved) keep the
+    strict bar 2e-5.  Below a gate, ANY two fp32 evaluation orders differ by a few flipped gates (pre-activations within
+    rounding of zero), each a rank-1 change of the gradients below it; which parameters it hits is a matter of which gates
+    flip, so the yardstick is the reference's fp32 worst case over all gate-affected parameters (x2), and per parameter
+    never more than 8x its own fp32 deviation.  tests: test_conv_layer_gate_controlled_parity pins the same kernels to
+    2e-5 once the gates are held fixed."""
+    noisy = [v[1] for v in errs.values() if v[1] >= 1e-5]
+    floor = 2.0 * max(noisy) if noisy else 0.0
+    bad = {}
+    for k, (e, e_ref) in errs.items():
+        bar = 2e-5 if e_ref < 1e-5 else min(floor, max(8 * e_ref, 2e-5))
+        if e > bar:
+            bad[k] = (e, e_ref, bar)
+    return bad
+
+
+def _gated_mlp64(p, pre, x, gate):
+    """2-layer MLP of the reference (mlp.py:91-99) in fp64 with the ReLU decisions given (gate: bool tensor)."""
+    h = F.linear(x, p[pre + ".lins.0.weight"], p[pre + ".lins.0.bias"])
+    y = F.layer_norm(h * gate, (h.shape[-1],), p[pre + ".normalizations.1.weight"], p[pre + ".normalizations.1.bias"], 1e-5)
+    return F.linear(y, p[pre + ".lins.1.weight"], p[pre + ".lins.1.bias"]), h
+
+
+@pytest.mark.parametrize("profile,B", [("qm9", 128), ("molecule3d", 300)])
+def test_conv_layer_gate_controlled_parity(profile, B):
+    """MHNNSConv at C=256 on BASELINE-sized batches (N ~ 2.3k and ~ 8.7k atoms) against the fp64 oracle WITH THE ReLU GATES
+    HELD FIXED at the CUDA path's own decisions (read from the layer Function's saved pre-activations).  With the gates
+    equal, what is left is rounding: output and every gradient agree to 2e-5 (no 5e-3 floor).  The
+    gates themselves must be the fp64 oracle's except where the pre-activation is within rounding of zero."""
+    from equihgnn_b200.layers.fused_conv import MHNNSConvFused
+    C = 256
+    b = synthetic.make_batch(profile, B, 91)
+    N = b.num_atoms
+    torch.manual_seed(17)
+    m = MHNNSConv(C, mlp1_layers=2, mlp2_layers=2, mlp3_layers=2, aggr="mean", dropout=0.0, normalization="ln")
+    g = torch.Generator().manual_seed(18)
+    X, X0 = torch.randn(N, C, generator=g), torch.randn(N, C, generator=g)
+    w = torch.randn(N, C, generator=g)
+    md = m.to(DEV)
+    Xd, X0d = X.to(DEV).requires_grad_(True), X0.to(DEV).requires_grad_(True)
+    V, E = b.edge_index0.to(DEV), b.edge_index1.to(DEV)
+    inc = ops.build_incidence(V, E, N, b.num_hyperedges)
+    eps = tuple(getattr(md, f"W{k}").normalizations[1].eps for k in (1, 2, 3))
+    out = MHNNSConvFused.apply(Xd, X0d, inc, "mean", 0.5, False, eps, *md._fused_params())
+    saved = out.grad_fn.saved_tensors
+    h1, A, Bm, h3 = saved[1].cpu(), saved[4].cpu(), saved[5].cpu(), saved[8].cpu()
+    (out * w.to(DEV)).sum().backward()
+    # the CUDA path's gate decisions (fp32, the kernel's own arithmetic: one add for the gathered pair)
+    g1, g3 = h1 > 0, h3 > 0
+    pre2 = A[b.edge_index0] + Bm[b.edge_index1]
+    g2 = pre2 > 0
+    # fp64 oracle with these gates
+    p = {"c." + k: v.detach().cpu().double().requires_grad_(True) for k, v in md.state_dict().items()}
+    Xr, X0r = X.double().requires_grad_(True), X0.double().requires_grad_(True)
+    Y, h1r = _gated_mlp64(p, "c.W1", Xr, g1)                                          # conv.py:172
+    Xe = R.scatter_rows(Y[b.edge_index0], b.edge_index1, b.num_hyperedges, "mean")    # conv.py:173
+    Xev, h2r = _gated_mlp64(p, "c.W2", torch.cat([Xr[b.edge_index0], Xe[b.edge_index1]], -1), g2)   # conv.py:175-176
+    Xv = R.scatter_rows(Xev, b.edge_index0, N, "mean")                                # conv.py:177
+    outr, h3r = _gated_mlp64(p, "c.W3", 0.5 * Xv + 0.5 * X0r, g3)                     # conv.py:179-180
+    (outr * w.double()).sum().backward()
+    TOLG = 2e-5
+    assert rel_err(out, outr) < TOLG
+    assert rel_err(Xd.grad, Xr.grad) < TOLG and rel_err(X0d.grad, X0r.grad) < TOLG
+    got = {k: q.grad for k, q in md.named_parameters()}
+    scale = max(float(v.grad.abs().max()) for v in p.values())
+    for k, q in got.items():
+        den = max(float(p["c." + k].grad.abs().max()), 0.05 * scale)
+        assert float((q.cpu().double() - p["c." + k].grad).abs().max()) / den < TOLG, k
+    # the gates are the oracle's own wherever the pre-activation is not within rounding of zero
+    for gate, pre in ((g1, h1r), (g2, h2r), (g3, h3r)):
+        flipped = gate != (pre.detach() > 0)
+        if bool(flipped.any()):
+            assert float(pre.detach()[flipped].abs().max()) < 1e-5 * float(pre.detach().abs().max())
+
+
 def test_headline_shape_matches_the_verbatim_reference():
     """BASELINE configs[1] (the bench workload: QM9-shaped batch 128, C=256, L=3) against the VERBATIM reference run at
     that shape.  Predictions and loss to 5e-5 / 1e-5.  Gradients: the fixture also holds the verbatim
@@ -521,7 +598,7 @@ def test_headline_shape_matches_the_verbatim_reference():
     assert rel_err(pred, fx["pred64"]) < TOL_MODEL and rel_err(pred, fx["pred"]) < TOL_MODEL
     assert abs(float(loss.detach()) - float(fx["loss64"])) < 1e-5 * abs(float(fx["loss64"]))
     errs = headline_grad_errors(_named_grads(m), fx)
-    bad = {k: v for k, v in errs.items() if v[0] > max(2e-5, 4 * v[1])}
+    bad = _headline_bad(errs)
     assert not bad, bad
     # ... and through the Trainer's hand-scheduled layer Functions (the path the bench times)
     from equihgnn_b200.train import Trainer
@@ -531,7 +608,7 @@ def test_headline_shape_matches_the_verbatim_reference():
     torch.cuda.synchronize()
     assert abs(float(loss2) - float(fx["loss64"])) < 1e-5 * abs(float(fx["loss64"]))
     errs2 = headline_grad_errors({k: q.grad for k, q in tr.model.named_parameters()}, fx)
-    bad2 = {k: v for k, v in errs2.items() if v[0] > max(2e-5, 4 * v[1])}
+    bad2 = _headline_bad(errs2)
     assert not bad2, bad2
     tr.close()
 
