@@ -83,7 +83,7 @@ struct GroupParams {
 // ep_tid: 0..127 index of the thread among the four epilogue warps; full_parity: phase of tmem_full to wait for;
 // tmem_empty (optional): arrived on by every epilogue thread once the accumulators are in registers / staged, so a
 // persistent kernel can start the next tile's MMAs into this buffer while the stores are still in flight.
-template <int BN, class AM>
+template <int BN, class AM, bool STORE = true>
 __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint32_t tmem_base, uint64_t* tmem_full, int warp,
                                               int lane, int nkb, const Params& p, int m0, int n0, int ep_tid = -1,
                                               uint32_t full_parity = 0, uint64_t* tmem_empty = nullptr, int split_idx = -1) {
@@ -171,6 +171,10 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty);
     }
+    if constexpr (!STORE) {       // the caller stores the staged tile with every thread of the CTA (epilogue_store_all)
+      if (ep_tid == 0) EQH_STAMP(7);
+      return;
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
     if (ep_tid == 0) EQH_STAMP(7);
     float* out = final_out ? p.D : p.ws + (size_t)(split_idx >= 0 ? split_idx : (int)blockIdx.z) * p.M * p.N;
@@ -234,6 +238,75 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
         }
       }
     }
+}
+
+// Store phase of the epilogue executed by ALL threads of the CTA (after a CTA-wide barrier that follows the staging of
+// epilogue_tile<.., STORE = false>): the 128 x BN tile staged in shared memory (pitch BN + 4) goes to global memory as
+// coalesced float4 rows, + the fused SiLU-derivative factor and the residual.  With the four epilogue warps alone the
+// store loop was 1.3 us of a 6.9 us CTA (scratch/trace_ts.py); the other six warps are idle by then.
+template <int BN>
+__device__ __forceinline__ void epilogue_store_all(const uint8_t* smem, const Params& p, int m0, int n0, int split_idx) {
+  constexpr int PITCH = BN + 4;
+  constexpr int C4 = BN / 4;
+  const float* stage_out = reinterpret_cast<const float*>(smem);
+  const bool final_out = (p.ws == nullptr);
+  float* out = final_out ? p.D : p.ws + (size_t)split_idx * p.M * p.N;
+  const int64_t ld = final_out ? p.ldd : p.N;
+  const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool has_res = final_out && p.residual != nullptr;
+  const bool has_aux = final_out && p.dsilu_aux != nullptr;
+  const bool aux_vec = has_aux && (p.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dsilu_aux) & 15) == 0);
+  const int rows_here = min(BM, p.M - m0);
+  const int total = rows_here * C4;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 2 * kThreads) {
+    float4 x[2], rr[2], a4[2];
+    int rr_[2], n_[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = e0 + u * kThreads;
+      ok[u] = e < total;
+      const int r = ok[u] ? e / C4 : 0, c = ok[u] ? (e - r * C4) * 4 : 0;
+      rr_[u] = r; n_[u] = n0 + c;
+      ok[u] = ok[u] && n_[u] < p.N;
+      if (!ok[u]) continue;
+      x[u] = *reinterpret_cast<const float4*>(stage_out + r * PITCH + c);
+      const bool full = vec_ok && n_[u] + 4 <= p.N;
+      if (has_res && full) rr[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)(m0 + r) * ld + n_[u]);   // may alias D
+      if (has_aux) {
+        const float* ap = p.dsilu_aux + (int64_t)(m0 + r) * p.ld_aux + n_[u];
+        if (aux_vec && n_[u] + 4 <= p.N) a4[u] = __ldg(reinterpret_cast<const float4*>(ap));
+        else a4[u] = make_float4(__ldg(ap), n_[u] + 1 < p.N ? __ldg(ap + 1) : 0.f, n_[u] + 2 < p.N ? __ldg(ap + 2) : 0.f,
+                                 n_[u] + 3 < p.N ? __ldg(ap + 3) : 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int r = rr_[u], n = n_[u];
+      if (has_aux) {
+        x[u].x *= dsilu_f(a4[u].x); x[u].y *= dsilu_f(a4[u].y); x[u].z *= dsilu_f(a4[u].z); x[u].w *= dsilu_f(a4[u].w);
+      }
+      float* dst = out + (int64_t)(m0 + r) * ld + n;
+      if (vec_ok && n + 4 <= p.N) {
+        if (has_res) {
+          x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
+          x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
+        }
+        *reinterpret_cast<float4*>(dst) = x[u];
+      } else {
+        const float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n + j < p.N) {
+            float t = v[j];
+            if (has_res) t += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
+            dst[j] = t;
+          }
+        }
+      }
+    }
+  }
 }
 
 // Split-K finish, executed by the whole CTA after its partial tile is written (includes the block barriers).

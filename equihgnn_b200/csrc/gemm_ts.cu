@@ -83,6 +83,10 @@ __device__ __forceinline__ void gemm_ts_tile(const CUtensorMap* __restrict__ ptm
   __shared__ int s_last;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) {       // the descriptors live in the kernel's parameter space: start their fetch before the setup
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ptmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ptmB)) : "memory");
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = bx * BN, m0 = by * BM;
   if (threadIdx.x == 0) EQH_STAMP(0);
@@ -214,7 +218,7 @@ __device__ __forceinline__ void gemm_ts_tile(const CUtensorMap* __restrict__ ptm
       if (r == 0 && i < 8) EQH_STAMP(40 + i);
     }
     // ===================== epilogue (same warps) =====================
-    epilogue_tile<BN, AM>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0, -1, 0, nullptr, bz);
+    epilogue_tile<BN, AM, false>(smem, sbias, tmem_base, tmem_full, warp, lane, nkb, p, m0, n0, -1, 0, nullptr, bz);
   } else {
     // ===================== B split (hi / lo): warps 2, 3, 8, 9 =====================
     const int t = ((warp < 4 ? warp - 2 : warp - 6) << 5) + lane;      // 0..127
@@ -243,10 +247,14 @@ __device__ __forceinline__ void gemm_ts_tile(const CUtensorMap* __restrict__ ptm
   }
   if (threadIdx.x == 128) EQH_STAMP(8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (p.ws != nullptr) __threadfence();       // this split's partial tile is visible device-wide before the arrival
-  __syncthreads();
+  __syncthreads();                            // the tile is staged in shared memory, every TMEM read has completed
   if (warp == 2) tmem_dealloc(tmem_base, 512);
-  if (p.ws != nullptr) splitk_finish<BN>(p, m0, n0, &s_last, tile, nz);
+  epilogue_store_all<BN>(smem, p, m0, n0, bz);     // all ten warps store
+  if (p.ws != nullptr) {
+    __threadfence();                          // this split's partial tile is visible device-wide before the arrival
+    __syncthreads();
+    splitk_finish<BN>(p, m0, n0, &s_last, tile, nz);
+  }
 }
 
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>

@@ -340,7 +340,8 @@ class _SideWork:
     @contextlib.contextmanager
     def _forked(self, device, keep):
         side = self.stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))
+        origin = torch.cuda.current_stream(device)
+        side.wait_stream(origin)
         key = side.device.index
         first = not self.pending.get(key)
         self.pending.setdefault(key, []).extend(keep)
@@ -348,9 +349,12 @@ class _SideWork:
             self.pending[key].append(None)
         if first:
             # whoever reads the gradients after backward() returns must see them: join at the end of this backward
-            # pass (the Trainer joins explicitly as well; a second join is a no-op)
+            # pass (the Trainer joins explicitly as well; a second join is a no-op).  The engine may run its final
+            # callbacks on a worker thread whose current stream is NOT the stream the backward ran on (during a graph
+            # capture that is an uncaptured stream: cudaErrorStreamCaptureIsolation), so the callback joins into the
+            # stream this fork came from.
             try:
-                torch.autograd.Variable._execution_engine.queue_callback(lambda k=key: self.join(k))
+                torch.autograd.Variable._execution_engine.queue_callback(lambda k=key, o=origin: self.join(k, stream=o))
             except RuntimeError:
                 pass                      # not inside a backward pass: the caller joins
         self.active += 1                  # GEMMs planned inside are "background" work (see eqh_gemm_plan flag 0x8000)
@@ -360,14 +364,14 @@ class _SideWork:
         finally:
             self.active -= 1
 
-    def join(self, device=None) -> None:
-        """Make the current stream wait for all side work issued so far (no-op when there is none)."""
+    def join(self, device=None, stream=None) -> None:
+        """Make `stream` (default: the current stream) wait for all side work issued so far (no-op when there is none)."""
         keys = list(self.pending) if device is None else [torch.device(device).index
                                                           if torch.device(device).index is not None
                                                           else torch.cuda.current_device()]
         for key in keys:
             if self.pending.get(key):
-                torch.cuda.current_stream(key).wait_stream(self.streams[key])
+                (stream if stream is not None else torch.cuda.current_stream(key)).wait_stream(self.streams[key])
                 self.pending[key] = []
 
 
