@@ -120,6 +120,7 @@ class GraphedTrainer(Trainer):
         self.B = real_graphs
         self.buckets: Dict[Tuple[int, int, int, int], _Bucket] = {}
         self._pool = None
+        self._cap_stream = None
         self.replays = 0
         self.own_launches = 0
         legal = (not self.distributed) or uniform_shapes
@@ -155,7 +156,14 @@ class GraphedTrainer(Trainer):
         buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
         if self.in_graph_step:
             buffers += [(t, t.detach().clone()) for t in (self.fp.flat, self.exp_avg, self.exp_avg_sq, self.step_dev)]
-        s = torch.cuda.Stream()
+        # Warm-up and capture run on ONE persistent stream.  The autograd engine ties every AccumulateGrad node to the stream
+        # that was current when it was created and, at the end of a backward, makes the caller's stream wait for all of
+        # them -- also for those that received no gradient because the kernels accumulate into the flat buffer directly.
+        # A node that survived from the warm-up on a different (uncaptured) stream would make the capturing stream wait
+        # on uncaptured work (cudaErrorStreamCaptureIsolation); with one stream the engine has nothing to synchronise.
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("EQH_CAPTURE_PRIORITY", "0")))
+        s = self._cap_stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
@@ -178,9 +186,7 @@ class GraphedTrainer(Trainer):
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
             kw["pool"] = self._pool
-        prio = int(os.environ.get("EQH_CAPTURE_PRIORITY", "0"))
-        if prio != 0:
-            kw["stream"] = torch.cuda.Stream(priority=prio)
+        kw["stream"] = self._cap_stream
         if self.distributed and self.in_graph_step:
             kw["capture_error_mode"] = "thread_local"      # NCCL's own threads may touch the CUDA API during the capture
         with torch.cuda.graph(g, **kw):
