@@ -118,8 +118,10 @@ class EGNNFused(torch.autograd.Function):
             gemm_raw(dPQ[:, Hp:], False, h, False, Hp, C, N, splits=0, out=T[Hp:])     # the dQ half, next to the dh GEMM
             _call("eqh_egnn_unpack_grads", 1, _p(T), _p(red), H0, C, Hp, _p(sink.out[id(w1)]), _p(sink.out[id(w2)]),
                   _p(sink.out[id(b2)]), _stream())
-        # dh = dh0 + [dP | dQ] . [W1a ; W1b]   (K = 2 Hp: split-K chosen by the planner, residual added by its finish)
-        dh = gemm_raw(dPQ, True, W1ab, False, N, C, 2 * Hp, residual=dh0, splits=0)
+        # dh = dh0 + [dP | dQ] . [W1a ; W1b]   (K = 2 Hp; small batches: split-K chosen by the planner, residual added by its finish)
+        # (large batches fill the GPU with output tiles alone: the persistent no-split kernel; measured at Molecule3D-1024
+        # 365 us with the planner's split vs ~180 us)
+        dh = gemm_raw(dPQ, True, W1ab, False, N, C, 2 * Hp, residual=dh0, splits=0 if N < 8192 else 1)
         return (dh, None, None, None) + (None,) * 10
 
 
