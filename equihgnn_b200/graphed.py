@@ -134,6 +134,17 @@ class GraphedTrainer(Trainer):
         self._loss_evt = [None, None]
         self._issued = 0
 
+    def release(self) -> None:
+        """Drop the captured graphs (and with them the NCCL work captured inside).  Call before
+        `torch.distributed.destroy_process_group()`: tearing the communicator down while live graphs still reference its
+        kernels blocks in the destroy."""
+        torch.cuda.synchronize()
+        self.buckets.clear()
+        self._pool = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def _fwd_bwd(self, data) -> torch.Tensor:
         self.fp.zero_grad()
         loss = model_loss(self.model, data, self.B)                    # the ghost molecule is not in the loss

@@ -692,6 +692,9 @@ def _ddp_worker(rank, world, port, out_dir):
         dist.all_gather(flats, a.fp.flat)
         assert all(torch.equal(flats[0], f) for f in flats[1:])                                # ranks stay in lock step
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+        a.release()                      # graphs holding captured NCCL work go before the communicator
+        b.release()
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
