@@ -794,15 +794,17 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None, dres
 
 
-LINEAR_MIN_ROWS = 64
-
-
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, act: Optional[str] = None,
            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """nn.Linear (+ optional fused ReLU / residual) for 2-D fp32 CUDA rows.  Shapes the tensor-core kernel does
-    not take (tiny row counts, K or N not a multiple of 4) go to the library GEMM."""
+    """nn.Linear (+ optional fused ReLU / residual) for 2-D fp32 CUDA rows on the tcgen05 GEMM.
+
+    Two documented exceptions go to torch's own Linear instead of this library's kernel, both outside the hot path:
+      * CPU tensors: the drop-in modules can be constructed, inspected and compared with the reference on the host
+        (tests/test_cpu_host.py); nothing is computed on the CPU by a training step (the C ABI raises on CPU pointers);
+      * K or N not a multiple of 4 (TMA needs 16-byte row strides): in the shipped models that is only the last readout
+        Linear with one target (N = 1), which the Trainer path replaces by the fused head + loss kernel (ops.head_mse)."""
     K, N = x.shape[-1], w.shape[0]
-    if x.dim() != 2 or x.shape[0] < LINEAR_MIN_ROWS or K % 4 or N % 4 or not x.is_cuda or x.dtype != torch.float32:
+    if not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32 or K % 4 or N % 4 or x.shape[0] == 0:
         y = torch.nn.functional.linear(x, w, b)
         if act == "relu":
             y = torch.relu(y)

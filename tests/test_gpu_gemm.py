@@ -262,3 +262,23 @@ def test_gemm_grouped_forward_layout_and_epilogue_extras():
     D = ops.gemm_raw(big, True, Wb, True, 30000, 512, 256, act="silu", stash=st)
     pre = big.double() @ Wb.double().t()
     assert rel_err(st, pre) < 2e-6 and rel_err(D, torch.nn.functional.silu(pre)) < 2e-6
+
+
+@pytest.mark.parametrize("M", [1, 7, 25, 63])
+def test_gemm_tiny_row_counts(M):
+    """Pooled readout rows (one per molecule): fewer rows than one tile, forward, dgrad and wgrad layouts."""
+    g = torch.Generator().manual_seed(M)
+    N, K = 128, 256
+    A, B, bias = _mk((M, K), g), _mk((N, K), g, 0.06), _mk((N,), g)
+    assert rel_err(ops.gemm_raw(A, True, B, True, M, N, K, bias=bias, act="relu"),
+                   torch.relu(A.double() @ B.double().t() + bias.double())) < 2e-6
+    dY, W = _mk((M, N), g), _mk((N, K), g, 0.06)
+    assert rel_err(ops.gemm_raw(dY, True, W, False, M, K, N), dY.double() @ W.double()) < 2e-6
+    assert rel_err(ops.gemm_raw(dY, False, A, False, N, K, M, splits=0), dY.double().t() @ A.double()) < 2e-6
+    x = A.clone().requires_grad_(True)
+    w = B.clone().requires_grad_(True)
+    y = ops.linear(x, w, bias, act="relu")
+    y.sum().backward()
+    xr, wr = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    torch.relu(xr @ wr.t() + bias.double()).sum().backward()
+    assert rel_err(x.grad, xr.grad) < 2e-6 and rel_err(w.grad, wr.grad) < 2e-6
