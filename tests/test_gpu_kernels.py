@@ -700,3 +700,89 @@ def test_egnn_coors_kernels_match_oracle(norm_coors):
         # the reference's own autograd pushes +-1e8-scaled terms through the self edge (rel / clamp(|rel|, 1e-8)); they
         # cancel exactly in fp64, and the kernel never forms them
         assert rel_err(got.grad, want.grad) < (2 * TOL), nm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# out-of-bounds write canaries (compute-sanitizer is not available on this GPU pool: profiles/r02_sanitizer.md)
+# ----------------------------------------------------------------------------------------------------------------------
+class _Canary:
+    """Carves output buffers out of one sentinel-filled arena with guard bands around each, so that any write outside an
+    output's own rows / columns is detected afterwards."""
+    SENT = -7.5e33
+
+    def __init__(self, floats=1 << 24):
+        self.arena = torch.full((floats,), self.SENT, dtype=torch.float32, device=DEV)
+        self.off = 4096
+        self.claims = []
+
+    def matrix(self, rows, cols, ld=None):
+        """[rows, cols] view with row stride ld >= cols inside the arena (the ld - cols gap columns are guards too)."""
+        ld = cols if ld is None else ld
+        start = (self.off + 63) // 64 * 64
+        n = rows * ld
+        self.off = start + n + 4096
+        assert self.off < self.arena.numel()
+        v = self.arena[start:start + n].view(rows, ld)[:, :cols]
+        self.claims.append((start, rows, cols, ld))
+        return v
+
+    def check(self):
+        torch.cuda.synchronize()
+        mask = torch.ones_like(self.arena, dtype=torch.bool)
+        for start, rows, cols, ld in self.claims:
+            m = mask[start:start + rows * ld].view(rows, ld)
+            m[:, :cols] = False
+        guards = self.arena[mask]
+        assert bool((guards == self.SENT).all()), "a kernel wrote outside its output"
+        for start, rows, cols, ld in self.claims:       # ... and every claimed element was written
+            v = self.arena[start:start + rows * ld].view(rows, ld)[:, :cols]
+            assert not bool((v == self.SENT).any()), "an output element was left unwritten"
+
+
+def test_kernels_write_only_their_outputs():
+    """Guard-band canaries around the outputs of the pointer-heavy kernels, on ragged shapes (rows / columns that do not
+    fill a tile, strided column-block outputs): nothing outside the output is written, everything inside is."""
+    from equihgnn_b200.ops import _call, _p, _stream
+    g = torch.Generator().manual_seed(77)
+    cz = _Canary()
+    # --- GEMM: ragged M / N, strided output, split-K, grouped launch, epilogue extras
+    for (M, N, K) in [(300, 72, 272), (129, 520, 64), (2341, 256, 256), (7, 128, 256)]:
+        A, B = torch.randn(M, K, generator=g).to(DEV), torch.randn(N, K, generator=g).to(DEV)
+        ops.gemm_raw(A, True, B, True, M, N, K, out=cz.matrix(M, N, ld=N + 12))
+        W = torch.randn(K, N, generator=g).to(DEV)
+        ops.gemm_raw(A, True, W, False, M, N, K, out=cz.matrix(M, N))
+    dY, X = torch.randn(2341, 72, generator=g).to(DEV), torch.randn(2341, 136, generator=g).to(DEV)
+    ops.gemm_raw(dY, False, X, False, 72, 136, 2341, splits=0, out=cz.matrix(72, 136, ld=140))
+    grp = ops.GemmGroup(DEV, False, False)
+    for _ in range(3):
+        grp.add(dY, X, 72, 136, 2341, cz.matrix(72, 136, ld=144))
+    grp.run()
+    A, B = torch.randn(300, 272, generator=g).to(DEV), torch.randn(136, 272, generator=g).to(DEV)
+    out, stash = cz.matrix(300, 136, ld=140), cz.matrix(300, 136, ld=140)
+    ops.gemm_raw(A, True, B, True, 300, 136, 272, act="silu", out=out, stash=stash)
+    # --- segmented reduction / row LayerNorm into a column block of a wider matrix
+    b = synthetic.make_batch("qm9", 16, 5)
+    inc = ops.build_incidence(b.edge_index0.to(DEV), b.edge_index1.to(DEV), b.num_atoms, b.num_hyperedges)
+    C = 64
+    src = torch.randn(inc.Z, C, generator=g).to(DEV)
+    o = cz.matrix(inc.E, C, ld=C + 32)
+    _call("eqh_gather_reduce_ld", 1, _p(src), C, _p(inc.perm_e), _p(inc.rowptr_e), None, inc.E, C, ops.MEAN, o.data_ptr(),
+          C + 32, _stream())
+    x = torch.randn(b.num_atoms, C, generator=g).to(DEV)
+    gam, bet = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    o = cz.matrix(b.num_atoms, C, ld=C + 16)
+    _call("eqh_rowln_fwd_ld", 1, _p(x), C, _p(gam), _p(bet), 1e-5, 1, b.num_atoms, C, o.data_ptr(), C + 16, _stream())
+    # --- neighbour search, phi_e forward with m_i written into a column block
+    N = b.num_atoms
+    idx, d2 = cz.matrix(N, 16), cz.matrix(N, 16)
+    _call("eqh_knn", 1, _p(b.pos.to(DEV)), N, 16, None, None, 0, idx.data_ptr(), d2.data_ptr(), _stream())
+    cz.check()
+    idx32 = idx.contiguous().view(torch.int32)
+    Hp = 192
+    PQ = torch.randn(N, 2 * Hp, generator=g).to(DEV) * 0.1
+    wc, W2, b2 = (torch.randn(*s, generator=g).to(DEV) * 0.1 for s in ((Hp,), (16, Hp), (16,)))
+    S2 = cz.matrix(N * 16, 16)
+    ni = cz.matrix(N, 16, ld=C + 16)                 # m_i next to (unwritten here) LayerNorm columns: ld gap = guards
+    _call("eqh_egnn_edge_fwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2), _p(b2), _p(idx32), _p(d2.contiguous()),
+          N, Hp, S2.data_ptr(), None, ni.data_ptr(), C + 16, None, _stream())
+    cz.check()
