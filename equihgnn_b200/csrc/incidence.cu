@@ -51,6 +51,76 @@ __global__ void __launch_bounds__(1024) k_scan(const int32_t* cnt, int64_t n, in
   if (t == 1023) rowptr[n] = part[1023];
 }
 
+// Multi-CTA exclusive scan for long count arrays (the single CTA above walks n / 1024 counts per thread serially: 98 us for
+// the transposed kNN incidence of a Molecule3D-1024 batch).  Two launches: every CTA sums its contiguous chunk, then every
+// CTA adds up the (<= kScanBlocks) chunk sums before it and scans its own chunk with a block-wide scan.  Integer sums:
+// the result does not depend on the order.
+constexpr int kScanBlocks = 2 * kSMs;
+
+__global__ void __launch_bounds__(256) k_scan_partial(const int32_t* __restrict__ cnt, int64_t n, int64_t per,
+                                                       int32_t* __restrict__ block_sum) {
+  pdl_prologue();
+  __shared__ int32_t red[8];
+  const int64_t lo = blockIdx.x * per, hi = min(n, lo + per);
+  int32_t s = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s += cnt[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    block_sum[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const int32_t* cnt, int64_t n, int64_t per,
+                                                     const int32_t* __restrict__ block_sum, int nblocks, int32_t* rowptr,
+                                                     int32_t* cursor /* may alias cnt */) {
+  pdl_prologue();
+  __shared__ int32_t warp_tot[8];
+  __shared__ int32_t base_s;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib == 0) {                                    // offset of this chunk: sum of the chunk sums before it
+    int32_t b = 0;
+    for (int k = lane; k < (int)blockIdx.x; k += 32) b += __ldg(block_sum + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
+    if (lane == 0) base_s = b;
+  }
+  __syncthreads();
+  int32_t run = base_s;
+  const int64_t lo = blockIdx.x * per, hi = min(n, lo + per);
+  for (int64_t i0 = lo; i0 < hi; i0 += 256) {
+    const int64_t i = i0 + threadIdx.x;
+    const int32_t c = i < hi ? cnt[i] : 0;
+    int32_t inc = c;                                 // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[wib] = inc;
+    __syncthreads();
+    int32_t wbase = 0, tile = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int32_t t = warp_tot[w];
+      if (w < wib) wbase += t;
+      tile += t;
+    }
+    if (i < hi) {
+      const int32_t ex = run + wbase + inc - c;
+      rowptr[i] = ex;
+      cursor[i] = ex;
+    }
+    run += tile;
+    __syncthreads();
+  }
+  if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) rowptr[n] = run;
+}
+
 template <typename IdxT>
 __global__ void k_place(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, int32_t* __restrict__ cursor,
                         int32_t* __restrict__ slot_z) {
@@ -63,11 +133,14 @@ __global__ void k_place(const IdxT* __restrict__ dst, int64_t Z, int64_t n_dst, 
   slot_z[p] = (int32_t)z;
 }
 
+constexpr int kOrderStage = 1024;     // segment length up to which k_order stages the segment in shared memory
+
 // one warp per segment: order the segment's incidence ids ascending by counting ranks.
 template <typename IdxT>
 __global__ void k_order(const int32_t* __restrict__ rowptr, int64_t n_dst, const int32_t* __restrict__ slot_z,
                         const IdxT* __restrict__ other, int32_t* __restrict__ perm, int32_t* __restrict__ other_sorted) {
   pdl_prologue();
+  __shared__ int32_t order_stage[8][kOrderStage];
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -80,6 +153,22 @@ __global__ void k_order(const int32_t* __restrict__ rowptr, int64_t n_dst, const
 #pragma unroll 4
       for (int k = 0; k < len; ++k) rank += (__shfl_sync(kFull, mine, k) < mine);
       if (lane < len) {
+        perm[lo + rank] = mine;
+        if (other_sorted) other_sorted[lo + rank] = (int32_t)other[mine];
+      }
+    } else if (len <= kOrderStage) {
+      // long segment (a conjugated hyperedge of an OPV polymer, a hub atom of the transposed kNN incidence, the ghost
+      // segment of a padded batch): staged once in shared memory, ranks counted from there (broadcast reads) instead of
+      // len^2 global loads
+      int32_t* stage = order_stage[threadIdx.x >> 5];
+      __syncwarp();
+      for (int32_t a = lane; a < len; a += 32) stage[a] = slot_z[lo + a];
+      __syncwarp();
+      for (int32_t a = lane; a < len; a += 32) {
+        const int32_t mine = stage[a];
+        int32_t rank = 0;
+#pragma unroll 8
+        for (int32_t b = 0; b < len; ++b) rank += (stage[b] < mine);
         perm[lo + rank] = mine;
         if (other_sorted) other_sorted[lo + rank] = (int32_t)other[mine];
       }
@@ -110,7 +199,16 @@ static int build(const IdxT* dst, const IdxT* other, int64_t Z, int64_t n_dst, i
   const int T = 256;
   if (Z > 0) launch_kernel(k_hist<IdxT>, dim3((unsigned)((Z + T - 1) / T)), dim3(T), 0, st, dst, Z, n_dst, cnt, dst32, status);
   // in-place: the scan reads cnt[i] before overwriting cursor[i] (same thread, same i)
-  launch_kernel(k_scan, dim3(1), dim3(1024), 0, st, cnt, n_dst, rowptr, cnt);
+  if (n_dst <= 16384) {
+    launch_kernel(k_scan, dim3(1), dim3(1024), 0, st, cnt, n_dst, rowptr, cnt);
+  } else {
+    int32_t* block_sum = slot_z + Z;                 // [kScanBlocks] behind the slot list
+    int64_t per = (n_dst + kScanBlocks - 1) / kScanBlocks;
+    per = (per + 255) / 256 * 256;
+    const int nblocks = (int)((n_dst + per - 1) / per);
+    launch_kernel(k_scan_partial, dim3((unsigned)nblocks), dim3(256), 0, st, cnt, n_dst, per, block_sum);
+    launch_kernel(k_scan_apply, dim3((unsigned)nblocks), dim3(256), 0, st, cnt, n_dst, per, block_sum, nblocks, rowptr, cnt);
+  }
   if (Z > 0) {
     launch_kernel(k_place<IdxT>, dim3((unsigned)((Z + T - 1) / T)), dim3(T), 0, st, dst, Z, n_dst, cnt, slot_z);
     int64_t warps = n_dst;
@@ -148,7 +246,7 @@ int eqh_pool_index(const int64_t* ptr, int64_t num_graphs, const int64_t* batch,
 
 size_t eqh_incidence_workspace_bytes(int64_t Z, int64_t n_dst) {
   if (Z < 0 || n_dst < 0) return 0;
-  return sizeof(int32_t) * (size_t)(n_dst + 1 + Z);
+  return sizeof(int32_t) * (size_t)(n_dst + 1 + Z + eqh::kScanBlocks);
 }
 
 int eqh_incidence_build_i64(const int64_t* dst, const int64_t* other, int64_t Z, int64_t n_dst, int32_t* rowptr,
