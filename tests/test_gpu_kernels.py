@@ -23,7 +23,8 @@ def _ref_csr(dst, n):
 
 
 @pytest.mark.parametrize("Z,n,seed", [(0, 5, 0), (1, 1, 1), (1000, 37, 2), (5000, 5000, 3), (4096, 3, 4),
-                                      (20000, 1, 5), (70000, 30000, 6)])
+                                      (20000, 1, 5), (70000, 30000, 6), (20000, 100, 7), (40000, 47, 8),
+                                      (500000, 31000, 9)])
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_incidence_build_bit_exact(Z, n, seed, dtype):
     g = torch.Generator().manual_seed(seed)
