@@ -62,6 +62,10 @@ struct Params {
   float* stash;
   const float* dsilu_aux;
   int64_t ld_aux;
+  // second bias [N], added unscaled AFTER the activation and out_scale:  D = out_scale * act(A.B^T + bias * rowscale) + bias2
+  // + res_scale * residual  (two Linears merged into one GEMM keep the outer Linear's bias separate from the inner one's,
+  // which carries the row scale / mix factor)
+  const float* bias2;
 };
 
 // A group of independent problems launched as one grid (gemm_ts.cu: k_gemm_ts_grouped)
@@ -102,7 +106,10 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
     // bias tile -> shared memory once (zero outside N), so the element loop has no bounds checks
     {
       const int tt = ep_tid;
-      if (tt < BN) sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
+      if (tt < BN) {
+        sbias[tt] = (final_out && p.bias && n0 + tt < p.N) ? __ldg(p.bias + n0 + tt) : 0.f;
+        sbias[BN + tt] = (final_out && p.bias2 && n0 + tt < p.N) ? __ldg(p.bias2 + n0 + tt) : 0.f;
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int act = final_out ? p.act : 0;
@@ -163,9 +170,11 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
         for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < 32; j += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(sbias + BN + c0 + j);     // bias2 (zero when absent)
         *reinterpret_cast<float4*>(stage_out + row * PITCH + c0 + j) =
-            make_float4(v[j] * osc, v[j + 1] * osc, v[j + 2] * osc, v[j + 3] * osc);
+            make_float4(v[j] * osc + c4.x, v[j + 1] * osc + c4.y, v[j + 2] * osc + c4.z, v[j + 3] * osc + c4.w);
+      }
     }
     if (tmem_empty != nullptr) {                         // all TMEM reads of this thread are complete
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

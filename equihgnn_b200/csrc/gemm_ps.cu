@@ -49,7 +49,7 @@ constexpr uint32_t kBBytes = BN * BK * 4;                // 8 KB
 constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;  // 32 KB
 constexpr size_t kRing = (size_t)SB * kStageBytes;
 constexpr size_t kStaging = (size_t)BM * (BN + 4) * 4;   // epilogue staging, separate from the ring
-constexpr size_t kSmem = kRing + kStaging + 1024 + BN * 4;
+constexpr size_t kSmem = kRing + kStaging + 1024 + 2 * BN * 4;
 constexpr uint32_t kAccBuf = 3 * BN;                     // 192 columns per accumulator buffer
 constexpr uint32_t kAcol = 2 * kAccBuf;                  // 384
 static_assert(kAcol + SA * 64 <= 512, "TMEM budget");

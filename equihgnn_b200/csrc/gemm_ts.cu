@@ -52,7 +52,7 @@ struct TsCfg {
   static constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;
   static constexpr uint32_t kAcol = AccMap<BN>::NA * BN; // first TMEM column of the A ring
   static constexpr size_t kRing = (size_t)SB * kStageBytes;
-  static constexpr size_t kSmem = kRing + 512 + BN * 4;         // ring + barriers + bias tile
+  static constexpr size_t kSmem = kRing + 512 + 2 * BN * 4;     // ring + barriers + bias / bias2 tiles
   static_assert(kAcol + SA * 64 <= 512, "TMEM budget");
   static_assert(kRing >= (size_t)BM * (BN + 4) * 4, "epilogue staging must fit in the B ring");
 };

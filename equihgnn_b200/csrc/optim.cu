@@ -65,9 +65,30 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   }
 }
 
+__global__ void __launch_bounds__(256) k_rank1(float* __restrict__ out, int64_t ld, const float* __restrict__ u,
+                                                const float* __restrict__ v, int64_t M, int64_t N, float scale) {
+  pdl_prologue();
+  const int64_t total = M * N;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / N, n = t - m * N;
+    out[m * ld + n] += scale * __ldg(u + m) * __ldg(v + n);
+  }
+}
+
 }  // namespace eqh
 
 extern "C" {
+
+int eqh_rank1_update(float* out, int64_t ld, const float* u, const float* v, int64_t M, int64_t N, float scale,
+                     eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(M >= 0 && N >= 0 && ld >= N && (M * N == 0 || (out && u && v)));
+  if (M * N == 0) return EQH_OK;
+  int64_t blocks = (M * N + 255) / 256;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  launch_kernel(k_rank1, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), out, ld, u, v, M, N, scale);
+  EQH_LAUNCH_RC();
+}
 
 int eqh_version(void) { return 100; /* 0.1.0 */ }
 

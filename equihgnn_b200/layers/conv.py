@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .fused_conv import MHNNConvFused, MHNNSConvFused
+from .fused_conv import MHNNConvFused, MHNNSConvFused, MHNNSConvMerged, conv_products
 from .mlp import MLP
 
 
@@ -148,6 +148,8 @@ class MHNNSConv(nn.Module):
         # set by equihgnn_b200.train.Trainer: parameter gradients are accumulated straight into p.grad by the
         # kernels' epilogues instead of being returned to autograd (see layers/fused_conv.py)
         self.direct_param_grad = False
+        self._products = None            # merged weights prepared ahead of the layer loop (prepare_products)
+        self._products_sticky = False
 
     def _layer_fusable(self, x) -> bool:
         ws = [getattr(self, f"W{k}", None) for k in (1, 2, 3)]
@@ -169,6 +171,35 @@ class MHNNSConv(nn.Module):
             if isinstance(w, MLP):
                 w.reset_parameters()
 
+    def _mergeable(self) -> bool:
+        ws = [getattr(self, f"W{k}", None) for k in (1, 2, 3)]
+        return (ops.CONV_MERGED and all(isinstance(w, MLP) and w.fusable() and w.normalization == "ln" for w in ws)
+                and self.hid_dim in (32, 64, 128, 256, 512) and self.aggr in ("mean", "sum")
+                and ws[0].lins[0].weight.is_cuda and ws[0].lins[0].weight.dtype == torch.float32)
+
+    def prepare_products(self) -> None:
+        """Compute the merged weights now (they depend on the parameters only).  A model that applies this ONE module
+        several times (the shared conv of mhnns / egnn_equihnns) calls this ahead of its layer loop -- on a parallel branch
+        of the captured graph -- then `prepare_x0(x0)` once x0 exists, and `release_products()` after the loop; without
+        them every application computes its own."""
+        if not self._mergeable():
+            return
+        p = self._fused_params()
+        self._products = conv_products(p[4], p[5], p[6], p[10], p[11], p[12], self.hid_dim)
+        self._products_sticky = True
+
+    def prepare_x0(self, x0: torch.Tensor) -> None:
+        """X0 . W3.lin0^T (the residual-mix term of every application, conv.py:179-180) once for all of them."""
+        if self._products is None or not self._products_sticky or x0.dim() != 2:
+            return
+        w30 = self.W3.lins[0].weight
+        N, C = x0.shape
+        z0 = ops.gemm_raw(ops._f32(x0, "MHNNSConv X0"), True, w30, True, N, C, C)
+        self._products = tuple(self._products[:4]) + (z0,)
+
+    def release_products(self) -> None:
+        self._products, self._products_sticky = None, False
+
     def forward(self, X, vertex, edges, X0, incidence: "ops.Incidence | None" = None, num_hyperedges=None):
         N = X.shape[-2]
         inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, N, num_hyperedges)
@@ -177,6 +208,10 @@ class MHNNSConv(nn.Module):
             if self._layer_fusable(x):
                 eps = tuple(getattr(self, f"W{k}").normalizations[1].eps for k in (1, 2, 3))
                 direct = self.direct_param_grad and torch.is_grad_enabled()
+                if ops.CONV_MERGED:
+                    products, self._products = self._products, (self._products if self._products_sticky else None)
+                    return MHNNSConvMerged.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, products,
+                                                 *self._fused_params())
                 return MHNNSConvFused.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, *self._fused_params())
             Xe = ops.v2e_gather_reduce(self.W1(x), inc, self.aggr)        # conv.py:172-173
             Xv = _pair_scatter(self.W2, x, Xe, inc, "v", self.aggr)       # conv.py:175-177

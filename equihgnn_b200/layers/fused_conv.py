@@ -45,30 +45,55 @@ class _GradSink:
             # p.grad was re-bound -- never into a private tensor the optimizer would not read)
             self.out[id(p)] = ops.direct_target_strict(p) if direct else None
         self.params = params
+        self.zeroed = set()       # returned-mode targets created as zeros (ensure): later writes accumulate
+        self.after = []           # closures run after the grouped GEMM and the column sums (conversions of merged gradients)
         self.batch = ops.ColsumBatch(params[0].device)
         # weight gradients dW = dY^T . X are queued and launched as ONE grouped GEMM per flush() (ops.GemmGroup)
         self.group = ops.GemmGroup(params[0].device, False, False) if ops.WGRAD_GROUPED else None
 
-    def weight(self, p, dy, x, cols=None):
-        """p.grad[:, cols] (+)= dy^T x   (dy [M, out], x [M, in])"""
+    def ensure(self, p):
+        """The gradient target of p as an ACCUMULATION target: p.grad (direct) or a zero tensor (returned mode)."""
+        if self.out[id(p)] is None:
+            self.out[id(p)] = torch.zeros_like(p)
+            self.zeroed.add(id(p))
+        return self.out[id(p)]
+
+    def weight(self, p, dy, x, cols=None, scale: float = 1.0):
+        """p.grad[:, cols] (+)= scale * dy^T x   (dy [M, out], x [M, in])"""
         M, n_out = dy.shape
         n_in = x.shape[1]
         tgt = self.out[id(p)]
         fresh = tgt is None
         if fresh:
             tgt = self.out[id(p)] = torch.empty_like(p)
-            self._fresh_cols = getattr(self, "_fresh_cols", {})
         view = tgt if cols is None else tgt[:, cols]
-        acc = self.direct or (not fresh and cols is None)
+        acc = self.direct or (not fresh and cols is None) or id(p) in self.zeroed
         if self.group is not None and ops._gemm_ok(dy) and ops._gemm_ok(x) and view.stride(1) == 1 and view.stride(0) % 4 == 0 \
                 and view.data_ptr() % 16 == 0:
-            self.group.add(dy, x, n_out, n_in, M, view, accumulate=acc)
+            self.group.add(dy, x, n_out, n_in, M, view, accumulate=acc, out_scale=scale)
             return
         if self.side:
             with ops.side_work.fork(dy.device, keep=(dy, x)):
-                gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view)
+                gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None,
+                         out_scale=scale)
         else:
-            gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None)
+            gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None, out_scale=scale)
+
+    def scratch_weight(self, dy, x, scale: float = 1.0):
+        """A scratch matrix scale * dy^T x (queued with the layer's weight gradients): the gradient of a MERGED weight."""
+        M, n_out = dy.shape
+        n_in = x.shape[1]
+        out = torch.empty((n_out, n_in), dtype=torch.float32, device=dy.device)
+        if self.group is not None:
+            self.group.add(dy, x, n_out, n_in, M, out, accumulate=False, out_scale=scale)
+        else:
+            self.after.insert(0, lambda: gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=out, out_scale=scale))
+        return out
+
+    def scratch_bias(self, dy, roww=None, scale: float = 1.0):
+        out = torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
+        self.batch.add(dy, out, roww, scale=scale)
+        return out
 
     def bias(self, p, dy, roww=None):
         """p.grad (+)= sum_r roww[r] * dy[r, :]  (queued; finished by flush())"""
@@ -91,16 +116,21 @@ class _GradSink:
 
     def flush(self):
         group = self.group if (self.group is not None and self.group.problems) else None
+        after, self.after = self.after, []
         if self.side:
             keep = tuple(self.batch.keep) + (tuple(group.keep) if group else ())
             with ops.side_work.fork(self.batch.device, keep=keep):
                 if group:
                     group.run()
                 self.batch.run()
+                for fn in after:
+                    fn()
         else:
             if group:
                 group.run()
             self.batch.run()
+            for fn in after:
+                fn()
 
     def results(self):
         return tuple(None if self.direct else self.out[id(p)] for p in self.params)
@@ -201,6 +231,148 @@ class MHNNSConvFused(torch.autograd.Function):
         sink.bias(b10, dh1)
         sink.flush()      # all bias / LayerNorm-affine gradients of the layer: one launch
         return (dX, dX0, None, None, None, None, None) + sink.results()
+
+
+def conv_products(w11, b11, w20, w21, b21, w30, C: int):
+    """Merged weights of MHNNSConv's back-to-back Linears (parameters only: computed off the critical path):
+         Wp = W2.lin0[:, C:] . W1.lin1,  bp = W2.lin0[:, C:] . b(W1.lin1)     (last Linear of W1 commuted with the V2E mean,
+                                                                               then absorbed by W2's first Linear)
+         Wq = W3.lin0 . W2.lin1,         bq = W3.lin0 . b(W2.lin1)            (last Linear of W2 commuted with the E2V mean,
+                                                                               absorbed by W3's first Linear)"""
+    w20b = w20[:, C:]
+    Wp = gemm_raw(w20b, True, w11, False, C, C, C)
+    bp = gemm_raw(b11.view(1, C), True, w20b, True, 1, C, C).view(C)
+    Wq = gemm_raw(w30, True, w21, False, C, C, C)
+    bq = gemm_raw(b21.view(1, C), True, w30, True, 1, C, C).view(C)
+    return Wp, bp, Wq, bq
+
+
+class MHNNSConvMerged(torch.autograd.Function):
+    """MHNNSConv (conv.py:169-182) with the two pairs of back-to-back Linears merged: 4 GEMMs on the critical chain of the
+    forward instead of 6 (and 4 instead of 6 in the backward).  Exact algebra (linearity of the segmented mean / sum and of
+    the residual mix):
+        Bm = mean_e(LN1(..)[v]) . Wp^T + bp * [e non-empty] + b(W2.lin0)
+        h3 = (1-a) (U . Wq^T + bq * [v non-empty]) + a X0 . W3.lin0^T + b(W3.lin0)
+    The gradients of the merged weights are converted back to the parameters' own gradients by four small [C,C,C] GEMMs,
+    two rank-1 updates and two matrix-vector products per layer, on the side stream."""
+
+    @staticmethod
+    def forward(ctx, X, X0, inc, aggr, alpha, direct, eps, products, *params):
+        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+        X = ops._f32(X, "MHNNSConv X")
+        X0 = ops._f32(X0, "MHNNSConv X0")
+        N, C = X.shape
+        E = inc.E
+        dev = X.device
+        mode = _MODES[aggr]
+        A = torch.empty((N, C), dtype=torch.float32, device=dev)
+        Z0 = None if products is None or len(products) < 5 else products[4]      # X0 . W3.lin0^T, shared by the layers
+        own_z0 = Z0 is None
+        if own_z0:
+            Z0 = torch.empty((N, C), dtype=torch.float32, device=dev)
+        with ops.branch_work.fork(dev, keep=(X, X0, A, Z0)):
+            if products is None:
+                products = conv_products(w11, b11, w20, w21, b21, w30, C)
+            gemm_raw(X, True, w20[:, :C], True, N, C, C, out=A)
+            if own_z0:
+                gemm_raw(X0, True, w30, True, N, C, C, out=Z0)
+        Wp, bp, Wq, bq = products[:4]
+        h1 = gemm_raw(X, True, w10, True, N, C, C, bias=b10)
+        y1 = _rowln_fwd(h1, g1, t1, eps[0])
+        Xe1 = gather_reduce_raw(y1, inc.vtx_by_e, inc.rowptr_e, None, E, mode)                      # conv.py:172-173
+        rs_e = inc.nonempty("e") if mode == MEAN else inc.counts("e")
+        ops.branch_work.join(dev)
+        Bm = gemm_raw(Xe1, True, Wp, True, E, C, C, bias=bp, rowscale=rs_e, bias2=b20)
+        U = torch.empty((N, C), dtype=torch.float32, device=dev)
+        _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
+              mode, _p(U), _stream(), nbytes=4.0 * C * (2 * N + E) + 4.0 * (inc.Z + N + 1))         # conv.py:175-177
+        rs_v = inc.nonempty("v") if mode == MEAN else inc.counts("v")
+        h3 = gemm_raw(U, True, Wq, True, N, C, C, bias=bq, rowscale=rs_v, out_scale=1.0 - alpha, bias2=b30, residual=Z0,
+                      res_scale=alpha)                                                              # conv.py:179 + W3.lin0
+        y3 = _rowln_fwd(h3, g3, t3, eps[2])
+        out = gemm_raw(y3, True, w31, True, N, C, C, bias=b31)                                      # conv.py:180
+        ctx.save_for_backward(X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq, *params)
+        ctx.inc, ctx.mode, ctx.alpha, ctx.direct, ctx.eps = inc, mode, alpha, direct, eps
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        saved = ctx.saved_tensors
+        X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq = saved[:14]
+        params = saved[14:]
+        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+        inc, mode, alpha, eps = ctx.inc, ctx.mode, ctx.alpha, ctx.eps
+        sink = _GradSink(params, ctx.direct)
+        dOut = ops._f32(dOut, "MHNNSConv grad")
+        N, C = X.shape
+        E = inc.E
+        dev = X.device
+        # ---- W3.lin1, LayerNorm
+        dy3 = gemm_raw(dOut, True, w31, False, N, C, C)
+        sink.weight(w31, dOut, y3)
+        sink.bias(b31, dOut)
+        dh3, part = _rowln_bwd(h3, g3, eps[2], dy3)
+        sink.affine(g3, t3, part)
+        # ---- merged [W3.lin0 . W2.lin1] and the residual mix: dU on the chain, dX0 on a branch
+        dX0 = torch.empty((N, C), dtype=torch.float32, device=dev)
+        with ops.branch_work.fork(dev, keep=(dh3, dX0)):
+            gemm_raw(dh3, True, w30, False, N, C, C, out=dX0, out_scale=alpha)
+        dU = gemm_raw(dh3, True, Wq, False, N, C, C, out_scale=1.0 - alpha)
+        sink.bias(b30, dh3)
+        dWq = sink.scratch_weight(dh3, U, scale=1.0 - alpha)
+        dbq = sink.scratch_bias(dh3, roww=rs_v, scale=1.0 - alpha)
+        gw30, gw21, gb21 = sink.ensure(w30), sink.ensure(w21), sink.ensure(b21)
+        sink.weight(w30, dh3, X0, scale=alpha)
+        w20b = w20[:, C:]
+
+        def convert_q():
+            gemm_raw(dWq, True, w21, True, C, C, C, out=gw30, residual=gw30)                 # d W3.lin0 += dWq . W2.lin1^T
+            ops.rank1_update_(gw30, dbq, b21)                                                #             + dbq (x) b(W2.lin1)
+            gemm_raw(w30, False, dWq, False, C, C, C, out=gw21, residual=gw21)               # d W2.lin1 += W3.lin0^T . dWq
+            gemm_raw(dbq.view(1, C), True, w30, False, 1, C, C, out=gb21.view(1, C), residual=gb21.view(1, C))
+        sink.after.append(convert_q)
+        # ---- fused message backward
+        dA = torch.empty_like(A)
+        dBm = torch.empty_like(Bm)
+        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev)
+        u_rp = inc.rowptr_v if mode == MEAN else None
+        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), N, C, _p(g2), _p(t2),
+              eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream(),
+              nbytes=4.0 * C * (3 * N + E) + 4.0 * (inc.Z + N + 1) + 8.0 * C * partial_rows())
+        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), E, C,
+              _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream(),
+              nbytes=4.0 * C * (2 * N + 2 * E) + 4.0 * (2 * inc.Z + E + 1))
+        sink.affine(g2, t2, part)
+        # dX = dA . W2.lin0[:, :C] is needed only by the last GEMM of this backward: a parallel branch
+        dX = torch.empty((N, C), dtype=torch.float32, device=dev)
+        with ops.branch_work.fork(dev, keep=(dA, dX)):
+            gemm_raw(dA, True, w20[:, :C], False, N, C, C, out=dX)
+        sink.ensure(w20)
+        sink.weight(w20, dA, X, cols=slice(0, C))
+        # ---- merged [W2.lin0[:, C:] . W1.lin1] through the V2E mean
+        sink.bias(b20, dBm)
+        dWp = sink.scratch_weight(dBm, Xe1)
+        dbp = sink.scratch_bias(dBm, roww=rs_e)
+        gw20, gw11, gb11 = sink.out[id(w20)], sink.ensure(w11), sink.ensure(b11)
+
+        def convert_p():
+            gw20b = gw20[:, C:]
+            gemm_raw(dWp, True, w11, True, C, C, C, out=gw20b, residual=gw20b)               # d W2.lin0[:, C:] += dWp . W1.lin1^T
+            ops.rank1_update_(gw20b, dbp, b11)
+            gemm_raw(w20b, False, dWp, False, C, C, C, out=gw11, residual=gw11)              # d W1.lin1 += W2.lin0[:, C:]^T . dWp
+            gemm_raw(dbp.view(1, C), True, w20b, False, 1, C, C, out=gb11.view(1, C), residual=gb11.view(1, C))
+        sink.after.append(convert_p)
+        dXe1 = gemm_raw(dBm, True, Wp, False, E, C, C)
+        # V2E gather-mean backward: dy1[n] = sum over n's incidences of dXe1[e] / |e|
+        dy1 = gather_reduce_raw(dXe1, inc.edge_by_v, inc.rowptr_v, inc.rowptr_e if mode == MEAN else None, N, SUM)
+        dh1, part = _rowln_bwd(h1, g1, eps[0], dy1)
+        sink.affine(g1, t1, part)
+        ops.branch_work.join(dev)
+        gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX)          # dX += dh1 . W1.lin0 (in-place epilogue)
+        sink.weight(w10, dh1, X)
+        sink.bias(b10, dh1)
+        sink.flush()      # grouped weight gradients, column sums, then the conversions of the merged gradients
+        return (dX, dX0, None, None, None, None, None, None) + sink.results()
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -653,7 +653,8 @@ def gemm_plan(M: int, N: int, K: int, splits: int = 1, flags: int = 0):
 def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=None, act=None, residual=None,
              splits: int = 1, write_hi: bool = False, rowscale=None, out: Optional[torch.Tensor] = None,
              out_scale: float = 1.0, res_scale: float = 1.0, flags: Optional[int] = None,
-             stash: Optional[torch.Tensor] = None, dsilu_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+             stash: Optional[torch.Tensor] = None, dsilu_aux: Optional[torch.Tensor] = None,
+             bias2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = out_scale * act(A.B^T + bias * rowscale) + res_scale * residual with A logical [M,K], B logical [N,K]; an
     operand flagged k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3).  `out` may be a row-strided
     view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation).
@@ -675,14 +676,15 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
             ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
             cnt = counters(tiles, dev)
     flops = 2.0 * M * N * K
-    if stash is not None or dsilu_aux is not None:
+    if stash is not None or dsilu_aux is not None or bias2 is not None:
         if splits != 1:
-            raise RuntimeError("gemm_raw: stash / dsilu_aux need splits == 1")
+            raise RuntimeError("gemm_raw: stash / dsilu_aux / bias2 need splits == 1")
         if stash is not None and stash.stride(0) != ldd:
             raise RuntimeError("gemm_raw: stash must have the row stride of the output")
-        _call("eqh_gemm_tf32x3_ex", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
+        _call("eqh_gemm_tf32x3_ex2", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
               _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
-              _p(stash), _p(dsilu_aux), dsilu_aux.stride(0) if dsilu_aux is not None else 0, _stream(), nbytes=flops)
+              _p(stash), _p(dsilu_aux), dsilu_aux.stride(0) if dsilu_aux is not None else 0, _p(bias2), _stream(),
+              nbytes=flops)
         return D
     _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
           _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
@@ -699,7 +701,7 @@ class GemmGroup:
         self.device, self.a_kmajor, self.b_kmajor = device, a_kmajor, b_kmajor
         self.problems, self.keep = [], []
 
-    def add(self, A, B, M: int, N: int, K: int, out: torch.Tensor, accumulate: bool = False, out_scale: float = 1.0) -> None:
+    def add(self, A, B, M: int, N: int, K: int, out: torch.Tensor, accumulate: bool = False, out_scale: float = 1.0) -> None:  # noqa: E501
         """out[M,N] (+)= out_scale * A.B^T  (A logical [M,K], B logical [N,K], stored as the group's majors say)"""
         self.problems.append(_lib.GemmProblem(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
                                               out.stride(0), M, N, K, None, None, out.data_ptr() if accumulate else None,
@@ -727,6 +729,13 @@ class GemmGroup:
 
 
 WGRAD_GROUPED = os.environ.get("EQH_WGRAD_GROUPED", "1") != "0"     # one grouped launch per layer for the weight gradients
+CONV_MERGED = os.environ.get("EQH_CONV_MERGED", "1") != "0"         # MHNNSConv with its back-to-back Linears merged
+
+
+def rank1_update_(out: torch.Tensor, u: torch.Tensor, v: torch.Tensor, scale: float = 1.0) -> None:
+    """out[m, n] += scale * u[m] * v[n] for a row-strided [M, N] matrix (eqh_rank1_update)."""
+    M, N = out.shape
+    _call("eqh_rank1_update", 1, _p(out), out.stride(0), _p(u), _p(v), M, N, scale, _stream())
 
 
 def _gemm_ok(t: torch.Tensor) -> bool:

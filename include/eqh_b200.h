@@ -424,6 +424,17 @@ EQH_API int eqh_gemm_tf32x3_ex(const float* A, int a_kmajor, int64_t lda, const 
                        const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
                        float* stash, const float* dsilu_aux, int64_t ld_aux, eqh_stream_t stream);
 
+/* ... and with a second bias [N] added unscaled after the activation and out_scale:
+ *   D = out_scale * act(A.B^T + bias * rowscale) + bias2 + res_scale * residual
+ * (two Linears merged into one GEMM: the inner bias carries the row scale / mix factor, the outer one does not). */
+EQH_API int eqh_gemm_tf32x3_ex2(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                        int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
+                        const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                        float* stash, const float* dsilu_aux, int64_t ld_aux, const float* bias2, eqh_stream_t stream);
+/* out[m, n] += u[m] * v[n]  (rank-1 update of a row-strided [M, N] matrix: the bias term of a merged weight product) */
+EQH_API int eqh_rank1_update(float* out, int64_t ld, const float* u, const float* v, int64_t M, int64_t N, float scale,
+                     eqh_stream_t stream);
+
 /* Several independent GEMMs with the same operand majors as ONE launch (the weight gradients dW = dY^T . X of all the
  * Linears of a layer, mlp.py:91-99 / conv.py:169-182 backward): D_i = out_scale_i * (A_i . B_i^T [+ bias_i * rowscale_i])
  * + res_scale_i * residual_i, operand conventions of eqh_gemm_tf32x3.  The planner picks one tile width for the group and
