@@ -325,7 +325,9 @@ int eqh_gemm_plan(int64_t M, int64_t N, int64_t K, int splits, int flags, int* b
 // ---- grouped launch: n independent problems with the same operand majors ------------------------------------------
 // Plan: one tile width for the group and, per problem, a split count such that every CTA owns about q K blocks; q and
 // the width minimise rounds x per-CTA cost (the cost model of gemm::plan), rounds = ceil(total CTAs / SMs).
-static void plan_group(const eqh_gemm_problem* pr, int n, int bn_req, int* bn_out, int* splits /*[n]*/) {
+// max_ctas > 0: background plan -- the group must not occupy more than max_ctas SMs (it runs next to a latency-critical
+// chain of small-grid kernels that needs the rest); the widest tile and the fewest splits that fit.
+static void plan_group(const eqh_gemm_problem* pr, int n, int bn_req, int* bn_out, int* splits /*[n]*/, int max_ctas = 0) {
   using namespace eqh;
   using namespace eqh::gemm;
   double best = 1e300;
@@ -339,7 +341,7 @@ static void plan_group(const eqh_gemm_problem* pr, int n, int bn_req, int* bn_ou
       if (s > 1 && q < 2) break;
       // the tensor core truncates when it accumulates: bound the accumulation chain of one CTA (as the single-problem
       // planner does with its kb/2..32 splits) -- 48 K blocks keep the result within 5e-6 of fp64 at K = 30000
-      if (q > 48 && s < 32) continue;
+      if (q > 48 && s < 32 && max_ctas == 0) continue;
       int64_t ctas = 0;
       double finish = 0.0;
       for (int i = 0; i < n; ++i) {
@@ -350,7 +352,8 @@ static void plan_group(const eqh_gemm_problem* pr, int n, int bn_req, int* bn_ou
         ctas += ((pr[i].M + BM - 1) / BM) * ((pr[i].N + bn - 1) / bn) * s_eff;
         if (s_eff > 1) finish = std::max(finish, 4.0 * bn * (double)s_eff);
       }
-      const int64_t rounds = (ctas + kSMs - 1) / kSMs;
+      if (max_ctas > 0 && ctas > max_ctas && !(bn == 128 && s == 1)) continue;   // (the smallest plan is always allowed)
+      const int64_t rounds = max_ctas > 0 ? 1 : (ctas + kSMs - 1) / kSMs;
       const double cost = (double)rounds * ((double)q * (300.0 + 6.4 * bn) + 1500.0) + finish;
       if (cost < best - 1e-9) { best = cost; best_bn = bn; best_q = (int)q; }
     }
@@ -384,7 +387,7 @@ int eqh_gemm_grouped_plan(const eqh_gemm_problem* problems, int n, int a_kmajor,
   if (rc) return rc;
   EQH_CHECK_ARG(bn && splits && ws_floats && n_counters);
   const int code = (flags >> 9) & 3;
-  plan_group(problems, n, code ? (16 << code) : 0, bn, splits);
+  plan_group(problems, n, code ? (16 << code) : 0, bn, splits, (flags >> 16) & 0xfff);
   int64_t ws = 0, cnt = 0;
   for (int i = 0; i < n; ++i) {
     if (splits[i] > 1) {
@@ -406,7 +409,7 @@ int eqh_gemm_grouped(const eqh_gemm_problem* problems, int n, int a_kmajor, int 
   if (rc) return rc;
   int BN, splits[kMaxGroup];
   const int code = (flags >> 9) & 3;
-  plan_group(problems, n, code ? (16 << code) : 0, &BN, splits);
+  plan_group(problems, n, code ? (16 << code) : 0, &BN, splits, (flags >> 16) & 0xfff);
   static GroupParams g;                        // ~3 KB: too large for the stack of every caller; filled and launched under a lock
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);

@@ -49,7 +49,8 @@ class _GradSink:
         self.after = []           # closures run after the grouped GEMM and the column sums (conversions of merged gradients)
         self.batch = ops.ColsumBatch(params[0].device)
         # weight gradients dW = dY^T . X are queued and launched as ONE grouped GEMM per flush() (ops.GemmGroup)
-        self.group = ops.GemmGroup(params[0].device, False, False) if ops.WGRAD_GROUPED else None
+        self.group = ops.GemmGroup(params[0].device, False, False, ops.WGRAD_MAX_CTAS if direct else 0) \
+            if ops.WGRAD_GROUPED else None
 
     def ensure(self, p):
         """The gradient target of p as an ACCUMULATION target: p.grad (direct) or a zero tensor (returned mode)."""

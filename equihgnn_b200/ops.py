@@ -697,9 +697,10 @@ class GemmGroup:
     as ONE grid (eqh_gemm_grouped): instead of one launch per parameter -- each a few CTA rounds with its own prologue,
     split-K finish and tail -- the group fills the GPU once."""
 
-    def __init__(self, device, a_kmajor: bool, b_kmajor: bool):
+    def __init__(self, device, a_kmajor: bool, b_kmajor: bool, max_ctas: int = 0):
         self.device, self.a_kmajor, self.b_kmajor = device, a_kmajor, b_kmajor
         self.problems, self.keep = [], []
+        self.flags = GEMM_FLAGS | ((max_ctas & 0xfff) << 16)
 
     def add(self, A, B, M: int, N: int, K: int, out: torch.Tensor, accumulate: bool = False, out_scale: float = 1.0) -> None:  # noqa: E501
         """out[M,N] (+)= out_scale * A.B^T  (A logical [M,K], B logical [N,K], stored as the group's majors say)"""
@@ -711,24 +712,28 @@ class GemmGroup:
     def run(self) -> None:
         import ctypes
         lib = _lib.load()
+        if self.problems and max(q.K for q in self.problems) > 8192:
+            self.flags &= 0xffff           # long reductions: no SM cap (accumulation chains stay short, the GPU is filled)
         for i in range(0, len(self.problems), _lib.GEMM_MAX_GROUP):
             chunk = self.problems[i:i + _lib.GEMM_MAX_GROUP]
             arr = (_lib.GemmProblem * len(chunk))(*chunk)
             bn, ws_f, n_cnt = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
             splits = (ctypes.c_int * len(chunk))()
-            _lib.check(lib.eqh_gemm_grouped_plan(arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), GEMM_FLAGS,
+            _lib.check(lib.eqh_gemm_grouped_plan(arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), self.flags,
                                                  ctypes.byref(bn), splits, ctypes.byref(ws_f), ctypes.byref(n_cnt)),
                        "eqh_gemm_grouped_plan")
             ws = torch.empty(max(ws_f.value, 4), dtype=torch.float32, device=self.device)
             cnt = counters(int(n_cnt.value), self.device)
             flops = sum(2.0 * q.M * q.N * q.K for q in chunk)
-            _call("eqh_gemm_grouped", 1, arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), GEMM_FLAGS, _p(ws), _p(cnt),
+            _call("eqh_gemm_grouped", 1, arr, len(chunk), int(self.a_kmajor), int(self.b_kmajor), self.flags, _p(ws), _p(cnt),
                   _stream(), nbytes=flops)
             self.keep.append(ws)
         self.problems = []
 
 
 WGRAD_GROUPED = os.environ.get("EQH_WGRAD_GROUPED", "1") != "0"     # one grouped launch per layer for the weight gradients
+# SM budget of a grouped weight-gradient launch that runs next to the dX chain (0 = no cap: plan for latency)
+WGRAD_MAX_CTAS = int(os.environ.get("EQH_WGRAD_MAX_CTAS", "0"))
 CONV_MERGED = os.environ.get("EQH_CONV_MERGED", "1") != "0"         # MHNNSConv with its back-to-back Linears merged
 
 
