@@ -150,6 +150,7 @@ class MHNNSConv(nn.Module):
         self.direct_param_grad = False
         self._products = None            # merged weights prepared ahead of the layer loop (prepare_products)
         self._products_sticky = False
+        self._shared_acc, self._app_index = None, 0
 
     def _layer_fusable(self, x) -> bool:
         ws = [getattr(self, f"W{k}", None) for k in (1, 2, 3)]
@@ -185,8 +186,18 @@ class MHNNSConv(nn.Module):
         if not self._mergeable():
             return
         p = self._fused_params()
-        self._products = conv_products(p[4], p[5], p[6], p[10], p[11], p[12], self.hid_dim)
+        C = self.hid_dim
+        self._products = conv_products(p[4], p[5], p[6], p[10], p[11], p[12], C)
         self._products_sticky = True
+        self._app_index = 0
+        self._shared_acc = None
+        if torch.is_grad_enabled():
+            # accumulators of the merged weights' gradients over all applications of this forward pass (zeroed here; the
+            # backward of application 0 converts them once)
+            dev = p[0].device
+            buf = torch.zeros(2 * C * C + 2 * C, dtype=torch.float32, device=dev)
+            self._shared_acc = {"dWp": buf[:C * C].view(C, C), "dWq": buf[C * C:2 * C * C].view(C, C),
+                                "dbp": buf[2 * C * C:2 * C * C + C], "dbq": buf[2 * C * C + C:]}
 
     def prepare_x0(self, x0: torch.Tensor) -> None:
         """X0 . W3.lin0^T (the residual-mix term of every application, conv.py:179-180) once for all of them."""
@@ -199,6 +210,7 @@ class MHNNSConv(nn.Module):
 
     def release_products(self) -> None:
         self._products, self._products_sticky = None, False
+        self._shared_acc, self._app_index = None, 0
 
     def forward(self, X, vertex, edges, X0, incidence: "ops.Incidence | None" = None, num_hyperedges=None):
         N = X.shape[-2]
@@ -209,8 +221,11 @@ class MHNNSConv(nn.Module):
                 eps = tuple(getattr(self, f"W{k}").normalizations[1].eps for k in (1, 2, 3))
                 direct = self.direct_param_grad and torch.is_grad_enabled()
                 if ops.CONV_MERGED:
-                    products, self._products = self._products, (self._products if self._products_sticky else None)
-                    return MHNNSConvMerged.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, products,
+                    products, shared = self._products, None
+                    if self._products_sticky and self._shared_acc is not None:
+                        shared = (self._shared_acc, self._app_index)        # see MHNNSConvMerged.forward
+                        self._app_index += 1
+                    return MHNNSConvMerged.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, products, shared,
                                                  *self._fused_params())
                 return MHNNSConvFused.apply(x, x0, inc, self.aggr, float(self.alpha), direct, eps, *self._fused_params())
             Xe = ops.v2e_gather_reduce(self.W1(x), inc, self.aggr)        # conv.py:172-173

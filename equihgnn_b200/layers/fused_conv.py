@@ -80,20 +80,23 @@ class _GradSink:
         else:
             gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None, out_scale=scale)
 
-    def scratch_weight(self, dy, x, scale: float = 1.0):
-        """A scratch matrix scale * dy^T x (queued with the layer's weight gradients): the gradient of a MERGED weight."""
+    def scratch_weight(self, dy, x, scale: float = 1.0, into=None):
+        """A scratch matrix (+)= scale * dy^T x (queued with the layer's weight gradients): the gradient of a MERGED weight.
+        into: an accumulator shared by several applications of one module (accumulated), else a fresh matrix."""
         M, n_out = dy.shape
         n_in = x.shape[1]
-        out = torch.empty((n_out, n_in), dtype=torch.float32, device=dy.device)
+        out = into if into is not None else torch.empty((n_out, n_in), dtype=torch.float32, device=dy.device)
+        acc = into is not None
         if self.group is not None:
-            self.group.add(dy, x, n_out, n_in, M, out, accumulate=False, out_scale=scale)
+            self.group.add(dy, x, n_out, n_in, M, out, accumulate=acc, out_scale=scale)
         else:
-            self.after.insert(0, lambda: gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=out, out_scale=scale))
+            self.after.insert(0, lambda: gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=out,
+                                                  residual=out if acc else None, out_scale=scale))
         return out
 
-    def scratch_bias(self, dy, roww=None, scale: float = 1.0):
-        out = torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
-        self.batch.add(dy, out, roww, scale=scale)
+    def scratch_bias(self, dy, roww=None, scale: float = 1.0, into=None):
+        out = into if into is not None else torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
+        self.batch.add(dy, out, roww, scale=scale, accumulate=into is not None)
         return out
 
     def bias(self, p, dy, roww=None):
@@ -258,7 +261,10 @@ class MHNNSConvMerged(torch.autograd.Function):
     two rank-1 updates and two matrix-vector products per layer, on the side stream."""
 
     @staticmethod
-    def forward(ctx, X, X0, inc, aggr, alpha, direct, eps, products, *params):
+    def forward(ctx, X, X0, inc, aggr, alpha, direct, eps, products, shared, *params):
+        """shared: None, or (accumulators {dWp, dbp, dWq, dbq}, application index) when ONE module is applied several times
+        with shared products (MHNNSConv.prepare_products): every application's backward accumulates the gradients of the
+        merged weights, and application 0 -- whose backward runs last -- converts them to parameter gradients once."""
         (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
         X = ops._f32(X, "MHNNSConv X")
         X0 = ops._f32(X0, "MHNNSConv X0")
@@ -294,12 +300,15 @@ class MHNNSConvMerged(torch.autograd.Function):
         out = gemm_raw(y3, True, w31, True, N, C, C, bias=b31)                                      # conv.py:180
         ctx.save_for_backward(X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq, *params)
         ctx.inc, ctx.mode, ctx.alpha, ctx.direct, ctx.eps = inc, mode, alpha, direct, eps
+        ctx.shared = shared
         return out
 
     @staticmethod
     def backward(ctx, dOut):
         saved = ctx.saved_tensors
         X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq = saved[:14]
+        acc, app = ctx.shared if ctx.shared is not None else (None, 0)
+        convert = app == 0                 # (the only application, or the one whose backward runs last)
         params = saved[14:]
         (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
         inc, mode, alpha, eps = ctx.inc, ctx.mode, ctx.alpha, ctx.eps
@@ -320,18 +329,11 @@ class MHNNSConvMerged(torch.autograd.Function):
             gemm_raw(dh3, True, w30, False, N, C, C, out=dX0, out_scale=alpha)
         dU = gemm_raw(dh3, True, Wq, False, N, C, C, out_scale=1.0 - alpha)
         sink.bias(b30, dh3)
-        dWq = sink.scratch_weight(dh3, U, scale=1.0 - alpha)
-        dbq = sink.scratch_bias(dh3, roww=rs_v, scale=1.0 - alpha)
+        dWq = sink.scratch_weight(dh3, U, scale=1.0 - alpha, into=acc["dWq"] if acc else None)
+        dbq = sink.scratch_bias(dh3, roww=rs_v, scale=1.0 - alpha, into=acc["dbq"] if acc else None)
         gw30, gw21, gb21 = sink.ensure(w30), sink.ensure(w21), sink.ensure(b21)
         sink.weight(w30, dh3, X0, scale=alpha)
         w20b = w20[:, C:]
-
-        def convert_q():
-            gemm_raw(dWq, True, w21, True, C, C, C, out=gw30, residual=gw30)                 # d W3.lin0 += dWq . W2.lin1^T
-            ops.rank1_update_(gw30, dbq, b21)                                                #             + dbq (x) b(W2.lin1)
-            gemm_raw(w30, False, dWq, False, C, C, C, out=gw21, residual=gw21)               # d W2.lin1 += W3.lin0^T . dWq
-            gemm_raw(dbq.view(1, C), True, w30, False, 1, C, C, out=gb21.view(1, C), residual=gb21.view(1, C))
-        sink.after.append(convert_q)
         # ---- fused message backward
         dA = torch.empty_like(A)
         dBm = torch.empty_like(Bm)
@@ -352,17 +354,29 @@ class MHNNSConvMerged(torch.autograd.Function):
         sink.weight(w20, dA, X, cols=slice(0, C))
         # ---- merged [W2.lin0[:, C:] . W1.lin1] through the V2E mean
         sink.bias(b20, dBm)
-        dWp = sink.scratch_weight(dBm, Xe1)
-        dbp = sink.scratch_bias(dBm, roww=rs_e)
+        dWp = sink.scratch_weight(dBm, Xe1, into=acc["dWp"] if acc else None)
+        dbp = sink.scratch_bias(dBm, roww=rs_e, into=acc["dbp"] if acc else None)
         gw20, gw11, gb11 = sink.out[id(w20)], sink.ensure(w11), sink.ensure(b11)
 
-        def convert_p():
+        def convert_all():
+            """gradients of the merged weights -> the parameters' own gradients: 3 grouped launches + 2 rank-1 updates"""
             gw20b = gw20[:, C:]
-            gemm_raw(dWp, True, w11, True, C, C, C, out=gw20b, residual=gw20b)               # d W2.lin0[:, C:] += dWp . W1.lin1^T
-            ops.rank1_update_(gw20b, dbp, b11)
-            gemm_raw(w20b, False, dWp, False, C, C, C, out=gw11, residual=gw11)              # d W1.lin1 += W2.lin0[:, C:]^T . dWp
-            gemm_raw(dbp.view(1, C), True, w20b, False, 1, C, C, out=gb11.view(1, C), residual=gb11.view(1, C))
-        sink.after.append(convert_p)
+            g1_ = ops.GemmGroup(dev, True, True)
+            g1_.add(dWq, w21, C, C, C, gw30, accumulate=True)                 # d W3.lin0 += dWq . W2.lin1^T
+            g1_.add(dWp, w11, C, C, C, gw20b, accumulate=True)                # d W2.lin0[:, C:] += dWp . W1.lin1^T
+            g1_.run()
+            g2_ = ops.GemmGroup(dev, False, False)
+            g2_.add(w30, dWq, C, C, C, gw21, accumulate=True)                 # d W2.lin1 += W3.lin0^T . dWq
+            g2_.add(w20b, dWp, C, C, C, gw11, accumulate=True)                # d W1.lin1 += W2.lin0[:, C:]^T . dWp
+            g2_.run()
+            g3_ = ops.GemmGroup(dev, True, False)                             # bias gradients: matrix-vector products
+            g3_.add(dbq.view(1, C), w30, 1, C, C, gb21.view(1, C), accumulate=True)     # db(W2.lin1) += W3.lin0^T dbq
+            g3_.add(dbp.view(1, C), w20b, 1, C, C, gb11.view(1, C), accumulate=True)    # db(W1.lin1) += W2.lin0[:, C:]^T dbp
+            g3_.run()
+            ops.rank1_update_(gw30, dbq, b21)                                 # d W3.lin0 += dbq (x) b(W2.lin1)
+            ops.rank1_update_(gw20b, dbp, b11)                                # d W2.lin0[:, C:] += dbp (x) b(W1.lin1)
+        if convert:
+            sink.after.append(convert_all)
         dXe1 = gemm_raw(dBm, True, Wp, False, E, C, C)
         # V2E gather-mean backward: dy1[n] = sum over n's incidences of dXe1[e] / |e|
         dy1 = gather_reduce_raw(dXe1, inc.edge_by_v, inc.rowptr_v, inc.rowptr_e if mode == MEAN else None, N, SUM)
@@ -373,7 +387,7 @@ class MHNNSConvMerged(torch.autograd.Function):
         sink.weight(w10, dh1, X)
         sink.bias(b10, dh1)
         sink.flush()      # grouped weight gradients, column sums, then the conversions of the merged gradients
-        return (dX, dX0, None, None, None, None, None, None) + sink.results()
+        return (dX, dX0, None, None, None, None, None, None, None) + sink.results()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
