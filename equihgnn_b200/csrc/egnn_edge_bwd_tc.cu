@@ -499,7 +499,15 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
 static int groups_of(int64_t H) { return (int)((H + GC - 1) / GC); }
 static int slices_of(int64_t H) {
   const int gr = groups_of(H);
-  const int s = kSMs / gr;
+  // CTAs = groups x slices, one per SM (200 KB of shared memory each).  EQH_EDGE_BWD_FREE_SMS leaves that many SMs to the
+  // kernels of the parallel graph branches (weight-gradient GEMMs, column sums, the bucketed gradient exchange) that would
+  // otherwise wait for this kernel to end: it is the longest single kernel of the backward's tail.
+  static const int free_sms = []() {
+    const char* e = getenv("EQH_EDGE_BWD_FREE_SMS");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 ? 0 : (v > kSMs / 2 ? kSMs / 2 : v);
+  }();
+  const int s = (kSMs - free_sms) / gr;
   return s < 1 ? 1 : s;
 }
 

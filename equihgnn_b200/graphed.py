@@ -149,7 +149,8 @@ class GraphedTrainer(Trainer):
         self.fp.zero_grad()
         loss = model_loss(self.model, data, self.B)                    # the ghost molecule is not in the loss
         loss.backward()
-        ops.side_work.join()        # the side-stream branch rejoins before the capture ends
+        ops.side_work.join()
+        ops.side_work_b.join()        # the side-stream branch rejoins before the capture ends
         return loss.detach()
 
     def _body(self, data) -> torch.Tensor:

@@ -34,8 +34,9 @@ def _rowln_bwd(x, g, eps, dy, relu=1):
 class _GradSink:
     """Where a parameter gradient goes: into p.grad (direct mode, accumulate) or into a fresh tensor (returned)."""
 
-    def __init__(self, params, direct):
+    def __init__(self, params, direct, side_work=None):
         self.direct = direct
+        self.sw = side_work if side_work is not None else ops.side_work
         # direct mode: nobody reads the gradients before the optimizer, so they are produced on the side stream
         # (a parallel branch of the captured graph) and joined by the Trainer
         self.side = direct        # (ops.side_work.fork degrades to the current stream outside graph capture)
@@ -74,7 +75,7 @@ class _GradSink:
             self.group.add(dy, x, n_out, n_in, M, view, accumulate=acc, out_scale=scale)
             return
         if self.side:
-            with ops.side_work.fork(dy.device, keep=(dy, x)):
+            with self.sw.fork(dy.device, keep=(dy, x)):
                 gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None,
                          out_scale=scale)
         else:
@@ -123,7 +124,7 @@ class _GradSink:
         after, self.after = self.after, []
         if self.side:
             keep = tuple(self.batch.keep) + (tuple(group.keep) if group else ())
-            with ops.side_work.fork(self.batch.device, keep=keep):
+            with self.sw.fork(self.batch.device, keep=keep):
                 if group:
                     group.run()
                 self.batch.run()

@@ -73,7 +73,7 @@ class EGNNFused(torch.autograd.Function):
         H0, Hp = w1.shape[0], bufs["W1a"].shape[0]
         ldn = C + M_DIM
         dev = h.device
-        sink = _GradSink((w1, b1, w2, b2, g, t, w5, b5, w6, b6), True)
+        sink = _GradSink((w1, b1, w2, b2, g, t, w5, b5, w6, b6), True, ops.side_work_b)
         # ---- node update: dt_pre = (dOut . W6) * SiLU'(t_pre) in the GEMM epilogue
         dt_pre = gemm_raw(dOut, True, w6, False, N, 2 * C, C, dsilu_aux=t_pre)
         sink.weight(w6, dOut, tt)
@@ -104,7 +104,7 @@ class EGNNFused(torch.autograd.Function):
         # and db1 start next to the dQ reduction, the merged weight gradient [dP | dQ]^T . h next to the dh GEMM.
         red = torch.empty(cols, dtype=torch.float32, device=dev)
         T = torch.empty((2 * Hp, C), dtype=torch.float32, device=dev)               # [dP | dQ]^T . h = [d W1a ; d W1b]
-        with ops.side_work.fork(dev, keep=(dPQ, part, red, T, h)):
+        with ops.side_work_b.fork(dev, keep=(dPQ, part, red, T, h)):
             # the dP half of the weight gradient runs under the dQ reduction (memory-bound: the tensor pipe is idle)
             gemm_raw(dPQ, False, h, False, Hp, C, N, splits=0, out=T[:Hp])
             batch = ops.ColsumBatch(dev)
@@ -114,7 +114,7 @@ class EGNNFused(torch.autograd.Function):
         # dQ[j] = sum over the edges (i, k) with idx[i, k] == j, ascending edge order (deterministic)
         _call("eqh_gather_reduce_ld", 1, _p(dPre), Hp, _p(graph.perm_j), _p(graph.rowptr_j), None, N, Hp, SUM,
               dPQ.data_ptr() + 4 * Hp, 2 * Hp, _stream(), nbytes=4.0 * Hp * (N * KNN_K + N) + 4.0 * (N * KNN_K + N + 1))
-        with ops.side_work.fork(dev, keep=(dPQ, h, T, red)):
+        with ops.side_work_b.fork(dev, keep=(dPQ, h, T, red)):
             gemm_raw(dPQ[:, Hp:], False, h, False, Hp, C, N, splits=0, out=T[Hp:])     # the dQ half, next to the dh GEMM
             _call("eqh_egnn_unpack_grads", 1, _p(T), _p(red), H0, C, Hp, _p(sink.out[id(w1)]), _p(sink.out[id(w2)]),
                   _p(sink.out[id(b2)]), _stream())

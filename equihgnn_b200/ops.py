@@ -376,6 +376,9 @@ class _SideWork:
 
 
 side_work = _SideWork()
+# second side stream: the EGNN layer's parameter-gradient work (its backward is the tail of the step; queued behind the conv
+# layers' weight gradients and conversions on ONE stream it ended 90 us after the main chain)
+side_work_b = _SideWork()
 # forward-time index / packing work that nothing on the critical path needs yet (incidence CSR next to the atom encoder
 # and the kNN search, the transposed kNN incidence next to the phi_e GEMMs): a second parallel branch of the captured graph
 prep_work = _SideWork()

@@ -164,10 +164,12 @@ class Trainer:
         loss = model_loss(self.model, data, data.y.view(-1).shape[0])
         loss.backward()
         ops.side_work.join()
+        ops.side_work_b.join()
         return loss.detach()
 
     def sync_gradients(self):
-        ops.side_work.join()        # weight-gradient work issued on the side stream
+        ops.side_work.join()
+        ops.side_work_b.join()        # weight-gradient work issued on the side stream
         if self.distributed:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
 
@@ -226,6 +228,7 @@ class Trainer:
         finally:
             ops.BOUNDARY_HOOK = None
         ops.side_work.join()
+        ops.side_work_b.join()
         if self._early_done:
             self._exchange_and_update(0, self.split, advance=True)
             torch.cuda.current_stream(self.fp.flat.device).wait_stream(self._comm)
