@@ -79,6 +79,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_EXT_SRC = os.path.join(CSRC, "torch_ext", "eqh_torch.cpp")
+TORCH_EXT_LIB = os.path.join(CSRC, "libeqh_b200_torch.so")
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """Compile the thin torch C++ extension over the C ABI (csrc/torch_ext/eqh_torch.cpp -> libeqh_b200_torch.so,
+    `torch.ops.load_library`).  Plain g++ against torch's headers: the file holds no kernels."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    build()                                   # the C-ABI library it links against
+    if not force and not _stale(TORCH_EXT_LIB, [TORCH_EXT_SRC, LIB, os.path.join(INCLUDE, "eqh_b200.h")]):
+        return TORCH_EXT_LIB
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    for inc in ce.include_paths() + [cuda_inc, INCLUDE]:
+        cmd += ["-I", inc]
+    import sysconfig
+    cmd += ["-I", sysconfig.get_paths()["include"]]
+    cmd += [TORCH_EXT_SRC, "-o", TORCH_EXT_LIB, "-L", tlib, "-L", CSRC, "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda",
+            "-lc10_cuda", "-leqh_b200", f"-Wl,-rpath,{tlib}", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"torch extension build failed:\n{r.stdout}\n{r.stderr[-4000:]}")
+    return TORCH_EXT_LIB
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)
+    if "--torch-ext" in sys.argv:
+        print(build_torch_ext(force="--force" in sys.argv))

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert loaded.eqh_partial_rows() == 296
     assert b"unsupported" in loaded.eqh_error_string(-2)
     # argument validation happens before any CUDA call, so these are safe on a CPU-only box
-    assert loaded.eqh_incidence_workspace_bytes(10, 4) == 4 * (4 + 1 + 10)
+    assert loaded.eqh_incidence_workspace_bytes(10, 4) == 4 * (4 + 1 + 10 + 2 * 148)      # counts + slots + scan block sums
     assert loaded.eqh_knn16(None, 100, None, None, None) == -1
     assert loaded.eqh_gather_reduce(None, None, None, None, -1, 64, 0, None, None) == -1
 
@@ -258,3 +258,15 @@ def test_direct_gradient_registry_is_keyed_on_identity():
         assert ops._direct_target(lin.weight) is lin.weight.grad
         assert lin.weight.grad.data_ptr() == fp.grad.data_ptr()
     assert not ops.direct_grad_registered(lin.weight)                 # the scope restores plain autograd semantics
+
+
+def test_torch_extension_loads_and_registers_its_ops():
+    """The thin torch C++ extension over the C ABI (north_star's host boundary): builds in-tree, registers torch.ops.eqh.*,
+    and refuses CPU tensors (no compute without a GPU here)."""
+    from equihgnn_b200 import build, torch_ext
+    build.build_torch_ext()
+    torch_ext.load()
+    for name in torch_ext.OPS:
+        assert hasattr(torch.ops.eqh, name), name
+    with pytest.raises(RuntimeError):
+        torch.ops.eqh.scatter(torch.randn(4, 32), torch.tensor([0, 1, 1, 0]), 2, "sum")
