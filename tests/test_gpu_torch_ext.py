@@ -22,18 +22,22 @@ def _ext():
 
 @pytest.mark.parametrize("reduce", ["sum", "mean"])
 def test_scatter_matches_ctypes_binding_and_golden(reduce):
+    import torch.nn.functional as F
     fx = load_golden("scatter")
-    src = fx["src"].to(DEV).requires_grad_(True)
+    src0 = F.pad(fx["src"], (0, 16))                         # C = 48 -> 64: the kernels take multiples of 32
+    src = src0.to(DEV).requires_grad_(True)
     index = fx["index"].to(DEV)
     out = torch.ops.eqh.scatter(src, index, fx["n"], reduce)
-    assert torch.equal(out.cpu(), fx[f"{reduce}_dimsize"])                       # bit-exact vs the reference's scatter
+    assert torch.equal(out.cpu()[:, :48], fx[f"{reduce}_dimsize"])               # bit-exact vs the reference's scatter
     w = torch.randn_like(out)
     (out * w).sum().backward()
-    src2 = fx["src"].to(DEV).requires_grad_(True)
+    src2 = src0.to(DEV).requires_grad_(True)
     out2 = ops.scatter(src2, index, dim=-2, dim_size=fx["n"], reduce=reduce)
     (out2 * w).sum().backward()
     assert torch.equal(out, out2) and torch.equal(src.grad, src2.grad)
-    assert torch.equal(torch_ext.scatter(fx["src"].to(DEV), index, reduce=reduce).cpu(), fx[f"{reduce}_auto"])
+    assert torch.equal(torch_ext.scatter(src0.to(DEV), index, reduce=reduce).cpu()[:, :48], fx[f"{reduce}_auto"])
+    with pytest.raises(NotImplementedError):                 # C = 48: unsupported width is reported, not computed wrongly
+        torch.ops.eqh.scatter(fx["src"].to(DEV), index, fx["n"], reduce)
 
 
 def test_primitives_match_ctypes_binding():
