@@ -645,7 +645,12 @@ def run_b200(a):
             out["roofline"] = {
                 "bound": "tensor", "kernel": "eqh_gemm_tf32x3 (fp32-faithful 3xTF32 row GEMM on tcgen05): the largest share of "
                                              "the step's kernel time",
-                "achieved": ach, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": None,
+                "achieved": ach, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach / bf16_burst,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE forward launch [2560,256]x[256,256] of this kernel
+                "traffic": 2938368.0,
+                "traffic_source": "CONSTANT from profiles/r02_kernels_ncu_full.md (ncu --set full, k_gemm_ts<64,1,1> at the "
+                                  "headline size: 2.94 MB read, 0 written -- the compulsory A tile bytes; weights and output "
+                                  "stay in L2); not re-measured by this run",
                 "peak_source": peak_src + ": dense bf16 burst (kernels timed one launch at a time); a TF32 MMA runs at half "
                                "the bf16 rate and the kernel issues 3 TF32 products per algorithmic product, so this "
                                "formulation's own ceiling is peak/6",
