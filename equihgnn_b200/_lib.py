@@ -85,6 +85,8 @@ _SIGNATURES = {
     "eqh_batchnorm_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "eqh_gemm_tf32x3_ex2": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                     c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P, _P]),
+    "eqh_gemm_tf32x3_ex3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
+                                    c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int64, _P]),
     "eqh_rank1_update": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_float, _P]),
     "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
                                   c_float, _P]),

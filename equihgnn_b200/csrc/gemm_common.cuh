@@ -66,6 +66,10 @@ struct Params {
   // + res_scale * residual  (two Linears merged into one GEMM keep the outer Linear's bias separate from the inner one's,
   // which carries the row scale / mix factor)
   const float* bias2;
+  // ReLU backward of the CONSUMER fused into this dgrad GEMM: after the residual is added, elements whose `relu_mask`
+  // [M, ld_mask] entry (the ReLU's output) is not positive are zeroed:  D = (mask > 0) ? (... + res_scale * residual) : 0
+  const float* relu_mask;
+  int64_t ld_mask;
 };
 
 // A group of independent problems launched as one grid (gemm_ts.cu: k_gemm_ts_grouped)
@@ -191,6 +195,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool has_res = final_out && p.residual != nullptr;
     const bool has_aux = final_out && p.dsilu_aux != nullptr;
+    const bool has_mask = final_out && p.relu_mask != nullptr;
     // a warp instruction covers 128 / BN rows of the tile as float4s; four such groups in flight per warp
     constexpr int LPR = BN / 4;                          // lanes per row
     constexpr int RPI = 32 / LPR;                        // rows per warp instruction
@@ -225,6 +230,11 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
               x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
               x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
             }
+            if (has_mask) {
+              const float* mp = p.relu_mask + (int64_t)(m0 + r) * p.ld_mask + n;
+              x[u].x = __ldg(mp) > 0.f ? x[u].x : 0.f; x[u].y = __ldg(mp + 1) > 0.f ? x[u].y : 0.f;
+              x[u].z = __ldg(mp + 2) > 0.f ? x[u].z : 0.f; x[u].w = __ldg(mp + 3) > 0.f ? x[u].w : 0.f;
+            }
             *reinterpret_cast<float4*>(out + (int64_t)(m0 + r) * ld + n) = x[u];
           }
         }
@@ -241,6 +251,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, float* sbias, uint3
               float x = src[j];
               if (has_aux) x *= dsilu_f(__ldg(p.dsilu_aux + (int64_t)(m0 + r) * p.ld_aux + n + j));
               if (has_res) x += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
+              if (has_mask && !(__ldg(p.relu_mask + (int64_t)(m0 + r) * p.ld_mask + n + j) > 0.f)) x = 0.f;
               dst[j] = x;
             }
           }
@@ -265,10 +276,12 @@ __device__ __forceinline__ void epilogue_store_all(const uint8_t* smem, const Pa
   const bool has_res = final_out && p.residual != nullptr;
   const bool has_aux = final_out && p.dsilu_aux != nullptr;
   const bool aux_vec = has_aux && (p.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dsilu_aux) & 15) == 0);
+  const bool has_mask = final_out && p.relu_mask != nullptr;
+  const bool mask_vec = has_mask && (p.ld_mask % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0);
   const int rows_here = min(BM, p.M - m0);
   const int total = rows_here * C4;
   for (int e0 = threadIdx.x; e0 < total; e0 += 2 * kThreads) {
-    float4 x[2], rr[2], a4[2];
+    float4 x[2], rr[2], a4[2], k4[2];
     int rr_[2], n_[2];
     bool ok[2];
 #pragma unroll
@@ -288,6 +301,12 @@ __device__ __forceinline__ void epilogue_store_all(const uint8_t* smem, const Pa
         else a4[u] = make_float4(__ldg(ap), n_[u] + 1 < p.N ? __ldg(ap + 1) : 0.f, n_[u] + 2 < p.N ? __ldg(ap + 2) : 0.f,
                                  n_[u] + 3 < p.N ? __ldg(ap + 3) : 0.f);
       }
+      if (has_mask) {
+        const float* mp = p.relu_mask + (int64_t)(m0 + r) * p.ld_mask + n_[u];
+        if (mask_vec && n_[u] + 4 <= p.N) k4[u] = __ldg(reinterpret_cast<const float4*>(mp));
+        else k4[u] = make_float4(__ldg(mp), n_[u] + 1 < p.N ? __ldg(mp + 1) : 0.f, n_[u] + 2 < p.N ? __ldg(mp + 2) : 0.f,
+                                 n_[u] + 3 < p.N ? __ldg(mp + 3) : 0.f);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -302,14 +321,21 @@ __device__ __forceinline__ void epilogue_store_all(const uint8_t* smem, const Pa
           x[u].x += p.res_scale * rr[u].x; x[u].y += p.res_scale * rr[u].y;
           x[u].z += p.res_scale * rr[u].z; x[u].w += p.res_scale * rr[u].w;
         }
+        if (has_mask) {
+          x[u].x = k4[u].x > 0.f ? x[u].x : 0.f; x[u].y = k4[u].y > 0.f ? x[u].y : 0.f;
+          x[u].z = k4[u].z > 0.f ? x[u].z : 0.f; x[u].w = k4[u].w > 0.f ? x[u].w : 0.f;
+        }
         *reinterpret_cast<float4*>(dst) = x[u];
       } else {
         const float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        const float km[4] = {has_mask ? k4[u].x : 1.f, has_mask ? k4[u].y : 1.f, has_mask ? k4[u].z : 1.f,
+                             has_mask ? k4[u].w : 1.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (n + j < p.N) {
             float t = v[j];
             if (has_res) t += p.res_scale * p.residual[(int64_t)(m0 + r) * ld + n + j];
+            if (!(km[j] > 0.f)) t = 0.f;
             dst[j] = t;
           }
         }

@@ -431,7 +431,7 @@ int eqh_gemm_grouped(const eqh_gemm_problem* problems, int n, int a_kmajor, int 
     p.M = (int)q.M; p.N = (int)q.N; p.K = (int)q.K;
     p.splits = splits[i];
     p.kb_per_split = (kb_total + splits[i] - 1) / splits[i];
-    p.stash = nullptr; p.dsilu_aux = nullptr; p.ld_aux = 0; p.bias2 = nullptr;
+    p.stash = nullptr; p.dsilu_aux = nullptr; p.ld_aux = 0; p.bias2 = nullptr; p.relu_mask = nullptr; p.ld_mask = 0;
     if (splits[i] > 1) {
       EQH_CHECK_ARG(ws && counters && !q.bias);                // the split-K finish applies scales / residual only
       p.ws = ws + ws_off;
@@ -477,10 +477,20 @@ int eqh_gemm_tf32x3_ex2(const float* A, int a_kmajor, int64_t lda, const float* 
                         int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act_flags,
                         const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
                         float* stash, const float* dsilu_aux, int64_t ld_aux, const float* bias2, eqh_stream_t stream) {
+  return eqh_gemm_tf32x3_ex3(A, a_kmajor, lda, B, b_kmajor, ldb, D, ldd, M, N, K, bias, rowscale, act_flags, residual, out_scale,
+                             res_scale, splits, ws, counters, stash, dsilu_aux, ld_aux, bias2, nullptr, 0, stream);
+}
+
+int eqh_gemm_tf32x3_ex3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                        int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act_flags,
+                        const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                        float* stash, const float* dsilu_aux, int64_t ld_aux, const float* bias2, const float* relu_mask,
+                        int64_t ld_mask, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::gemm;
-  EQH_CHECK_ARG(splits == 1 || (!stash && !dsilu_aux && !bias2));
+  EQH_CHECK_ARG(splits == 1 || (!stash && !dsilu_aux && !bias2 && !relu_mask));
   EQH_CHECK_ARG(!dsilu_aux || ld_aux >= N);
+  EQH_CHECK_ARG(!relu_mask || ld_mask >= N);
   const int act = act_flags & 0xff;
   EQH_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0 && splits >= 1 && act >= 0 && act <= 2);
   EQH_CHECK_ARG(M < (1 << 30) && N < (1 << 30) && K < (1 << 30));
@@ -522,7 +532,7 @@ int eqh_gemm_tf32x3_ex2(const float* A, int a_kmajor, int64_t lda, const float* 
   p.out_scale = out_scale; p.res_scale = res_scale;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.act = act;
   p.kb_per_split = kbps;
-  p.stash = stash; p.dsilu_aux = dsilu_aux; p.ld_aux = ld_aux; p.bias2 = bias2;
+  p.stash = stash; p.dsilu_aux = dsilu_aux; p.ld_aux = ld_aux; p.bias2 = bias2; p.relu_mask = relu_mask; p.ld_mask = ld_mask;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (persistent) return launch_ps(a_kmajor != 0, b_kmajor != 0, tmA, tmB, p, st);

@@ -87,6 +87,62 @@ __global__ void __launch_bounds__(256) k_knn16(const float* __restrict__ pos, in
   }
 }
 
+// Small clouds (N < 16384): ONE WARP PER QUERY with the top-16 list distributed over lanes 0-15 (sorted, one entry per
+// lane).  Each lane evaluates one candidate per round; a ballot finds the few that beat the current 16th distance and they
+// are inserted one by one (ascending lane = ascending index, so equal keys stay in index order) by a shuffle-up of the
+// list's tail.  ~16 (1 + ln(N/16)) insertions per query instead of a 16-deep insertion sort in every lane on (almost)
+// every candidate: 3-4x fewer instructions than k_knn16<32> at N = 2560, same keys, same tie rule, bit-identical result.
+constexpr int kWarpsPerCta = 8;
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_knn16_warp(const float* __restrict__ pos, int64_t N,
+                                                                  int32_t* __restrict__ idx, float* __restrict__ d2out) {
+  pdl_prologue();
+  __shared__ float sp[kTile * 3];
+  static_assert(kK == 16, "one list entry per lane of a half warp");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  const int64_t qc = q < N ? q : N - 1;
+  const float xi = __ldg(pos + qc * 3 + 0), yi = __ldg(pos + qc * 3 + 1), zi = __ldg(pos + qc * 3 + 2);
+  float ld = FLT_MAX;            // lanes 0-15: entry `lane` of the sorted list (lanes 16-31 mirror nothing: +inf keys)
+  int32_t lj = 0x7fffffff;
+  float thr = FLT_MAX;           // the list's 16th key, on all lanes
+  for (int64_t base = 0; base < N; base += kTile) {
+    const int n = (int)min((int64_t)kTile, N - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n * 3; t += kWarpsPerCta * 32) sp[t] = __ldg(pos + base * 3 + t);
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      const int c = c0 + lane;
+      float dd = FLT_MAX;
+      if (c < n) {
+        const float dx = __fsub_rn(xi, sp[3 * c + 0]);
+        const float dy = __fsub_rn(yi, sp[3 * c + 1]);
+        const float dz = __fsub_rn(zi, sp[3 * c + 2]);
+        dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      }
+      unsigned m = __ballot_sync(kFull, dd < thr);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float nd = __shfl_sync(kFull, dd, src);
+        if (nd < thr) {                                   // (thr may have dropped since the ballot; warp-uniform)
+          const int32_t nj = (int32_t)(base + c0 + src);
+          // insertion position = number of entries with key <= nd (equal keys have smaller indices: they stay in front)
+          const int p = __popc(__ballot_sync(kFull, lane < kK && ld <= nd));
+          const float ud = __shfl_up_sync(kFull, ld, 1);
+          const int32_t uj = __shfl_up_sync(kFull, lj, 1);
+          if (lane > p) { ld = ud; lj = uj; }
+          else if (lane == p) { ld = nd; lj = nj; }
+          thr = __shfl_sync(kFull, ld, kK - 1);
+        }
+      }
+    }
+  }
+  if (lane < kK && q < N) {
+    idx[q * kK + lane] = lj;
+    d2out[q * kK + lane] = ld;
+  }
+}
+
 }  // namespace eqh
 
 extern "C" int eqh_knn16(const float* pos, int64_t N, int32_t* idx, float* d2, eqh_stream_t stream) {
@@ -97,7 +153,8 @@ extern "C" int eqh_knn16(const float* pos, int64_t N, int32_t* idx, float* d2, e
   if (N >= 16384) {
     launch_kernel(k_knn16<8>, dim3((unsigned)((N + 31) / 32)), dim3(256), 0, st, pos, N, idx, d2);
   } else {
-    launch_kernel(k_knn16<32>, dim3((unsigned)((N + 7) / 8)), dim3(256), 0, st, pos, N, idx, d2);
+    launch_kernel(k_knn16_warp, dim3((unsigned)((N + kWarpsPerCta - 1) / kWarpsPerCta)), dim3(kWarpsPerCta * 32), 0, st, pos, N,
+                  idx, d2);
   }
   EQH_LAUNCH_RC();
 }

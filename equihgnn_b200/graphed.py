@@ -174,7 +174,7 @@ class GraphedTrainer(Trainer):
         # A node that survived from the warm-up on a different (uncaptured) stream would make the capturing stream wait
         # on uncaptured work (cudaErrorStreamCaptureIsolation); with one stream the engine has nothing to synchronise.
         if self._cap_stream is None:
-            self._cap_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("EQH_CAPTURE_PRIORITY", "0")))
+            self._cap_stream = torch.cuda.Stream(device=dev, priority=-1 if ops.STREAM_PRIORITIES else 0)   # (see ops._SideWork)
         s = self._cap_stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .fused_conv import MHNNConvFused, MHNNSConvFused, MHNNSConvMerged, conv_products
+from .fused_conv import MHNNConvFused, MHNNSConvFused, MHNNSConvMerged, MHNNSConvStack, conv_products
 from .mlp import MLP
 
 
@@ -178,7 +178,7 @@ class MHNNSConv(nn.Module):
                 and self.hid_dim in (32, 64, 128, 256, 512) and self.aggr in ("mean", "sum")
                 and ws[0].lins[0].weight.is_cuda and ws[0].lins[0].weight.dtype == torch.float32)
 
-    def prepare_products(self) -> None:
+    def prepare_products(self, accumulators: bool = True) -> None:
         """Compute the merged weights now (they depend on the parameters only).  A model that applies this ONE module
         several times (the shared conv of mhnns / egnn_equihnns) calls this ahead of its layer loop -- on a parallel branch
         of the captured graph -- then `prepare_x0(x0)` once x0 exists, and `release_products()` after the loop; without
@@ -191,7 +191,7 @@ class MHNNSConv(nn.Module):
         self._products_sticky = True
         self._app_index = 0
         self._shared_acc = None
-        if torch.is_grad_enabled():
+        if torch.is_grad_enabled() and accumulators:
             # accumulators of the merged weights' gradients over all applications of this forward pass (zeroed here; the
             # backward of application 0 converts them once)
             dev = p[0].device
@@ -234,3 +234,28 @@ class MHNNSConv(nn.Module):
             return self.W3(x)                                             # conv.py:180
 
         return _fold_leading(layer, (X, X0), 1)
+
+    def forward_stack(self, x, vertex, edges, nlayer: int, act: nn.Module, dropout: nn.Module,
+                      incidence: "ops.Incidence | None" = None, num_hyperedges=None):
+        """The layer loop of the wrappers that share ONE conv (equihnn_egnn.py:162-166, mhnn.py:126-130):
+               x0 = x;  repeat nlayer times:  x = act(conv(dropout(x), V, E, x0))
+        In the shipped configuration (ReLU, dropout inactive, LayerNorm MLPs, merged Linears) the whole loop is one
+        hand-scheduled Function (MHNNSConvStack); anything else runs the loop application by application."""
+        drop_on = dropout is not None and dropout.training and getattr(dropout, "p", 0.0) > 0.0
+        if (ops.CONV_STACK and nlayer >= 1 and isinstance(act, nn.ReLU) and not drop_on and x.dim() == 2
+                and self._mergeable() and self._layer_fusable(x)):
+            inc = incidence if incidence is not None else ops.incidence_cache.get(vertex, edges, x.shape[0], num_hyperedges)
+            eps = tuple(getattr(self, f"W{k}").normalizations[1].eps for k in (1, 2, 3))
+            direct = self.direct_param_grad and torch.is_grad_enabled()
+            products = self._products[:4] if (self._products is not None and self._products_sticky) else None
+            return MHNNSConvStack.apply(x, inc, self.aggr, float(self.alpha), direct, eps, products, int(nlayer),
+                                        *self._fused_params())
+        x0 = x
+        if self._products_sticky:
+            with ops.branch_work.fork(x.device, keep=(x0,)):          # X0 . W3.lin0^T once for all applications
+                self.prepare_x0(x0.detach())
+        for _ in range(nlayer):
+            x = dropout(x) if dropout is not None else x
+            x = self.forward(x, vertex, edges, x0, incidence=incidence, num_hyperedges=num_hyperedges)
+            x = act(x)
+        return x

@@ -81,13 +81,14 @@ class _GradSink:
         else:
             gemm_raw(dy, False, x, False, n_out, n_in, M, splits=0, out=view, residual=view if acc else None, out_scale=scale)
 
-    def scratch_weight(self, dy, x, scale: float = 1.0, into=None):
+    def scratch_weight(self, dy, x, scale: float = 1.0, into=None, accumulate: bool = True):
         """A scratch matrix (+)= scale * dy^T x (queued with the layer's weight gradients): the gradient of a MERGED weight.
-        into: an accumulator shared by several applications of one module (accumulated), else a fresh matrix."""
+        into: an accumulator shared by several applications of one module (accumulated unless accumulate is False), else a
+        fresh matrix."""
         M, n_out = dy.shape
         n_in = x.shape[1]
         out = into if into is not None else torch.empty((n_out, n_in), dtype=torch.float32, device=dy.device)
-        acc = into is not None
+        acc = into is not None and accumulate
         if self.group is not None:
             self.group.add(dy, x, n_out, n_in, M, out, accumulate=acc, out_scale=scale)
         else:
@@ -95,9 +96,9 @@ class _GradSink:
                                                   residual=out if acc else None, out_scale=scale))
         return out
 
-    def scratch_bias(self, dy, roww=None, scale: float = 1.0, into=None):
+    def scratch_bias(self, dy, roww=None, scale: float = 1.0, into=None, accumulate: bool = True):
         out = into if into is not None else torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
-        self.batch.add(dy, out, roww, scale=scale, accumulate=into is not None)
+        self.batch.add(dy, out, roww, scale=scale, accumulate=into is not None and accumulate)
         return out
 
     def bias(self, p, dy, roww=None):
@@ -252,6 +253,127 @@ def conv_products(w11, b11, w20, w21, b21, w30, C: int):
     return Wp, bp, Wq, bq
 
 
+def _merged_fwd(X, X0, Z0, inc, mode, alpha, eps, products, params, relu_out: bool):
+    """One application of MHNNSConv with merged Linears (see MHNNSConvMerged).  Z0 = X0 . W3.lin0^T or None (computed here,
+    on the branch); relu_out: the activation that follows the layer in the wrappers, in the last GEMM's epilogue.
+    -> (out, (h1, y1, Xe1, A, Bm, U, h3, y3), products, Z0, rs_e, rs_v)"""
+    (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+    N, C = X.shape
+    E = inc.E
+    dev = X.device
+    A = torch.empty((N, C), dtype=torch.float32, device=dev)
+    own_z0 = Z0 is None
+    if own_z0:
+        Z0 = torch.empty((N, C), dtype=torch.float32, device=dev)
+    with ops.branch_work.fork(dev, keep=(X, X0, A, Z0)):
+        if products is None:
+            products = conv_products(w11, b11, w20, w21, b21, w30, C)
+        gemm_raw(X, True, w20[:, :C], True, N, C, C, out=A)
+        if own_z0:
+            gemm_raw(X0, True, w30, True, N, C, C, out=Z0)
+    Wp, bp, Wq, bq = products[:4]
+    h1 = gemm_raw(X, True, w10, True, N, C, C, bias=b10)
+    y1 = _rowln_fwd(h1, g1, t1, eps[0])
+    Xe1 = gather_reduce_raw(y1, inc.vtx_by_e, inc.rowptr_e, None, E, mode)                      # conv.py:172-173
+    rs_e = inc.nonempty("e") if mode == MEAN else inc.counts("e")
+    ops.branch_work.join(dev)
+    Bm = gemm_raw(Xe1, True, Wp, True, E, C, C, bias=bp, rowscale=rs_e, bias2=b20)
+    U = torch.empty((N, C), dtype=torch.float32, device=dev)
+    _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
+          mode, _p(U), _stream(), nbytes=4.0 * C * (2 * N + E) + 4.0 * (inc.Z + N + 1))         # conv.py:175-177
+    rs_v = inc.nonempty("v") if mode == MEAN else inc.counts("v")
+    h3 = gemm_raw(U, True, Wq, True, N, C, C, bias=bq, rowscale=rs_v, out_scale=1.0 - alpha, bias2=b30, residual=Z0,
+                  res_scale=alpha)                                                              # conv.py:179 + W3.lin0
+    y3 = _rowln_fwd(h3, g3, t3, eps[2])
+    out = gemm_raw(y3, True, w31, True, N, C, C, bias=b31, act="relu" if relu_out else None)    # conv.py:180
+    return out, (h1, y1, Xe1, A, Bm, U, h3, y3), products, Z0, rs_e, rs_v
+
+
+def _merged_bwd(X, X0, layer, rs_e, rs_v, Wp, Wq, params, inc, mode, alpha, eps, dOut, sink, acc, acc_first: bool,
+                dX0, dX0_first: bool, relu_mask=None, fold_dX0: bool = False, convert: bool = True):
+    """Backward of one application (dOut: gradient of its output BEFORE the trailing activation).
+    acc: dict of the merged weights' gradient accumulators {dWp, dbp, dWq, dbq}: written when acc_first (entries are
+    created if missing), accumulated otherwise; convert: turn them into parameter gradients after this layer's weight
+    gradients.  dX0: [N, C] buffer that receives (dX0_first) or accumulates alpha * dh3 . W3.lin0; fold_dX0: add it to dX
+    (X0 is X: the first application of a stack).  relu_mask: the ReLU output that produced X -- the returned dX is already
+    the gradient of that ReLU's input.  -> dX; sink.flush() is the caller's."""
+    (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
+    h1, y1, Xe1, A, Bm, U, h3, y3 = layer
+    N, C = X.shape
+    E = inc.E
+    dev = X.device
+    # ---- W3.lin1, LayerNorm
+    dy3 = gemm_raw(dOut, True, w31, False, N, C, C)
+    sink.weight(w31, dOut, y3)
+    sink.bias(b31, dOut)
+    dh3, part = _rowln_bwd(h3, g3, eps[2], dy3)
+    sink.affine(g3, t3, part)
+    # ---- merged [W3.lin0 . W2.lin1] and the residual mix: dU on the chain, dX0 on a branch
+    with ops.branch_work.fork(dev, keep=(dh3, dX0)):
+        gemm_raw(dh3, True, w30, False, N, C, C, out=dX0, out_scale=alpha, residual=None if dX0_first else dX0)
+    dU = gemm_raw(dh3, True, Wq, False, N, C, C, out_scale=1.0 - alpha)
+    sink.bias(b30, dh3)
+    dWq = acc["dWq"] = sink.scratch_weight(dh3, U, scale=1.0 - alpha, into=acc.get("dWq"), accumulate=not acc_first)
+    dbq = acc["dbq"] = sink.scratch_bias(dh3, roww=rs_v, scale=1.0 - alpha, into=acc.get("dbq"), accumulate=not acc_first)
+    gw30, gw21, gb21 = sink.ensure(w30), sink.ensure(w21), sink.ensure(b21)
+    sink.weight(w30, dh3, X0, scale=alpha)
+    w20b = w20[:, C:]
+    # ---- fused message backward
+    dA = torch.empty_like(A)
+    dBm = torch.empty_like(Bm)
+    part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev)
+    u_rp = inc.rowptr_v if mode == MEAN else None
+    _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), N, C, _p(g2), _p(t2),
+          eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream(),
+          nbytes=4.0 * C * (3 * N + E) + 4.0 * (inc.Z + N + 1) + 8.0 * C * partial_rows())
+    _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), E, C,
+          _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream(),
+          nbytes=4.0 * C * (2 * N + 2 * E) + 4.0 * (2 * inc.Z + E + 1))
+    sink.affine(g2, t2, part)
+    # dX = dA . W2.lin0[:, :C] (+ the accumulated dX0) is needed only by the last GEMM of this backward: a parallel branch
+    dX = torch.empty((N, C), dtype=torch.float32, device=dev)
+    with ops.branch_work.fork(dev, keep=(dA, dX, dX0)):
+        gemm_raw(dA, True, w20[:, :C], False, N, C, C, out=dX, residual=dX0 if fold_dX0 else None)
+    sink.ensure(w20)
+    sink.weight(w20, dA, X, cols=slice(0, C))
+    # ---- merged [W2.lin0[:, C:] . W1.lin1] through the V2E mean
+    sink.bias(b20, dBm)
+    dWp = acc["dWp"] = sink.scratch_weight(dBm, Xe1, into=acc.get("dWp"), accumulate=not acc_first)
+    dbp = acc["dbp"] = sink.scratch_bias(dBm, roww=rs_e, into=acc.get("dbp"), accumulate=not acc_first)
+    gw20, gw11, gb11 = sink.out[id(w20)], sink.ensure(w11), sink.ensure(b11)
+
+    def convert_all():
+        """gradients of the merged weights -> the parameters' own gradients: 3 grouped launches + 2 rank-1 updates"""
+        gw20b = gw20[:, C:]
+        g1_ = ops.GemmGroup(dev, True, True)
+        g1_.add(dWq, w21, C, C, C, gw30, accumulate=True)                 # d W3.lin0 += dWq . W2.lin1^T
+        g1_.add(dWp, w11, C, C, C, gw20b, accumulate=True)                # d W2.lin0[:, C:] += dWp . W1.lin1^T
+        g1_.run()
+        g2_ = ops.GemmGroup(dev, False, False)
+        g2_.add(w30, dWq, C, C, C, gw21, accumulate=True)                 # d W2.lin1 += W3.lin0^T . dWq
+        g2_.add(w20b, dWp, C, C, C, gw11, accumulate=True)                # d W1.lin1 += W2.lin0[:, C:]^T . dWp
+        g2_.run()
+        g3_ = ops.GemmGroup(dev, True, False)                             # bias gradients: matrix-vector products
+        g3_.add(dbq.view(1, C), w30, 1, C, C, gb21.view(1, C), accumulate=True)     # db(W2.lin1) += W3.lin0^T dbq
+        g3_.add(dbp.view(1, C), w20b, 1, C, C, gb11.view(1, C), accumulate=True)    # db(W1.lin1) += W2.lin0[:, C:]^T dbp
+        g3_.run()
+        ops.rank1_update_(gw30, dbq, b21)                                 # d W3.lin0 += dbq (x) b(W2.lin1)
+        ops.rank1_update_(gw20b, dbp, b11)                                # d W2.lin0[:, C:] += dbp (x) b(W1.lin1)
+    if convert:
+        sink.after.append(convert_all)
+    dXe1 = gemm_raw(dBm, True, Wp, False, E, C, C)
+    # V2E gather-mean backward: dy1[n] = sum over n's incidences of dXe1[e] / |e|
+    dy1 = gather_reduce_raw(dXe1, inc.edge_by_v, inc.rowptr_v, inc.rowptr_e if mode == MEAN else None, N, SUM)
+    dh1, part = _rowln_bwd(h1, g1, eps[0], dy1)
+    sink.affine(g1, t1, part)
+    ops.branch_work.join(dev)
+    # dX += dh1 . W1.lin0 (in-place epilogue), then the ReLU backward of the layer below
+    gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX, relu_mask=relu_mask)
+    sink.weight(w10, dh1, X)
+    sink.bias(b10, dh1)
+    return dX
+
+
 class MHNNSConvMerged(torch.autograd.Function):
     """MHNNSConv (conv.py:169-182) with the two pairs of back-to-back Linears merged: 4 GEMMs on the critical chain of the
     forward instead of 6 (and 4 instead of 6 in the backward).  Exact algebra (linearity of the segmented mean / sum and of
@@ -266,40 +388,12 @@ class MHNNSConvMerged(torch.autograd.Function):
         """shared: None, or (accumulators {dWp, dbp, dWq, dbq}, application index) when ONE module is applied several times
         with shared products (MHNNSConv.prepare_products): every application's backward accumulates the gradients of the
         merged weights, and application 0 -- whose backward runs last -- converts them to parameter gradients once."""
-        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
         X = ops._f32(X, "MHNNSConv X")
         X0 = ops._f32(X0, "MHNNSConv X0")
-        N, C = X.shape
-        E = inc.E
-        dev = X.device
         mode = _MODES[aggr]
-        A = torch.empty((N, C), dtype=torch.float32, device=dev)
         Z0 = None if products is None or len(products) < 5 else products[4]      # X0 . W3.lin0^T, shared by the layers
-        own_z0 = Z0 is None
-        if own_z0:
-            Z0 = torch.empty((N, C), dtype=torch.float32, device=dev)
-        with ops.branch_work.fork(dev, keep=(X, X0, A, Z0)):
-            if products is None:
-                products = conv_products(w11, b11, w20, w21, b21, w30, C)
-            gemm_raw(X, True, w20[:, :C], True, N, C, C, out=A)
-            if own_z0:
-                gemm_raw(X0, True, w30, True, N, C, C, out=Z0)
-        Wp, bp, Wq, bq = products[:4]
-        h1 = gemm_raw(X, True, w10, True, N, C, C, bias=b10)
-        y1 = _rowln_fwd(h1, g1, t1, eps[0])
-        Xe1 = gather_reduce_raw(y1, inc.vtx_by_e, inc.rowptr_e, None, E, mode)                      # conv.py:172-173
-        rs_e = inc.nonempty("e") if mode == MEAN else inc.counts("e")
-        ops.branch_work.join(dev)
-        Bm = gemm_raw(Xe1, True, Wp, True, E, C, C, bias=bp, rowscale=rs_e, bias2=b20)
-        U = torch.empty((N, C), dtype=torch.float32, device=dev)
-        _call("eqh_fused_msg_fwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), _p(inc.rowptr_v), N, C, _p(g2), _p(t2), eps[1],
-              mode, _p(U), _stream(), nbytes=4.0 * C * (2 * N + E) + 4.0 * (inc.Z + N + 1))         # conv.py:175-177
-        rs_v = inc.nonempty("v") if mode == MEAN else inc.counts("v")
-        h3 = gemm_raw(U, True, Wq, True, N, C, C, bias=bq, rowscale=rs_v, out_scale=1.0 - alpha, bias2=b30, residual=Z0,
-                      res_scale=alpha)                                                              # conv.py:179 + W3.lin0
-        y3 = _rowln_fwd(h3, g3, t3, eps[2])
-        out = gemm_raw(y3, True, w31, True, N, C, C, bias=b31)                                      # conv.py:180
-        ctx.save_for_backward(X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq, *params)
+        out, layer, products, Z0, rs_e, rs_v = _merged_fwd(X, X0, Z0, inc, mode, alpha, eps, products, params, False)
+        ctx.save_for_backward(X, X0, rs_e, rs_v, products[0], products[2], *layer, *params)
         ctx.inc, ctx.mode, ctx.alpha, ctx.direct, ctx.eps = inc, mode, alpha, direct, eps
         ctx.shared = shared
         return out
@@ -307,88 +401,60 @@ class MHNNSConvMerged(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dOut):
         saved = ctx.saved_tensors
-        X, X0, h1, y1, Xe1, A, Bm, U, h3, y3, rs_e, rs_v, Wp, Wq = saved[:14]
-        acc, app = ctx.shared if ctx.shared is not None else (None, 0)
-        convert = app == 0                 # (the only application, or the one whose backward runs last)
-        params = saved[14:]
-        (w10, b10, g1, t1, w11, b11, w20, b20, g2, t2, w21, b21, w30, b30, g3, t3, w31, b31) = params
-        inc, mode, alpha, eps = ctx.inc, ctx.mode, ctx.alpha, ctx.eps
+        X, X0, rs_e, rs_v, Wp, Wq = saved[:6]
+        layer, params = saved[6:14], saved[14:]
+        acc, app = ctx.shared if ctx.shared is not None else ({}, 0)
         sink = _GradSink(params, ctx.direct)
         dOut = ops._f32(dOut, "MHNNSConv grad")
-        N, C = X.shape
-        E = inc.E
-        dev = X.device
-        # ---- W3.lin1, LayerNorm
-        dy3 = gemm_raw(dOut, True, w31, False, N, C, C)
-        sink.weight(w31, dOut, y3)
-        sink.bias(b31, dOut)
-        dh3, part = _rowln_bwd(h3, g3, eps[2], dy3)
-        sink.affine(g3, t3, part)
-        # ---- merged [W3.lin0 . W2.lin1] and the residual mix: dU on the chain, dX0 on a branch
-        dX0 = torch.empty((N, C), dtype=torch.float32, device=dev)
-        with ops.branch_work.fork(dev, keep=(dh3, dX0)):
-            gemm_raw(dh3, True, w30, False, N, C, C, out=dX0, out_scale=alpha)
-        dU = gemm_raw(dh3, True, Wq, False, N, C, C, out_scale=1.0 - alpha)
-        sink.bias(b30, dh3)
-        dWq = sink.scratch_weight(dh3, U, scale=1.0 - alpha, into=acc["dWq"] if acc else None)
-        dbq = sink.scratch_bias(dh3, roww=rs_v, scale=1.0 - alpha, into=acc["dbq"] if acc else None)
-        gw30, gw21, gb21 = sink.ensure(w30), sink.ensure(w21), sink.ensure(b21)
-        sink.weight(w30, dh3, X0, scale=alpha)
-        w20b = w20[:, C:]
-        # ---- fused message backward
-        dA = torch.empty_like(A)
-        dBm = torch.empty_like(Bm)
-        part = torch.empty((partial_rows(), 2 * C), dtype=torch.float32, device=dev)
-        u_rp = inc.rowptr_v if mode == MEAN else None
-        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), None, _p(inc.edge_by_v), None, _p(inc.rowptr_v), N, C, _p(g2), _p(t2),
-              eps[1], _p(dU), _p(u_rp), _p(dA), _p(part), _stream(),
-              nbytes=4.0 * C * (3 * N + E) + 4.0 * (inc.Z + N + 1) + 8.0 * C * partial_rows())
-        _call("eqh_fused_msg_bwd", 1, _p(A), _p(Bm), _p(inc.vtx_by_e), None, _p(inc.vtx_by_e), _p(inc.rowptr_e), E, C,
-              _p(g2), _p(t2), eps[1], _p(dU), _p(u_rp), _p(dBm), None, _stream(),
-              nbytes=4.0 * C * (2 * N + 2 * E) + 4.0 * (2 * inc.Z + E + 1))
-        sink.affine(g2, t2, part)
-        # dX = dA . W2.lin0[:, :C] is needed only by the last GEMM of this backward: a parallel branch
-        dX = torch.empty((N, C), dtype=torch.float32, device=dev)
-        with ops.branch_work.fork(dev, keep=(dA, dX)):
-            gemm_raw(dA, True, w20[:, :C], False, N, C, C, out=dX)
-        sink.ensure(w20)
-        sink.weight(w20, dA, X, cols=slice(0, C))
-        # ---- merged [W2.lin0[:, C:] . W1.lin1] through the V2E mean
-        sink.bias(b20, dBm)
-        dWp = sink.scratch_weight(dBm, Xe1, into=acc["dWp"] if acc else None)
-        dbp = sink.scratch_bias(dBm, roww=rs_e, into=acc["dbp"] if acc else None)
-        gw20, gw11, gb11 = sink.out[id(w20)], sink.ensure(w11), sink.ensure(b11)
-
-        def convert_all():
-            """gradients of the merged weights -> the parameters' own gradients: 3 grouped launches + 2 rank-1 updates"""
-            gw20b = gw20[:, C:]
-            g1_ = ops.GemmGroup(dev, True, True)
-            g1_.add(dWq, w21, C, C, C, gw30, accumulate=True)                 # d W3.lin0 += dWq . W2.lin1^T
-            g1_.add(dWp, w11, C, C, C, gw20b, accumulate=True)                # d W2.lin0[:, C:] += dWp . W1.lin1^T
-            g1_.run()
-            g2_ = ops.GemmGroup(dev, False, False)
-            g2_.add(w30, dWq, C, C, C, gw21, accumulate=True)                 # d W2.lin1 += W3.lin0^T . dWq
-            g2_.add(w20b, dWp, C, C, C, gw11, accumulate=True)                # d W1.lin1 += W2.lin0[:, C:]^T . dWp
-            g2_.run()
-            g3_ = ops.GemmGroup(dev, True, False)                             # bias gradients: matrix-vector products
-            g3_.add(dbq.view(1, C), w30, 1, C, C, gb21.view(1, C), accumulate=True)     # db(W2.lin1) += W3.lin0^T dbq
-            g3_.add(dbp.view(1, C), w20b, 1, C, C, gb11.view(1, C), accumulate=True)    # db(W1.lin1) += W2.lin0[:, C:]^T dbp
-            g3_.run()
-            ops.rank1_update_(gw30, dbq, b21)                                 # d W3.lin0 += dbq (x) b(W2.lin1)
-            ops.rank1_update_(gw20b, dbp, b11)                                # d W2.lin0[:, C:] += dbp (x) b(W1.lin1)
-        if convert:
-            sink.after.append(convert_all)
-        dXe1 = gemm_raw(dBm, True, Wp, False, E, C, C)
-        # V2E gather-mean backward: dy1[n] = sum over n's incidences of dXe1[e] / |e|
-        dy1 = gather_reduce_raw(dXe1, inc.edge_by_v, inc.rowptr_v, inc.rowptr_e if mode == MEAN else None, N, SUM)
-        dh1, part = _rowln_bwd(h1, g1, eps[0], dy1)
-        sink.affine(g1, t1, part)
-        ops.branch_work.join(dev)
-        gemm_raw(dh1, True, w10, False, N, C, C, out=dX, residual=dX)          # dX += dh1 . W1.lin0 (in-place epilogue)
-        sink.weight(w10, dh1, X)
-        sink.bias(b10, dh1)
+        dX0 = torch.empty_like(X)
+        dX = _merged_bwd(X, X0, layer, rs_e, rs_v, Wp, Wq, params, ctx.inc, ctx.mode, ctx.alpha, ctx.eps, dOut, sink,
+                         acc, ctx.shared is None, dX0, True,
+                         convert=app == 0)          # (the only application, or the one whose backward runs last)
         sink.flush()      # grouped weight gradients, column sums, then the conversions of the merged gradients
         return (dX, dX0, None, None, None, None, None, None, None) + sink.results()
+
+
+class MHNNSConvStack(torch.autograd.Function):
+    """x -> relu(conv(..relu(conv(relu(conv(x, x)), x)).., x)): `nlayer` applications of ONE shared MHNNSConv with X0 = the
+    stack's input, each followed by ReLU (the layer loop of egnn_equihnns / mhnns with dropout off: equihnn_egnn.py:162-166,
+    mhnn.py:126-130) as one hand-scheduled Function.  On top of MHNNSConvMerged: the ReLUs live in GEMM epilogues (forward:
+    act of the last GEMM; backward: `relu_mask` of the dgrad GEMM that produces the gradient of the layer below), the
+    gradient of X0 is accumulated over the applications in the epilogue of its own GEMM and folded into dX by the first
+    application, X0 . W3.lin0^T is computed once, and the merged weights' gradients are accumulated over the applications
+    and converted once -- no autograd-generated launch between the first and the last kernel of the stack."""
+
+    @staticmethod
+    def forward(ctx, X, inc, aggr, alpha, direct, eps, products, nlayer, *params):
+        X = ops._f32(X, "MHNNSConv X")
+        mode = _MODES[aggr]
+        x, Z0, layers = X, None, []
+        rs_e = rs_v = None
+        for _ in range(nlayer):
+            x, layer, products, Z0, rs_e, rs_v = _merged_fwd(x, X, Z0, inc, mode, alpha, eps, products, params, True)
+            layers += [*layer, x]                  # ... and the layer's (rectified) output: the next X and the ReLU mask
+        ctx.save_for_backward(X, rs_e, rs_v, products[0], products[2], *layers, *params)
+        ctx.inc, ctx.mode, ctx.alpha, ctx.direct, ctx.eps, ctx.nlayer = inc, mode, alpha, direct, eps, nlayer
+        return x
+
+    @staticmethod
+    def backward(ctx, dOut):
+        saved = ctx.saved_tensors
+        L = ctx.nlayer
+        X, rs_e, rs_v, Wp, Wq = saved[:5]
+        layers, params = saved[5:5 + 9 * L], saved[5 + 9 * L:]
+        sink = _GradSink(params, ctx.direct)
+        outs = [layers[9 * l + 8] for l in range(L)]
+        # ReLU backward of the last application (the others are fused into the dgrad GEMM below them)
+        d = torch.ops.aten.threshold_backward(ops._f32(dOut, "MHNNSConv grad"), outs[L - 1], 0.0)
+        dX0 = torch.empty_like(X)
+        acc = {}
+        for l in range(L - 1, -1, -1):
+            x_in = outs[l - 1] if l > 0 else X
+            d = _merged_bwd(x_in, X, layers[9 * l:9 * l + 8], rs_e, rs_v, Wp, Wq, params, ctx.inc, ctx.mode, ctx.alpha,
+                            ctx.eps, d, sink, acc, l == L - 1, dX0, l == L - 1,
+                            relu_mask=x_in if l > 0 else None, fold_dX0=l == 0, convert=l == 0)
+            sink.flush()
+        return (d, None, None, None, None, None, None, None) + sink.results()
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -235,11 +235,7 @@ class MHNNS(nn.Module):
                                   real=int(getattr(data, "num_real_graphs", 0) or 0) or None)
         x = self.atom_encoder(data.x)
         ops.prep_work.join(dev)
-        x0 = x
-        for _ in range(self.nlayer):
-            x = self.dropout(x)
-            x = self.conv(x, V, E, x0, incidence=inc)
-            x = self.act(x)
+        x = self.conv.forward_stack(x, V, E, self.nlayer, self.act, self.dropout, incidence=inc)     # mhnn.py:126-130
         x = self.dropout(x)
         x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)
         return _readout(self.mlp_out, x, loss_target)
@@ -296,9 +292,10 @@ class EGNNEquiHNNS(nn.Module):
         # fills the GPU by itself (measured: no gain at Molecule3D-1024)
         with (ops.prep_work_b.fork(data.x.device) if N < 8192 else contextlib.nullcontext()):
             graph = ops.build_knn_graph(data.pos, need_transpose=False)    # (the EGNN layer builds the transpose it needs)
-        with ops.branch_work.fork(data.x.device):          # phi_e's weight re-layout and the shared conv's merged weights
-            self.egnn_layer.prepack(data.x.device)          # depend on the parameters only
-            self.conv.prepare_products()
+        with ops.branch_work.fork(data.x.device):          # phi_e's weight re-layout depends on the parameters only
+            self.egnn_layer.prepack(data.x.device)
+        with ops.aux_work.fork(data.x.device):             # ... and so do the shared conv's merged weights, needed only after
+            self.conv.prepare_products(accumulators=not ops.CONV_STACK)     # the EGNN layer: their own branch
         x = self.atom_encoder(data.x)
         x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False,   # coors_out is discarded (:158)
                                knn_graph=graph)
@@ -306,14 +303,9 @@ class EGNNEquiHNNS(nn.Module):
         ops.prep_work.join(data.x.device)
         ops.prep_work_b.join(data.x.device)
         x = ops.grad_boundary(x)       # backward: conv / readout gradients are final here -> their bucket's exchange starts
-        x0 = x
         ops.branch_work.join(data.x.device)
-        with ops.branch_work.fork(data.x.device, keep=(x0,)):     # X0 . W3.lin0^T once for the three applications
-            self.conv.prepare_x0(x0.detach())
-        for _ in range(self.nlayer):
-            x = self.dropout(x)
-            x = self.conv(x, V, E, x0, incidence=inc)
-            x = self.act(x)
+        ops.aux_work.join(data.x.device)
+        x = self.conv.forward_stack(x, V, E, self.nlayer, self.act, self.dropout, incidence=inc)  # equihnn_egnn.py:161-166
         self.conv.release_products()
         x = self.dropout(x)
         x = ops.global_add_pool(x, data.batch, _num_graphs(data), getattr(data, "ptr", None), index=pool)

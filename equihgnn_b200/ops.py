@@ -307,15 +307,22 @@ def direct_target_strict(p) -> torch.Tensor:
     return t
 
 
+STREAM_PRIORITIES = os.environ.get("EQH_STREAM_PRIORITIES", "1") != "0"
+
+
 class _SideWork:
     """Off-critical-path work (weight / bias gradients that are accumulated straight into the flat gradient buffer)
     runs on a second stream, forked from and joined back into the step's stream with events, so that inside the
     captured CUDA graph it becomes a parallel branch next to the dX chain.  Tensors handed to the side stream are
     kept alive until the join (the caching allocator only orders reuse on the allocating stream)."""
 
-    def __init__(self):
+    def __init__(self, background: bool = False):
         self.streams = {}
         self.pending = {}
+        # background work (weight gradients) runs at the default stream priority, everything on or feeding the critical
+        # chain at high priority: when a grouped weight-gradient launch and the next dgrad GEMM become ready at the same
+        # moment, the block scheduler places the chain's CTAs first (captured kernel nodes keep their stream's priority)
+        self.priority = 0 if (background or not STREAM_PRIORITIES) else -1
         self.enabled = os.environ.get("EQH_SIDE_STREAM", "1") != "0"
         self.always = os.environ.get("EQH_SIDE_STREAM", "1") == "always"      # also outside graph capture (tests)
         self.active = 0
@@ -326,7 +333,7 @@ class _SideWork:
             key = torch.cuda.current_device()
         st = self.streams.get(key)
         if st is None:
-            st = self.streams[key] = torch.cuda.Stream(device=key)
+            st = self.streams[key] = torch.cuda.Stream(device=key, priority=self.priority)
         return st
 
     def fork(self, device, keep=()):
@@ -375,16 +382,17 @@ class _SideWork:
                 self.pending[key] = []
 
 
-side_work = _SideWork()
+side_work = _SideWork(background=True)
 # second side stream: the EGNN layer's parameter-gradient work (its backward is the tail of the step; queued behind the conv
 # layers' weight gradients and conversions on ONE stream it ended 90 us after the main chain)
-side_work_b = _SideWork()
+side_work_b = _SideWork(background=True)
 # forward-time index / packing work that nothing on the critical path needs yet (incidence CSR next to the atom encoder
 # and the kNN search, the transposed kNN incidence next to the phi_e GEMMs): a second parallel branch of the captured graph
 prep_work = _SideWork()
 # independent GEMMs of a layer whose result the critical chain needs only later (X.W2a^T of MHNNSConv next to the W1 chain,
 # its dX next to the dXe -> dY -> dh1 chain): a third parallel branch
 branch_work = _SideWork()
+aux_work = _SideWork(background=True)    # parameter-only preparation that is needed late (the shared conv's merged weights)
 prep_work_b = _SideWork()     # second branch: the kNN search (needs only the coordinates) next to the atom encoder and the phi_e GEMMs
 
 
@@ -657,13 +665,15 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
              splits: int = 1, write_hi: bool = False, rowscale=None, out: Optional[torch.Tensor] = None,
              out_scale: float = 1.0, res_scale: float = 1.0, flags: Optional[int] = None,
              stash: Optional[torch.Tensor] = None, dsilu_aux: Optional[torch.Tensor] = None,
-             bias2: Optional[torch.Tensor] = None) -> torch.Tensor:
+             bias2: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = out_scale * act(A.B^T + bias * rowscale) + res_scale * residual with A logical [M,K], B logical [N,K]; an
     operand flagged k-major is stored [rows,K], otherwise [K,rows] (see eqh_gemm_tf32x3).  `out` may be a row-strided
     view (its row stride is used as ldd) and `residual` may be `out` itself (in-place accumulation).
     splits: 1 = no split-K, 0 = let the kernel's planner choose (weight gradients), >1 = at most that many.
     stash: [M, N] tensor with D's row stride that receives the pre-activation (act = 'silu' keeps what its backward needs);
-    dsilu_aux: [M, >=N] tensor, the result is multiplied by SiLU'(dsilu_aux) before the residual (SiLU backward fused)."""
+    dsilu_aux: [M, >=N] tensor, the result is multiplied by SiLU'(dsilu_aux) before the residual (SiLU backward fused);
+    relu_mask: [M, >=N] tensor (a ReLU's output): elements where it is not positive are zeroed AFTER the residual is added
+    (the ReLU backward of the consumer fused into this dgrad GEMM)."""
     dev = A.device
     D = torch.empty((M, N), dtype=torch.float32, device=dev) if out is None else out
     ldd = D.stride(0)
@@ -679,15 +689,15 @@ def gemm_raw(A, a_kmajor: bool, B, b_kmajor: bool, M: int, N: int, K: int, bias=
             ws = torch.empty((splits, M * N), dtype=torch.float32, device=dev)
             cnt = counters(tiles, dev)
     flops = 2.0 * M * N * K
-    if stash is not None or dsilu_aux is not None or bias2 is not None:
+    if stash is not None or dsilu_aux is not None or bias2 is not None or relu_mask is not None:
         if splits != 1:
-            raise RuntimeError("gemm_raw: stash / dsilu_aux / bias2 need splits == 1")
+            raise RuntimeError("gemm_raw: stash / dsilu_aux / bias2 / relu_mask need splits == 1")
         if stash is not None and stash.stride(0) != ldd:
             raise RuntimeError("gemm_raw: stash must have the row stride of the output")
-        _call("eqh_gemm_tf32x3_ex2", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
+        _call("eqh_gemm_tf32x3_ex3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
               _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
-              _p(stash), _p(dsilu_aux), dsilu_aux.stride(0) if dsilu_aux is not None else 0, _p(bias2), _stream(),
-              nbytes=flops)
+              _p(stash), _p(dsilu_aux), dsilu_aux.stride(0) if dsilu_aux is not None else 0, _p(bias2), _p(relu_mask),
+              relu_mask.stride(0) if relu_mask is not None else 0, _stream(), nbytes=flops)
         return D
     _call("eqh_gemm_tf32x3", 1, _p(A), int(a_kmajor), A.stride(0), _p(B), int(b_kmajor), B.stride(0),
           _p(D), ldd, M, N, K, _p(bias), _p(rowscale), fl, _p(residual), out_scale, res_scale, splits, _p(ws), _p(cnt),
@@ -738,6 +748,7 @@ WGRAD_GROUPED = os.environ.get("EQH_WGRAD_GROUPED", "1") != "0"     # one groupe
 # SM budget of a grouped weight-gradient launch that runs next to the dX chain (0 = no cap: plan for latency)
 WGRAD_MAX_CTAS = int(os.environ.get("EQH_WGRAD_MAX_CTAS", "0"))
 CONV_MERGED = os.environ.get("EQH_CONV_MERGED", "1") != "0"         # MHNNSConv with its back-to-back Linears merged
+CONV_STACK = os.environ.get("EQH_CONV_STACK", "1") != "0"           # the shared conv's layer loop as ONE Function
 
 
 def rank1_update_(out: torch.Tensor, u: torch.Tensor, v: torch.Tensor, scale: float = 1.0) -> None:

@@ -208,7 +208,7 @@ class Trainer:
         dev = self.fp.flat.device
         main = torch.cuda.current_stream(dev)
         if self._comm is None:
-            self._comm = torch.cuda.Stream(device=dev)
+            self._comm = torch.cuda.Stream(device=dev, priority=-1 if ops.STREAM_PRIORITIES else 0)
         self._comm.wait_stream(main)
         side = ops.side_work.streams.get(dev.index if dev.index is not None else torch.cuda.current_device())
         if side is not None:

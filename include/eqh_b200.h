@@ -431,6 +431,14 @@ EQH_API int eqh_gemm_tf32x3_ex2(const float* A, int a_kmajor, int64_t lda, const
                         int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
                         const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
                         float* stash, const float* dsilu_aux, int64_t ld_aux, const float* bias2, eqh_stream_t stream);
+/* ... and with the ReLU backward of the consumer fused in (the activation between two MHNNSConv applications,
+ * equihnn_egnn.py:164-166 / mhnn.py:128-130): elements whose relu_mask[m, n] (the ReLU's OUTPUT, [M, ld_mask]) is not
+ * positive are zeroed after the residual is added:  D = relu_mask > 0 ? (... + res_scale * residual) : 0. */
+EQH_API int eqh_gemm_tf32x3_ex3(const float* A, int a_kmajor, int64_t lda, const float* B, int b_kmajor, int64_t ldb, float* D,
+                        int64_t ldd, int64_t M, int64_t N, int64_t K, const float* bias, const float* rowscale, int act,
+                        const float* residual, float out_scale, float res_scale, int splits, float* ws, int32_t* counters,
+                        float* stash, const float* dsilu_aux, int64_t ld_aux, const float* bias2, const float* relu_mask,
+                        int64_t ld_mask, eqh_stream_t stream);
 /* out[m, n] += u[m] * v[n]  (rank-1 update of a row-strided [M, N] matrix: the bias term of a merged weight product) */
 EQH_API int eqh_rank1_update(float* out, int64_t ld, const float* u, const float* v, int64_t M, int64_t N, float scale,
                      eqh_stream_t stream);

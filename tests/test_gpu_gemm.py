@@ -282,3 +282,22 @@ def test_gemm_tiny_row_counts(M):
     xr, wr = A.double().requires_grad_(True), B.double().requires_grad_(True)
     torch.relu(xr @ wr.t() + bias.double()).sum().backward()
     assert rel_err(x.grad, xr.grad) < 2e-6 and rel_err(w.grad, wr.grad) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(2560, 256, 256), (1000, 520, 272), (30000, 256, 256)])
+def test_gemm_relu_mask_epilogue(M, N, K):
+    """dgrad GEMM with the consumer's ReLU backward fused in: D = mask > 0 ? (dY . W + residual) : 0 -- bit-identical to
+    the unfused GEMM followed by the mask (in-place accumulation included), on the one-tile and the persistent variant."""
+    g = torch.Generator().manual_seed(M + N)
+    dY, W = _mk((M, K), g), _mk((K, N), g, 0.06)
+    res = _mk((M, N), g)
+    y = torch.relu(_mk((M + 3, N + 8), g))[3:, 4:4 + N]            # a ReLU output as a strided, unaligned view
+    plain = ops.gemm_raw(dY, True, W, False, M, N, K, residual=res)
+    D = ops.gemm_raw(dY, True, W, False, M, N, K, residual=res, relu_mask=y)
+    assert torch.equal(D, torch.where(y > 0, plain, torch.zeros_like(plain)))
+    ya = torch.relu(_mk((M, N), g))                                # aligned mask: the vector path
+    acc = res.clone()
+    ops.gemm_raw(dY, True, W, False, M, N, K, out=acc, residual=acc, relu_mask=ya)
+    assert torch.equal(acc, torch.where(ya > 0, plain, torch.zeros_like(plain)))
+    with pytest.raises(RuntimeError):
+        ops.gemm_raw(dY, True, W, False, M, N, K, splits=4, relu_mask=ya)

@@ -796,3 +796,67 @@ def test_whole_model_parity_at_large_configs(profile, B, buckets):
         print(f"{profile}-{B}: N={n_atoms} loss {loss:.7f} oracle {loss64:.7f} worst gradient error {worst:.2e}")
         assert abs(loss - loss64) < 1e-5 * max(1.0, abs(loss64))
         assert worst < 5e-3
+
+
+@pytest.mark.parametrize("cls", [EGNNEquiHNNS, MHNNS])
+@pytest.mark.parametrize("trainer", [False, True])
+def test_conv_stack_matches_the_layer_loop(cls, trainer, monkeypatch):
+    """The shared conv's layer loop as ONE Function (MHNNSConvStack: ReLUs and the X0-gradient accumulation in GEMM
+    epilogues) against the application-by-application loop of the same kernels: bit-identical forward, gradients equal up
+    to the fp32 summation order of the three X0 contributions (equihnn_egnn.py:161-166, mhnn.py:126-130)."""
+    from equihgnn_b200.train import Trainer
+    C, B = 64, 48
+    b = synthetic.make_batch("qm9", B, 77).to(DEV)
+    args = synthetic.model_args(hidden=C)
+
+    def run(stack):
+        monkeypatch.setattr(ops, "CONV_STACK", stack)
+        torch.manual_seed(9)
+        m = cls(1, args).to(DEV).train()
+        if trainer:
+            tr = Trainer(m, lr=1e-3)
+            loss = tr.forward_backward(b)
+            torch.cuda.synchronize()
+            out = (float(loss), {k: q.grad.clone() for k, q in m.named_parameters()})
+            tr.close()
+            return out
+        pred = m(b)
+        loss = F.mse_loss(pred, b.y)
+        loss.backward()
+        return (pred.detach().clone(), {k: (q.grad.clone() if q.grad is not None else None) for k, q in m.named_parameters()})
+
+    a, ga = run(True)
+    z, gz = run(False)
+    assert (a == z) if trainer else torch.equal(a, z)
+    scale = max(float(v.abs().max()) for v in gz.values() if v is not None)
+    for k in gz:
+        if gz[k] is None:
+            assert ga[k] is None or float(ga[k].abs().max()) == 0.0, k
+            continue
+        assert float((ga[k] - gz[k]).abs().max()) / scale < 2e-6, k
+
+
+def test_conv_stack_steps_aside_for_dropout_and_other_activations():
+    """Dropout in training mode or an activation other than ReLU between the applications: the loop runs application by
+    application (same result as calling the module in a Python loop)."""
+    import torch.nn as nn
+    C = 64
+    b = synthetic.make_batch("qm9", 16, 5).to(DEV)
+    torch.manual_seed(2)
+    conv = MHNNSConv(C, 2, 2, 2, aggr="mean", dropout=0.0, normalization="ln").to(DEV).train()
+    x = torch.randn(b.x.shape[0], C, device=DEV)
+    inc = ops.build_incidence(b.edge_index0, b.edge_index1, x.shape[0], int(b.edge_index1.max()) + 1)
+    for act in (nn.ReLU(), nn.SiLU()):
+        got = conv.forward_stack(x, b.edge_index0, b.edge_index1, 3, act, nn.Dropout(0.0), incidence=inc)
+        want = x
+        for _ in range(3):
+            want = act(conv(want, b.edge_index0, b.edge_index1, x, incidence=inc))
+        assert rel_err(got, want) < 1e-6, type(act).__name__
+    drop = nn.Dropout(0.5).train()
+    torch.manual_seed(3)
+    got = conv.forward_stack(x, b.edge_index0, b.edge_index1, 2, nn.ReLU(), drop, incidence=inc)
+    torch.manual_seed(3)
+    want = x
+    for _ in range(2):
+        want = torch.relu(conv(drop(want), b.edge_index0, b.edge_index1, x, incidence=inc))
+    assert torch.equal(got, want)
