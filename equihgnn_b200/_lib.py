@@ -58,6 +58,7 @@ _SIGNATURES = {
     "eqh_atom_encoder_slices": (c_int, [c_int64]),
     "eqh_atom_encoder_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "eqh_atom_encoder_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P, _P]),
+    "eqh_collate_incidence": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     "eqh_collate": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
     "eqh_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "eqh_gemm_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
@@ -87,6 +88,12 @@ _SIGNATURES = {
                                     c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P, _P]),
     "eqh_gemm_tf32x3_ex3": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                     c_int, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int64, _P]),
+    "eqh_egnn_edge_slot_keys": (c_int, [c_int64]),
+    "eqh_egnn_edge_slots_mark": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
+    "eqh_egnn_edge_slots_assign": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P]),
+    "eqh_egnn_edge_bwd_tc_slots": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P,
+                                           _P, _P, _P, _P]),
+    "eqh_cell_order": (c_int, [_P, c_int64, _P, _P, c_size_t, _P]),
     "eqh_rank1_update": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_float, _P]),
     "eqh_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P,
                                   c_float, _P]),
@@ -117,6 +124,17 @@ class Store(ctypes.Structure):
     """struct eqh_store (include/eqh_b200.h)"""
     _fields_ = [(n, c_void_p) for n in ("x", "pos", "y", "v_loc", "e_loc", "edge_attr", "e_order", "atom_off", "he_off",
                                         "inc_off")]
+
+
+class StoreCsr(ctypes.Structure):
+    """struct eqh_store_csr (include/eqh_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("rowptr_e_loc", "perm_e_loc", "rowptr_v_loc", "perm_v_loc")]
+
+
+class IncidenceOut(ctypes.Structure):
+    """struct eqh_incidence_out (include/eqh_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("rowptr_e", "perm_e", "vtx_by_e", "rowptr_v", "perm_v", "edge_by_v", "vertex32",
+                                        "edges32")]
 
 
 class Batch(ctypes.Structure):

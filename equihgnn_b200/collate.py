@@ -41,6 +41,19 @@ class MoleculeStore:
         }
         self.c_store = _lib.Store(**{k: v.data_ptr() for k, v in self.t.items()})
         self.size = len(mols)
+        # per-molecule LOCAL incidence CSR in both groupings (stable orders, computed once per dataset): the collation
+        # emits the batch's CSR from these by gather + offset (eqh_collate_incidence) instead of rebuilding it every step
+        rp_e, pm_e, rp_v, pm_v = [], [], [], []
+        for m in mols:
+            v_loc, e_loc = np.asarray(m[4], dtype=np.int64), np.asarray(m[5], dtype=np.int64)
+            pm_e.append(np.argsort(e_loc, kind="stable"))
+            pm_v.append(np.argsort(v_loc, kind="stable"))
+            rp_e.append(np.concatenate([[0], np.cumsum(np.bincount(e_loc, minlength=m[1]))]))
+            rp_v.append(np.concatenate([[0], np.cumsum(np.bincount(v_loc, minlength=m[0]))]))
+        cat32 = lambda parts: dev(np.concatenate(parts).astype(np.int32))
+        self.csr = {"rowptr_e_loc": cat32(rp_e), "perm_e_loc": cat32(pm_e), "rowptr_v_loc": cat32(rp_v),
+                    "perm_v_loc": cat32(pm_v)}
+        self.c_csr = _lib.StoreCsr(**{k: v.data_ptr() for k, v in self.csr.items()})
 
     def shape_of(self, ids: Sequence[int]) -> Tuple[int, int, int]:
         ids = np.asarray(ids, dtype=np.int64)
@@ -71,11 +84,31 @@ def empty_packed(B: int, bucket: Optional[Tuple[int, int, int]], shape: Tuple[in
     return like.pack(device=device)
 
 
+def empty_incidence(shape: Tuple[int, int, int], device) -> ops.Incidence:
+    """Uninitialised incidence CSR buffers of a batch with (N, E, Z) atoms / hyperedges / incidences: views into one buffer."""
+    N, E, Z = shape
+    sizes = [("rowptr_e", E + 1), ("perm_e", Z), ("vtx_by_e", Z), ("rowptr_v", N + 1), ("perm_v", Z), ("edge_by_v", Z),
+             ("vertex32", Z), ("edges32", Z)]
+    total, offs = 0, []
+    for _, n in sizes:
+        offs.append(total)
+        total += (n + 3) // 4 * 4               # 16-byte aligned fields
+    flat = torch.empty(total, dtype=torch.int32, device=device)
+    f = {name: flat[o:o + n] for (name, n), o in zip(sizes, offs)}
+    inc = ops.Incidence(N, E, Z, f["rowptr_e"], f["perm_e"], f["vtx_by_e"], f["rowptr_v"], f["perm_v"], f["edge_by_v"],
+                        f["vertex32"], f["edges32"])
+    inc._flat = flat
+    return inc
+
+
 def collate_device(store: MoleculeStore, ids: Sequence[int], bucket: Optional[Tuple[int, int, int]] = None,
-                   out: Optional[HBatch] = None, step_inputs: Optional[torch.Tensor] = None) -> HBatch:
+                   out: Optional[HBatch] = None, step_inputs: Optional[torch.Tensor] = None,
+                   with_incidence: bool = True) -> HBatch:
     """Gather the molecules `ids` into one batch on the device.  bucket=(N_pad, E_pad, Z_pad) appends the ghost molecule
     (graphed.pad_batch); `out` is a packed batch of the right shape to write into (e.g. a captured graph's static
-    inputs); `step_inputs` a pinned buffer from store.step_inputs(ids) (built here when omitted)."""
+    inputs); `step_inputs` a pinned buffer from store.step_inputs(ids) (built here when omitted).
+    with_incidence: also emit the batch's incidence CSR (`out.incidence`, both groupings) from the store's per-molecule
+    CSRs -- the model wrappers then skip the per-step build (ops.incidence_of)."""
     B = len(ids)
     N, E, Z = store.shape_of(ids)
     Np, Ep, Zp = bucket if bucket is not None else (N, E, Z)
@@ -95,7 +128,15 @@ def collate_device(store: MoleculeStore, ids: Sequence[int], bucket: Optional[Tu
     import ctypes
     ops._call("eqh_collate", 1, ctypes.byref(store.c_store), dev_in.data_ptr(), dev_in.data_ptr() + 4 * B, B, N, E, Z, Np, Ep,
               Zp, side, origin, ctypes.byref(c_out), ops._stream())
-    out._keep = dev_in          # the kernel reads it asynchronously
+    if with_incidence:
+        inc = getattr(out, "incidence", None)
+        if inc is None or (inc.N, inc.E, inc.Z) != (Np, Ep, Zp):
+            inc = out.incidence = empty_incidence((Np, Ep, Zp), store.device)
+        c_inc = _lib.IncidenceOut(**{f: getattr(inc, f).data_ptr() for f in ("rowptr_e", "perm_e", "vtx_by_e", "rowptr_v",
+                                                                             "perm_v", "edge_by_v", "vertex32", "edges32")})
+        ops._call("eqh_collate_incidence", 1, ctypes.byref(store.c_store), ctypes.byref(store.c_csr), dev_in.data_ptr(),
+                  dev_in.data_ptr() + 4 * B, B, N, E, Z, Np, Ep, Zp, ctypes.byref(c_inc), ops._stream())
+    out._keep = dev_in          # the kernels read it asynchronously
     return out
 
 
@@ -104,10 +145,11 @@ class StoreTrainer(GraphedTrainer):
     fixed_bucket: pad every batch to this (N_pad, E_pad, Z_pad) instead of its own bucket (uniform shapes over ranks)."""
 
     def __init__(self, model, store: MoleculeStore, real_graphs: int, fixed_bucket: Optional[Tuple[int, int, int]] = None,
-                 **kw):
+                 with_incidence: bool = True, **kw):
         super().__init__(model, real_graphs, **kw)
         self.store = store
         self.fixed_bucket = fixed_bucket
+        self.with_incidence = with_incidence      # the collation emits the incidence CSR: no build kernels in the graph
 
     def step_from_ids(self, ids: Sequence[int], step_inputs: Optional[torch.Tensor] = None, sync: bool = True):
         shape = self.store.shape_of(ids)
@@ -116,12 +158,12 @@ class StoreTrainer(GraphedTrainer):
         key = (bucket[0], bucket[1], bucket[2], len(ids) + 1)
         bk = self.buckets.get(key)
         if bk is None:
-            like = collate_device(self.store, ids, bucket)
+            like = collate_device(self.store, ids, bucket, with_incidence=self.with_incidence)
             bk = self.buckets[key] = self._capture(like)
-        collate_device(self.store, ids, bucket, out=bk.static, step_inputs=step_inputs)
+        collate_device(self.store, ids, bucket, out=bk.static, step_inputs=step_inputs, with_incidence=self.with_incidence)
         bk.graph.replay()
         self.replays += 1
-        self.own_launches += bk.launches + 1
+        self.own_launches += bk.launches + (2 if self.with_incidence else 1)
         if self.in_graph_step:
             self.t += 1
         self._finish_outside()

@@ -101,7 +101,103 @@ __global__ void __launch_bounds__(256) k_collate(const __grid_constant__ Collate
   if (t <= G) a.out.ptr[t] = t <= B ? (int64_t)__ldg(aoff + t) : a.Np;
 }
 
+struct CollateCsrArgs {
+  eqh_store st;
+  eqh_store_csr csr;
+  const int32_t* ids;
+  const int32_t* off;
+  int32_t B;
+  int64_t N, E, Z, Np, Ep, Zp;
+  eqh_incidence_out out;
+};
+
+// ghost segments: incidence zi of the gz ghost incidences belongs to segment zi % n_seg, so segment s holds
+// zi = s, s + n_seg, ...: q + (s < r) of them (q = gz / n_seg, r = gz % n_seg) and starts at s * q + min(s, r)
+__device__ __forceinline__ int64_t ghost_start(int64_t s, int64_t q, int64_t r) { return s * q + (s < r ? s : r); }
+// sorted position p (0 <= p < gz) -> the incidence zi that lands there
+__device__ __forceinline__ int64_t ghost_source(int64_t p, int64_t q, int64_t r, int64_t n_seg) {
+  int64_t s, j;
+  if (p < r * (q + 1)) { s = p / (q + 1); j = p - s * (q + 1); }
+  else { const int64_t u = p - r * (q + 1); s = r + u / q; j = u - (u / q) * q; }     // (q >= 1 here: p >= r (q + 1) and p < gz)
+  return s + j * n_seg;
+}
+
+__global__ void __launch_bounds__(256) k_collate_csr(const __grid_constant__ CollateCsrArgs a) {
+  pdl_prologue();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int B = a.B;
+  const int32_t* aoff = a.off;
+  const int32_t* hoff = a.off + (B + 1);
+  const int32_t* zoff = a.off + 2 * (B + 1);
+  const int64_t ga = a.Np - a.N, ge = a.Ep - a.E, gz = a.Zp - a.Z;
+  // ---- per incidence: both sorted orders and the int32 index lists
+  if (t < a.Zp) {
+    if (t < a.Z) {
+      const int b = find_mol(zoff, B, t);
+      const int32_t z0 = __ldg(zoff + b), a0 = __ldg(aoff + b), h0 = __ldg(hoff + b);
+      const int64_t src = __ldg(a.st.inc_off + __ldg(a.ids + b));
+      const int32_t k = (int32_t)(t - z0);
+      const int32_t pe = __ldg(a.csr.perm_e_loc + src + k), pv = __ldg(a.csr.perm_v_loc + src + k);
+      a.out.perm_e[t] = z0 + pe;
+      a.out.vtx_by_e[t] = a0 + __ldg(a.st.v_loc + src + pe);
+      a.out.perm_v[t] = z0 + pv;
+      a.out.edge_by_v[t] = h0 + __ldg(a.st.e_loc + src + pv);
+      a.out.vertex32[t] = a0 + __ldg(a.st.v_loc + src + k);
+      a.out.edges32[t] = h0 + __ldg(a.st.e_loc + src + k);
+    } else {
+      const int64_t zi = t - a.Z;
+      a.out.vertex32[t] = (int32_t)(a.N + zi % ga);
+      a.out.edges32[t] = (int32_t)(a.E + zi % ge);
+      const int64_t se = ghost_source(zi, gz / ge, gz % ge, ge);
+      a.out.perm_e[t] = (int32_t)(a.Z + se);
+      a.out.vtx_by_e[t] = (int32_t)(a.N + se % ga);
+      const int64_t sv = ghost_source(zi, gz / ga, gz % ga, ga);
+      a.out.perm_v[t] = (int32_t)(a.Z + sv);
+      a.out.edge_by_v[t] = (int32_t)(a.E + sv % ge);
+    }
+  }
+  // ---- row pointers
+  if (t <= a.Ep) {
+    if (t < a.E) {
+      const int b = find_mol(hoff, B, t);
+      const int64_t m = __ldg(a.ids + b);
+      a.out.rowptr_e[t] = __ldg(zoff + b) + __ldg(a.csr.rowptr_e_loc + __ldg(a.st.he_off + m) + m + (t - __ldg(hoff + b)));
+    } else {
+      a.out.rowptr_e[t] = (int32_t)(a.Z + (ge > 0 ? ghost_start(t - a.E, gz / ge, gz % ge) : 0));
+    }
+  }
+  if (t <= a.Np) {
+    if (t < a.N) {
+      const int b = find_mol(aoff, B, t);
+      const int64_t m = __ldg(a.ids + b);
+      a.out.rowptr_v[t] = __ldg(zoff + b) + __ldg(a.csr.rowptr_v_loc + __ldg(a.st.atom_off + m) + m + (t - __ldg(aoff + b)));
+    } else {
+      a.out.rowptr_v[t] = (int32_t)(a.Z + (ga > 0 ? ghost_start(t - a.N, gz / ga, gz % ga) : 0));
+    }
+  }
+}
+
 }  // namespace eqh
+
+extern "C" int eqh_collate_incidence(const eqh_store* store, const eqh_store_csr* csr, const int32_t* ids, const int32_t* offsets,
+                                     int64_t B, int64_t N, int64_t E, int64_t Z, int64_t N_pad, int64_t E_pad, int64_t Z_pad,
+                                     const eqh_incidence_out* out, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(store && csr && ids && offsets && out && B > 0 && B < (1 << 24) && N >= 0 && E >= 0 && Z >= 0);
+  EQH_CHECK_ARG(N_pad >= N && E_pad >= E && Z_pad >= Z && N_pad < ((int64_t)1 << 31) && Z_pad < ((int64_t)1 << 31));
+  const bool ghost = N_pad > N;
+  EQH_CHECK_ARG(ghost ? (E_pad > E) : (E_pad == E && Z_pad == Z));
+  EQH_CHECK_ARG(csr->rowptr_e_loc && csr->perm_e_loc && csr->rowptr_v_loc && csr->perm_v_loc);
+  EQH_CHECK_ARG(out->rowptr_e && out->perm_e && out->vtx_by_e && out->rowptr_v && out->perm_v && out->edge_by_v &&
+                out->vertex32 && out->edges32);
+  CollateCsrArgs a;
+  a.st = *store; a.csr = *csr; a.ids = ids; a.off = offsets; a.B = (int32_t)B;
+  a.N = N; a.E = E; a.Z = Z; a.Np = N_pad; a.Ep = E_pad; a.Zp = Z_pad; a.out = *out;
+  int64_t m = N_pad + 1 > Z_pad ? N_pad + 1 : Z_pad;
+  if (E_pad + 1 > m) m = E_pad + 1;
+  launch_kernel(k_collate_csr, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
+  EQH_LAUNCH_RC();
+}
 
 extern "C" int eqh_collate(const eqh_store* store, const int32_t* ids, const int32_t* offsets, int64_t B, int64_t N, int64_t E,
                            int64_t Z, int64_t N_pad, int64_t E_pad, int64_t Z_pad, int64_t ghost_side, float ghost_origin,

@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "eqh_b200.h"
 
 #ifndef __CUDA_ARCH__
@@ -53,8 +56,30 @@ static inline bool pdl_enabled() {
 }
 #endif
 
+// Every kernel of the library asks for the MAXIMUM shared-memory carve-out, also those that use none.  An SM changes its
+// L1 / shared-memory split only when it is empty: a CTA of a small kernel launched under the driver's default (small)
+// carve-out keeps every 194-200 KB GEMM / edge-kernel CTA of a parallel graph branch off that SM until it has drained, and
+// vice versa (measured in the step timeline: the P|Q GEMM started only when the neighbour search next to it retired its
+// first CTAs, row kernels next to a grouped weight-gradient launch took 19 us instead of 4).  With one split everywhere
+// the branches of the captured step really share SMs.  EQH_SMEM_CARVEOUT=default restores the driver's choice.
+static inline void prefer_max_smem(const void* kernel) {
+#ifndef __CUDA_ARCH__
+  static const bool on = []() {
+    const char* e = getenv("EQH_SMEM_CARVEOUT");
+    return !(e && e[0] == 'd');
+  }();
+  if (!on) return;
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert(kernel).second)
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
+}
+
 template <typename... KArgs, typename... Args>
 static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  prefer_max_smem(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

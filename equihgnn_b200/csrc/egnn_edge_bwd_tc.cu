@@ -60,6 +60,8 @@ struct Meta {
   int32_t j[EB];
   float dd[EB];
   int32_t atom[2];
+  int32_t slot[EB];   // slot mode: row of the partial-dQ buffer this edge accumulates into
+  uint8_t first8[4];  // ... and, bit k of byte 2 * half + (k >> 3) [k & 7]: the edge is the first of its slot (it writes)
 };
 constexpr uint32_t kW2TBytes = GC * 128;           // [128 c][hi 16 | lo 16] K-major, 128B swizzle
 constexpr uint32_t kBBytes = EB * 128;             // 4 KB: B1 [32 e][hi 16 | lo 16], B2 [hi 16 | lo 16 rows][32 e]
@@ -130,12 +132,40 @@ __device__ __forceinline__ float fast_dsilu(float x) {
 // byte offset of 16-byte chunk `chunk` of row `row` in a K-major tile with 128-byte rows and the 128B swizzle
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
 
+// ---- slot mode (dQ partial sums inside the CTA's sub-slices instead of one dPre row per edge) --------------------------
+// The slice of a CTA is cut into kEpiWG contiguous SUB-SLICES, one per column warpgroup: block bl of the pipeline (the
+// warpgroup bl % kEpiWG processes it) is block sub_start(bl % kEpiWG) + bl / kEpiWG of the slice.  All edges of a sub-slice
+// that point at the same atom j accumulate into ONE row ("slot") of the partial buffer, in the warpgroup's own program
+// order (deterministic, no atomics: one thread owns a column of a sub-slice for the whole kernel); with the atoms in grid-
+// cell order a sub-slice of ~600 atoms hits each of its neighbours 5-6 times, so the buffer and the reduction that follows
+// shrink by that factor.  Slots are numbered j-major (egnn_edge_slots.cu): the rows of one j are consecutive and the final
+// dQ[j] is a plain segmented sum over consecutive rows.
+struct SubSlice {
+  int64_t b_begin;   // first block (two atoms) of the slice
+  int nb;            // blocks in the slice
+  int start[kEpiWG]; // first block of each sub-slice, relative to b_begin
+};
+__host__ __device__ __forceinline__ SubSlice sub_slices(int64_t N, int nslices, int sl) {
+  SubSlice s;
+  const int64_t nblk = (N + 1) >> 1;
+  s.b_begin = nblk * sl / nslices;
+  s.nb = (int)(nblk * (sl + 1) / nslices - s.b_begin);
+  int at = 0;
+  for (int w = 0; w < kEpiWG; ++w) {
+    s.start[w] = at;
+    at += (s.nb - w + kEpiWG - 1) / kEpiWG;      // pipeline blocks bl < nb with bl % kEpiWG == w
+  }
+  return s;
+}
+
+template <bool SLOTS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ wc,
               const float* __restrict__ W2, const int32_t* __restrict__ idx, const float* __restrict__ d2,
               const float* __restrict__ S2, const float* __restrict__ dMi, int64_t N, int H, int ngroups, int nslices,
               float* __restrict__ dP, float* __restrict__ dPre, float* __restrict__ part, int64_t part_cols,
-              const int32_t* __restrict__ order, int64_t ldpq, int64_t lddp, int64_t lddmi) {
+              const int32_t* __restrict__ order, int64_t ldpq, int64_t lddp, int64_t lddmi,
+              const int32_t* __restrict__ slot_edge) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* ds_full = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [DSLOT] dS2 tiles + meta written
@@ -161,6 +191,11 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
   const int64_t nblk = (N + 1) >> 1;           // blocks of two atoms
   const int64_t b_begin = nblk * sl / nslices, b_end = nblk * (sl + 1) / nslices;
   const int nb = (int)(b_end - b_begin);
+  constexpr bool slots = SLOTS;
+  // slot mode: first block of the sub-slices of warpgroups 1 and 2 (sub_slices(): warpgroup w owns the pipeline blocks
+  // bl < nb with bl % kEpiWG == w, as one contiguous run of the slice)
+  static_assert(kEpiWG == 3, "sub-slice starts below");
+  const int ss1 = (nb + 2) / 3, ss2 = ss1 + (nb + 1) / 3;
   const int64_t ld = H;
 
   if (threadIdx.x == 0) {
@@ -222,12 +257,15 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     constexpr int PD = 4;
     struct PV {
       float4 s2, gm;
-      int32_t jj, atom;
+      int32_t jj, atom, slot;
       float dd;
     };
     auto load_atom = [&](int bl) -> int32_t {           // atom of this thread's edge in block bl; -1: none
       if (bl >= nb) return -1;
-      const int64_t aslot = (b_begin + bl) * 2 + (el >> 4);
+      // slot mode: the warpgroup bl % kEpiWG walks its own contiguous sub-slice
+      const int wq = bl % kEpiWG;
+      const int64_t blk = slots ? (int64_t)(wq == 0 ? 0 : (wq == 1 ? ss1 : ss2)) + bl / kEpiWG : (int64_t)bl;
+      const int64_t aslot = (b_begin + blk) * 2 + (el >> 4);
       if (aslot >= N) return -1;
       return order ? __ldg(order + aslot) : (int32_t)aslot;
     };
@@ -236,6 +274,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       v.atom = atom;
       v.s2 = v.gm = make_float4(0.f, 0.f, 0.f, 0.f);
       v.jj = 0;
+      v.slot = 0;
       v.dd = 0.f;
       if (atom >= 0) {
         const int64_t e = (int64_t)atom * kNbr + (el & 15);
@@ -244,6 +283,7 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         if (oq == 0) {
           v.jj = __ldg(idx + e);
           v.dd = __ldg(d2 + e);
+          if (slots) v.slot = __ldg(slot_edge + e);
         }
       }
       return v;
@@ -273,7 +313,15 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
       if (oq == 0) {
         m->j[el] = v.jj;
         m->dd[el] = v.dd;
+        m->slot[el] = v.slot & 0x7fffffff;
         if ((el & 15) == 0) m->atom[el >> 4] = v.atom;
+      }
+      if (slots) {      // this warp's 8 edges (lanes 0, 4, .., 28) -> one byte of first-edge flags
+        const unsigned bal = __ballot_sync(kFull, oq == 0 && v.slot < 0);
+        unsigned m8 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m8 |= ((bal >> (4 * i)) & 1u) << i;
+        if (lane == 0) m->first8[warp] = (uint8_t)m8;
       }
       db[0] += ds.x; db[1] += ds.y; db[2] += ds.z; db[3] += ds.w;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -374,6 +422,8 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
     const bool cv = col < H;
     const float wcr = cv ? __ldg(wc + col) : 0.f;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const char* slot_base = reinterpret_cast<const char*>(dPre + col);      // slot mode: row s of this column at + s * ldb
+    const uint32_t ldb = (uint32_t)ld * 4u;
     float dwc = 0.f;
     // Q[j] / P[i] row segments (512 B each) of the warpgroup's NEXT block are copied into shared memory with 16-byte
     // cp.async (one row per warp instruction, fully coalesced) while the current block is processed.
@@ -427,6 +477,22 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
         const bool wr = cv && at >= 0;
         const float pi = wr ? qs[(EB + half) * GC] : 0.f;
         float dh[kNbr], hv[kNbr];
+        // slot mode: the rows this atom's 16 edges accumulate into are fetched BEFORE the element math (one L2 round trip
+        // hidden behind ~600 instructions).  The 16 neighbours of one atom are distinct, so are their slots; earlier
+        // updates of a slot were made by THIS thread (its column, its sub-slice) -- program order is the only ordering
+        // needed, and the volatile asm keeps the loads behind the previous half's stores.  The first edge of a slot
+        // writes (no zero-fill of the buffer).
+        float old[kNbr];
+        if (slots && wr) {
+          const uint32_t fm = reinterpret_cast<const uint16_t*>(m->first8)[half];
+#pragma unroll
+          for (int k = 0; k < kNbr; ++k) {
+            const uint32_t sk = (uint32_t)m->slot[half * 16 + k];
+            old[k] = 0.f;
+            if (!((fm >> k) & 1u))
+              asm volatile("ld.global.f32 %0, [%1];" : "=f"(old[k]) : "l"(slot_base + (uint64_t)sk * ldb) : "memory");
+          }
+        }
         tmem_ld16(d1 + half * 16, dh);
         float dpa = 0.f;
 #pragma unroll
@@ -443,10 +509,17 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
           dwc += dd * dpre;
           dh[k] = dpre;
         }
-        if (wr) {                                         // one branch per atom: the element loop above is straight-line code
+        if (wr && !slots) {                               // one branch per atom: the element loop above is straight-line code
           float* dprow = dPre + ((int64_t)at * kNbr) * ld + col;
 #pragma unroll
           for (int k = 0; k < kNbr; ++k, dprow += ld) *dprow = dh[k];
+          dP[(int64_t)at * lddp + col] = dpa;
+        } else if (wr) {
+#pragma unroll
+          for (int k = 0; k < kNbr; ++k) {
+            const uint32_t sk = (uint32_t)m->slot[half * 16 + k];
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(slot_base + (uint64_t)sk * ldb), "f"(old[k] + dh[k]) : "memory");
+          }
           dP[(int64_t)at * lddp + col] = dpa;
         }
         tmem_st16(a2 + half * 16, hv);                    // hi: the tensor core ignores the low 13 bits
@@ -496,6 +569,54 @@ k_edge_bwd_tc(const float* __restrict__ P, const float* __restrict__ Q, const fl
   }
 }
 
+// ---- slot numbering (integer work; deterministic: atomicMin only) ------------------------------------------------------
+// position ap of the visiting order -> sub-slice u = slice * kEpiWG + warpgroup
+__device__ __forceinline__ int sub_slice_of(int64_t ap, int64_t N, int nslices) {
+  const int64_t nblk = (N + 1) >> 1, B = ap >> 1;
+  int sl = (int)(((B + 1) * nslices + nblk - 1) / nblk) - 1;         // largest sl with nblk * sl / nslices <= B
+  sl = sl < 0 ? 0 : (sl >= nslices ? nslices - 1 : sl);
+  while (sl > 0 && nblk * sl / nslices > B) --sl;
+  while (sl + 1 < nslices && nblk * (sl + 1) / nslices <= B) ++sl;
+  const SubSlice ss = sub_slices(N, nslices, sl);
+  const int rb = (int)(B - ss.b_begin);
+  int w = 0;
+#pragma unroll
+  for (int k = 1; k < kEpiWG; ++k)
+    if (rb >= ss.start[k]) w = k;
+  return sl * kEpiWG + w;
+}
+
+// pass 1: mark[j * U + u] = first position-edge (ap * 16 + k) of the pair (neighbour j, sub-slice u); mark starts at INT_MAX
+__global__ void __launch_bounds__(256) k_slots_mark(const int32_t* __restrict__ idx, const int32_t* __restrict__ order,
+                                                    int64_t N, int nslices, int32_t* __restrict__ mark) {
+  pdl_prologue();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= N * kNbr) return;
+  const int64_t ap = t / kNbr;
+  const int k = (int)(t % kNbr);
+  const int64_t atom = order ? __ldg(order + ap) : ap;
+  const int32_t j = __ldg(idx + atom * kNbr + k);
+  const int U = nslices * kEpiWG;
+  atomicMin(mark + (int64_t)j * U + sub_slice_of(ap, N, nslices), (int32_t)t);
+}
+
+// pass 2 (after an exclusive scan of [mark != INT_MAX] into slot_ext): slot_edge[atom * 16 + k] = slot | first-edge flag
+__global__ void __launch_bounds__(256) k_slots_assign(const int32_t* __restrict__ idx, const int32_t* __restrict__ order,
+                                                      int64_t N, int nslices, const int32_t* __restrict__ mark,
+                                                      const int32_t* __restrict__ slot_ext, int32_t* __restrict__ slot_edge) {
+  pdl_prologue();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= N * kNbr) return;
+  const int64_t ap = t / kNbr;
+  const int k = (int)(t % kNbr);
+  const int64_t atom = order ? __ldg(order + ap) : ap;
+  const int32_t j = __ldg(idx + atom * kNbr + k);
+  const int U = nslices * kEpiWG;
+  const int64_t key = (int64_t)j * U + sub_slice_of(ap, N, nslices);
+  const int32_t slot = __ldg(slot_ext + key);
+  slot_edge[atom * kNbr + k] = __ldg(mark + key) == (int32_t)t ? (slot | (int32_t)0x80000000) : slot;
+}
+
 static int groups_of(int64_t H) { return (int)((H + GC - 1) / GC); }
 static int slices_of(int64_t H) {
   const int gr = groups_of(H);
@@ -530,18 +651,63 @@ int eqh_egnn_edge_bwd_tc_ld(const float* P, const float* Q, int64_t ldpq, const 
                             const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi, int64_t N,
                             int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
                             eqh_stream_t stream) {
+  return eqh_egnn_edge_bwd_tc_slots(P, Q, ldpq, wc, W2, idx, d2, S2, dMi, lddmi, N, H, dP, lddp, dPre, part, order, nullptr,
+                                    stream);
+}
+
+// Slot numbering for the slot mode below (see k_edge_bwd_tc).  keys = N * eqh_egnn_edge_slot_keys(H) pairs (neighbour j,
+// sub-slice u), j-major.  Pass 1: `mark` [keys] (filled with INT32_MAX by the caller) <- first edge of every pair; the
+// caller turns [mark != INT32_MAX] into its exclusive prefix sum `slot_ext` [keys + 1]; pass 2: `slot_edge` [N*16].
+// slot_ext[j * U] (U = keys per j) is then the row pointer of the final segmented sum dQ[j] = sum of the rows of j.
+int eqh_egnn_edge_slot_keys(int64_t H) { return H > 0 ? eqh::edge_bwd_tc::slices_of(H) * eqh::edge_bwd_tc::kEpiWG : 0; }
+
+int eqh_egnn_edge_slots_mark(const int32_t* idx, const int32_t* order, int64_t N, int64_t H, int32_t* mark,
+                             eqh_stream_t stream) {
+  using namespace eqh;
+  using namespace eqh::edge_bwd_tc;
+  EQH_CHECK_ARG(idx && mark && N >= 0 && H > 0 && N * (int64_t)slices_of(H) * kEpiWG < ((int64_t)1 << 31));
+  if (N == 0) return EQH_OK;
+  launch_kernel(k_slots_mark, dim3((unsigned)((N * kNbr + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), idx,
+                order, N, slices_of(H), mark);
+  EQH_LAUNCH_RC();
+}
+
+int eqh_egnn_edge_slots_assign(const int32_t* idx, const int32_t* order, int64_t N, int64_t H, const int32_t* mark,
+                               const int32_t* slot_ext, int32_t* slot_edge, eqh_stream_t stream) {
+  using namespace eqh;
+  using namespace eqh::edge_bwd_tc;
+  EQH_CHECK_ARG(idx && mark && slot_ext && slot_edge && N >= 0 && H > 0);
+  if (N == 0) return EQH_OK;
+  launch_kernel(k_slots_assign, dim3((unsigned)((N * kNbr + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), idx,
+                order, N, slices_of(H), mark, slot_ext, slot_edge);
+  EQH_LAUNCH_RC();
+}
+
+// Slot mode: `slot_edge` [N*16] from eqh_egnn_edge_slots (NULL: one dPre row per edge, as above); dPre then receives one row
+// per (sub-slice, neighbour) pair -- at most N*16 rows, numbered j-major.
+int eqh_egnn_edge_bwd_tc_slots(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                               const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi,
+                               int64_t N, int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
+                               const int32_t* slot_edge, eqh_stream_t stream) {
   using namespace eqh;
   using namespace eqh::edge_bwd_tc;
   EQH_CHECK_ARG(P && Q && wc && W2 && idx && d2 && S2 && dMi && dP && dPre && part && N >= 0);
   EQH_CHECK_ARG(aligned16(S2) && aligned16(dMi) && aligned16(P) && aligned16(Q));
   EQH_CHECK_ARG(ldpq >= H && ldpq % 4 == 0 && lddp >= H && lddmi >= kM && lddmi % 4 == 0);
   if (H <= 0 || H % 64 != 0 || groups_of(H) > kSMs) return EQH_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-  if (e != cudaSuccess) return (int)e;
   const int gr = groups_of(H), sl = slices_of(H);
   const int64_t part_cols = (int64_t)(kM + 1) * H + kM;
-  launch_kernel(k_edge_bwd_tc, dim3((unsigned)(gr * sl)), dim3(kThreads), (size_t)kSmem, static_cast<cudaStream_t>(stream), P, Q, wc,
-                W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order, ldpq, lddp, lddmi);
+  if (slot_edge) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return (int)e;
+    launch_kernel(k_edge_bwd_tc<true>, dim3((unsigned)(gr * sl)), dim3(kThreads), (size_t)kSmem, static_cast<cudaStream_t>(stream),
+                  P, Q, wc, W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order, ldpq, lddp, lddmi, slot_edge);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return (int)e;
+    launch_kernel(k_edge_bwd_tc<false>, dim3((unsigned)(gr * sl)), dim3(kThreads), (size_t)kSmem, static_cast<cudaStream_t>(stream),
+                  P, Q, wc, W2, idx, d2, S2, dMi, N, (int)H, gr, sl, dP, dPre, part, part_cols, order, ldpq, lddp, lddmi, slot_edge);
+  }
   EQH_LAUNCH_RC();
 }
 

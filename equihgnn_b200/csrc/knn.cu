@@ -93,10 +93,13 @@ __global__ void __launch_bounds__(256) k_knn16(const float* __restrict__ pos, in
 // list's tail.  ~16 (1 + ln(N/16)) insertions per query instead of a 16-deep insertion sort in every lane on (almost)
 // every candidate: 3-4x fewer instructions than k_knn16<32> at N = 2560, same keys, same tie rule, bit-identical result.
 constexpr int kWarpsPerCta = 8;
+// small candidate tile (6 KB): two or three of these CTAs per SM leave room for a 194 KB GEMM CTA next to them (the P|Q
+// GEMM of phi_e runs beside the search)
+constexpr int kTileW = 512;
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_knn16_warp(const float* __restrict__ pos, int64_t N,
                                                                   int32_t* __restrict__ idx, float* __restrict__ d2out) {
   pdl_prologue();
-  __shared__ float sp[kTile * 3];
+  __shared__ float sp[kTileW * 3];
   static_assert(kK == 16, "one list entry per lane of a half warp");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = (int64_t)blockIdx.x * kWarpsPerCta + warp;
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_knn16_warp(const float* _
   float ld = FLT_MAX;            // lanes 0-15: entry `lane` of the sorted list (lanes 16-31 mirror nothing: +inf keys)
   int32_t lj = 0x7fffffff;
   float thr = FLT_MAX;           // the list's 16th key, on all lanes
-  for (int64_t base = 0; base < N; base += kTile) {
-    const int n = (int)min((int64_t)kTile, N - base);
+  for (int64_t base = 0; base < N; base += kTileW) {
+    const int n = (int)min((int64_t)kTileW, N - base);
     __syncthreads();
     for (int t = threadIdx.x; t < n * 3; t += kWarpsPerCta * 32) sp[t] = __ldg(pos + base * 3 + t);
     __syncthreads();

@@ -238,6 +238,29 @@ size_t eqh_knn16_grid_workspace_bytes(int64_t N) {
   return b;
 }
 
+// The grid-cell visiting order alone (atoms sorted by cell, stable): small clouds are searched by brute force, but the
+// phi_e backward's in-kernel dQ partial sums (eqh_egnn_edge_bwd_tc_slots) want spatially coherent slices all the same.
+int eqh_cell_order(const float* pos, int64_t N, int32_t* order, void* ws, size_t ws_bytes, eqh_stream_t stream) {
+  using namespace eqh;
+  EQH_CHECK_ARG(pos && order && ws && N > 0 && N < ((int64_t)1 << 31));
+  if (ws_bytes < eqh_knn16_grid_workspace_bytes(N)) return EQH_ERR_WORKSPACE;
+  EQH_CHECK_ARG(aligned16(ws));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int G = grid_dim_for(N);
+  const int64_t cells = (int64_t)G * G * G;
+  const int64_t Np = (N + 3) / 4 * 4;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  GridParams* gp = reinterpret_cast<GridParams*>(w);  w += 256;
+  int32_t* cell = reinterpret_cast<int32_t*>(w);      w += sizeof(int32_t) * Np * 2;
+  int32_t* dst32 = reinterpret_cast<int32_t*>(w);     w += sizeof(int32_t) * Np;
+  int32_t* cell_start = reinterpret_cast<int32_t*>(w); w += sizeof(int32_t) * ((cells + 1 + 3) / 4 * 4);
+  w += sizeof(float4) * N;
+  launch_kernel(k_grid_box, dim3(1), dim3(1024), 0, st, pos, N, (int32_t)G, gp);
+  launch_kernel(k_grid_cell, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, st, pos, N, (const GridParams*)gp, cell);
+  return eqh_incidence_build_i32(cell, nullptr, N, cells, cell_start, order, dst32, nullptr, nullptr, w,
+                                 eqh_incidence_workspace_bytes(N, cells), stream);
+}
+
 int eqh_knn16_grid(const float* pos, int64_t N, int32_t* idx, float* d2, void* ws, size_t ws_bytes, eqh_stream_t stream) {
   return eqh_knn16_grid_ordered(pos, N, idx, d2, nullptr, ws, ws_bytes, stream);
 }

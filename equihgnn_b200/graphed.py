@@ -162,6 +162,8 @@ class GraphedTrainer(Trainer):
         # static inputs: one contiguous buffer with every field a view into it (HBatch.pack), so a packed batch of the
         # same shapes arrives with a single copy
         static = like.pack(device=dev)
+        if getattr(like, "incidence", None) is not None:
+            static.incidence = like.incidence       # CSR buffers filled by the device collation next to the batch fields
         # warm-up on a side stream (NCCL / autograd buffers), then capture.  The warm-up steps must leave no trace: module
         # buffers (BatchNorm running statistics of mhnnm) and -- when the optimizer is part of the body -- parameters,
         # Adam moments and the step counter are restored afterwards.

@@ -145,8 +145,8 @@ class EGNN(nn.Module):
             raise NotImplementedError("equihgnn_b200.EGNN: dropout > 0 in training mode is not implemented")
         if feats.dim() != 3 or feats.shape[0] != 1:
             raise NotImplementedError("equihgnn_b200.EGNN expects feats [1,N,C] (the whole batch as one point cloud)")
-        h = feats[0]
-        x = coors[0]
+        h = feats.squeeze(0)       # (a view both ways: feats[0] would cost a zero-fill + copy in the backward)
+        x = coors.squeeze(0)
         N, C = h.shape
         if self._fusable(h, x, need_coors):
             from .fused_egnn import EGNNFused, pack_phi_e

@@ -159,7 +159,7 @@ class _SharedConvBase(nn.Module):
         dev = data.x.device
         real = int(getattr(data, "num_real_graphs", 0) or 0) or None
         with ops.prep_work.fork(dev):
-            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc = ops.incidence_of(data, N, _num_hyperedges(data))
             inc.nonempty("e"), inc.nonempty("v")
             pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None), real=real)
             he_pool = hyperedge_batch_index(data)
@@ -229,7 +229,7 @@ class MHNNS(nn.Module):
         N = data.x.shape[0]
         dev = data.x.device
         with ops.prep_work.fork(dev):
-            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc = ops.incidence_of(data, N, _num_hyperedges(data))
             inc.nonempty("e"), inc.nonempty("v")
             pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None),
                                   real=int(getattr(data, "num_real_graphs", 0) or 0) or None)
@@ -284,7 +284,7 @@ class EGNNEquiHNNS(nn.Module):
         V, E = data.edge_index0, data.edge_index1
         N = data.x.shape[0]
         with ops.prep_work.fork(data.x.device):          # captured graph: the incidence CSR is built next to the encoder / kNN search
-            inc = ops.build_incidence(V, E, N, _num_hyperedges(data))
+            inc = ops.incidence_of(data, N, _num_hyperedges(data))
             inc.nonempty("e"), inc.nonempty("v")             # count / mask vectors of the mean aggregation
             pool = ops.pool_index(data.batch, _num_graphs(data), getattr(data, "ptr", None),
                                   real=int(getattr(data, "num_real_graphs", 0) or 0) or None)
@@ -356,7 +356,7 @@ class MHNNM(nn.Module):
             x, _ = self.egnn_layer(x.unsqueeze(0), data.pos.unsqueeze(0), need_coors=False)    # coors_out discarded (:242)
             x = x.squeeze(0)
         e = bond_encode(self.bond_encoder, data.edge_attr)
-        inc = ops.build_incidence(V, E, N, e.shape[0])
+        inc = ops.incidence_of(data, N, e.shape[0])
         real = int(getattr(data, "num_real_graphs", 0) or 0)
         # ghost-padded batch: the padding atoms follow the real ones and stay out of the BatchNorm statistics; their number
         # is read on the device (ptr[real]: it changes between replays of one captured graph)

@@ -8,6 +8,7 @@ sm_100a kernel in csrc/.
 from __future__ import annotations
 
 import contextlib
+import dataclasses
 import os
 import weakref
 from dataclasses import dataclass
@@ -166,6 +167,18 @@ def build_incidence(vertex: torch.Tensor, edges: torch.Tensor, num_vertices: int
     rowptr_v, perm_v, vertex32, edge_by_v = csr_build(vertex, num_vertices, edges)
     return Incidence(num_vertices, num_hyperedges, vertex.numel(), rowptr_e, perm_e, vtx_by_e, rowptr_v, perm_v,
                      edge_by_v, vertex32, edges32)
+
+
+def incidence_of(data, num_vertices: int, num_hyperedges: Optional[int]) -> Incidence:
+    """The batch's incidence CSR: the one its collation emitted (`data.incidence`, collate.collate_device: no build
+    kernels in the step) when it matches the batch, else built here from the index lists."""
+    inc = getattr(data, "incidence", None)
+    if (inc is not None and inc.N == num_vertices and inc.Z == data.edge_index0.numel()
+            and (num_hyperedges is None or inc.E == num_hyperedges)):
+        # a fresh view: the lazily derived count / mask vectors must be recomputed from the CURRENT row pointers (the
+        # buffers are the static inputs of a captured graph, rewritten before every replay)
+        return dataclasses.replace(inc, _nonempty_e=None, _nonempty_v=None, _cnt_e=None, _cnt_v=None)
+    return build_incidence(data.edge_index0, data.edge_index1, num_vertices, num_hyperedges)
 
 
 class _IncidenceCache:
@@ -906,7 +919,10 @@ def atom_encode(x: torch.Tensor, tables) -> torch.Tensor:
     return _AtomEncode.apply(x, *tables)
 
 
+# phi_e backward with in-kernel dQ partial sums (layers/fused_egnn.py): None = when the atoms are visited in cell order
+EDGE_SLOTS = {"1": True, "0": False}.get(os.environ.get("EQH_EDGE_SLOTS", ""), None)
 EDGE_CELL_ORDER = os.environ.get("EQH_EDGE_CELL_ORDER", "1") != "0"   # edge kernels visit atoms in grid-cell order
+SMALL_CELL_ORDER = os.environ.get("EQH_SMALL_CELL_ORDER", "0") == "1"   # cell visiting order below KNN_GRID_MIN atoms too
 KNN_GRID_MIN = int(os.environ.get("EQH_KNN_GRID_MIN", "8192"))     # atoms per batch from which the cell grid is used
 
 
@@ -931,6 +947,12 @@ def knn16(pos: torch.Tensor, method: Optional[str] = None, return_order: bool = 
         _call("eqh_knn16_grid_ordered", 8, _p(pos), N, _p(idx), _p(d2), _p(order), _p(ws), nb, _stream())
     else:
         _call("eqh_knn16", 1, _p(pos), N, _p(idx), _p(d2), _stream())
+        if return_order and EDGE_CELL_ORDER and SMALL_CELL_ORDER:
+            # brute-force search, but the edge kernels still visit the atoms cell by cell (see fused_egnn._slot_mode)
+            nb = _lib.load().eqh_knn16_grid_workspace_bytes(N)
+            ws = torch.empty(nb, dtype=torch.uint8, device=pos.device)
+            order = torch.empty(N, dtype=torch.int32, device=pos.device)
+            _call("eqh_cell_order", 6, _p(pos), N, _p(order), _p(ws), nb, _stream())
     return (idx, d2, order) if return_order else (idx, d2)
 
 
@@ -1010,6 +1032,7 @@ class KnnGraph:
     rowptr_j: torch.Tensor   # [N+1] int32
     perm_j: torch.Tensor     # [N*16] int32 edge ids sorted by j (stable)
     order: Optional[torch.Tensor] = None   # [N] int32 atoms in grid-cell order (large batches): visiting order of the edge kernels
+    slots: Optional[tuple] = None          # (slot_edge, slot rowptr, Hp): slot numbering of the phi_e backward (fused_egnn._build_slots)
 
 
 def build_knn_graph(pos: torch.Tensor, need_transpose: bool = True) -> KnnGraph:

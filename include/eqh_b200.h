@@ -179,6 +179,10 @@ EQH_API int eqh_knn16_grid(const float* pos /*[N,3]*/, int64_t N, int32_t* idx /
  * neighbour-row gathers of the edge kernels local (the *_ordered entry points below). */
 EQH_API int eqh_knn16_grid_ordered(const float* pos, int64_t N, int32_t* idx, float* d2, int32_t* order /*[N]*/, void* ws,
                            size_t ws_bytes, eqh_stream_t stream);
+/* The cell visiting order alone: order [N] = atoms sorted by grid cell (stable), same grid as eqh_knn16_grid; workspace
+ * of eqh_knn16_grid_workspace_bytes(N). */
+EQH_API int eqh_cell_order(const float* pos, int64_t N, int32_t* order, void* ws, size_t ws_bytes, eqh_stream_t stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * EGNN edge model phi_e + neighbour pooling (egnn_layer.py:298-310,357-358).
@@ -313,6 +317,33 @@ EQH_API int eqh_collate(const eqh_store* store, const int32_t* ids /*dev [B]*/, 
                 int64_t B, int64_t N, int64_t E, int64_t Z, int64_t N_pad, int64_t E_pad, int64_t Z_pad, int64_t ghost_side,
                 float ghost_origin, const eqh_batch* out, eqh_stream_t stream);
 
+/* The incidence CSR of the collated batch (both groupings, what eqh_incidence_build_* would compute from the batch's
+ * edge_index0 / edge_index1: data/utils.py:172-178 numbering, conv.py:173/177 scatters) straight out of the collation:
+ * a batch is a block-diagonal concatenation of molecules in id order, so its stable by-hyperedge / by-vertex orders are
+ * the molecules' own LOCAL orders (computed once per dataset, kept in the store) shifted by the molecule's offsets --
+ * one gather + offset per element instead of histogram / scan / placement / ordering passes every step; the ghost
+ * molecule's segments (incidence zi -> atom N + zi % ga, hyperedge E + zi % ge) are closed-form.
+ * Bit-exact against eqh_incidence_build_i64 on the collated index lists.  All outputs int32. */
+typedef struct eqh_store_csr {
+  const int32_t* rowptr_e_loc; /* per molecule n_he+1 entries, molecule m starts at he_off[m] + m */
+  const int32_t* perm_e_loc;   /* [incidences] local position of the k-th incidence in by-hyperedge order */
+  const int32_t* rowptr_v_loc; /* per molecule n_atoms+1 entries, molecule m starts at atom_off[m] + m */
+  const int32_t* perm_v_loc;   /* [incidences] */
+} eqh_store_csr;
+typedef struct eqh_incidence_out {
+  int32_t* rowptr_e;  /* [E_pad+1] */
+  int32_t* perm_e;    /* [Z_pad] */
+  int32_t* vtx_by_e;  /* [Z_pad] */
+  int32_t* rowptr_v;  /* [N_pad+1] */
+  int32_t* perm_v;    /* [Z_pad] */
+  int32_t* edge_by_v; /* [Z_pad] */
+  int32_t* vertex32;  /* [Z_pad] edge_index0 as int32 */
+  int32_t* edges32;   /* [Z_pad] edge_index1 as int32 */
+} eqh_incidence_out;
+EQH_API int eqh_collate_incidence(const eqh_store* store, const eqh_store_csr* csr, const int32_t* ids /*dev [B]*/,
+                          const int32_t* offsets /*dev [3][B+1]*/, int64_t B, int64_t N, int64_t E, int64_t Z, int64_t N_pad,
+                          int64_t E_pad, int64_t Z_pad, const eqh_incidence_out* out, eqh_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * fp32-faithful row GEMM on the tcgen05 tensor cores (3xTF32 operand splitting, fp32 accumulate):
  *     D[M,N] = act( A . B^T + bias ) + residual          A logical [M,K], B logical [N,K]
@@ -412,6 +443,26 @@ EQH_API int eqh_egnn_edge_bwd_tc_ld(const float* P, const float* Q, int64_t ldpq
                             const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi, int64_t N,
                             int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
                             eqh_stream_t stream);
+/* phi_e backward with the dQ reduction started INSIDE the kernel ("slot mode"; egnn_layer.py:298-310 autograd, the
+ * scatter of d h_j): instead of one dPre row per kNN edge (16 N rows written, then read back by the segmented sum over the
+ * transposed neighbour lists) every (sub-slice of the visiting order, neighbour j) pair owns ONE row that its edges
+ * accumulate into in program order -- deterministic, no atomics.  With the atoms in grid-cell order a sub-slice meets each
+ * neighbour 5-6 times (measured on Molecule3D- / PCQM4Mv2-shaped batches), so the buffer and the reduction shrink by that
+ * factor.  Slots are numbered j-major: dQ[j] = sum of the consecutive rows slot_ext[j*U] .. slot_ext[(j+1)*U].
+ *   U = eqh_egnn_edge_slot_keys(H);  mark [N*U] int32 filled with INT32_MAX by the caller;
+ *   eqh_egnn_edge_slots_mark -> mark;  slot_ext [N*U+1] = exclusive prefix sum of (mark != INT32_MAX) (caller);
+ *   eqh_egnn_edge_slots_assign -> slot_edge [N*16];  eqh_egnn_edge_bwd_tc_slots(..., slot_edge): dPre receives the slot
+ *   rows (at most N*16), everything else as eqh_egnn_edge_bwd_tc_ld.  slot_edge == NULL: one row per edge. */
+EQH_API int eqh_egnn_edge_slot_keys(int64_t H);
+EQH_API int eqh_egnn_edge_slots_mark(const int32_t* idx, const int32_t* order, int64_t N, int64_t H, int32_t* mark,
+                             eqh_stream_t stream);
+EQH_API int eqh_egnn_edge_slots_assign(const int32_t* idx, const int32_t* order, int64_t N, int64_t H, const int32_t* mark,
+                               const int32_t* slot_ext, int32_t* slot_edge, eqh_stream_t stream);
+EQH_API int eqh_egnn_edge_bwd_tc_slots(const float* P, const float* Q, int64_t ldpq, const float* wc, const float* W2,
+                               const int32_t* idx, const float* d2, const float* S2, const float* dMi, int64_t lddmi,
+                               int64_t N, int64_t H, float* dP, int64_t lddp, float* dPre, float* part, const int32_t* order,
+                               const int32_t* slot_edge, eqh_stream_t stream);
+
 /* gradients of phi_e's packed weights back into the parameters' own layout, accumulating (inverse of eqh_egnn_pack):
  * T [2 Hp, C] = [dP | dQ]^T . h, red = (dW2 [16, Hp] | dwc [Hp] | db2 [16]) */
 EQH_API int eqh_egnn_unpack_grads(const float* T, const float* red, int64_t H0, int64_t C, int64_t Hp, float* gW1, float* gW2,

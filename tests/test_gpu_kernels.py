@@ -787,3 +787,93 @@ def test_kernels_write_only_their_outputs():
     _call("eqh_egnn_edge_fwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2), _p(b2), _p(idx32), _p(d2.contiguous()),
           N, Hp, S2.data_ptr(), None, ni.data_ptr(), C + 16, None, _stream())
     cz.check()
+
+
+@pytest.mark.parametrize("profile,B,H,ordered", [("qm9", 13, 192, False), ("qm9", 128, 1088, False), ("molecule3d", 320, 320, True),
+                                                  ("molecule3d", 121, 1088, True)])
+def test_egnn_edge_bwd_slot_mode(profile, B, H, ordered):
+    """phi_e backward with the dQ partial sums inside the kernel (eqh_egnn_edge_bwd_tc_slots).  The slot numbering is
+    integer work, checked exactly against a numpy restatement (one slot per (sub-slice, neighbour) pair, j-major, the
+    first edge of a pair flagged); dQ summed over the slot rows matches the fp64 scatter of d pre over the neighbour lists,
+    and dP / the weight-gradient partial sums those of the edge-row mode bit for bit up to the visiting order."""
+    import numpy as np
+    from equihgnn_b200.layers.fused_egnn import _build_slots
+    lib = ops._lib.load()
+    b = synthetic.make_batch(profile, B, 5)
+    pos = b.pos.to(DEV)
+    N = b.num_atoms
+    if ordered:
+        idx, d2, order = ops.knn16(pos, method="grid", return_order=True)
+    else:
+        idx, d2 = ops.knn16(pos)
+        order = None
+    graph = ops.KnnGraph(idx, d2, None, None, order)
+    slot_edge, rowptr = _build_slots(graph, N, H)
+    # ---- numpy restatement of the numbering
+    S, U = lib.eqh_egnn_edge_bwd_tc_rows(H), lib.eqh_egnn_edge_slot_keys(H)
+    assert U == 3 * S
+    nblk = (N + 1) // 2
+    ordr = order.cpu().numpy().astype(np.int64) if order is not None else np.arange(N)
+    sub = np.empty(N, dtype=np.int64)                     # sub-slice of every position of the visiting order
+    for sl in range(S):
+        b0, b1 = nblk * sl // S, nblk * (sl + 1) // S
+        nb = b1 - b0
+        start = 0
+        for w in range(3):
+            cnt = (nb - w + 2) // 3
+            lo, hi = (b0 + start) * 2, min((b0 + start + cnt) * 2, N)
+            sub[lo:hi] = sl * 3 + w
+            start += cnt
+    jj = idx.cpu().numpy().astype(np.int64)[ordr]            # [position, k]
+    key = jj * U + sub[:, None]
+    flat = key.reshape(-1)
+    uniq, first_pos = np.unique(flat, return_index=True)  # ascending keys = j-major slot order; first edge of every pair
+    slot_of = np.searchsorted(uniq, flat)
+    want = slot_of.astype(np.int64)
+    want_first = np.zeros(flat.shape[0], dtype=bool)
+    want_first[first_pos] = True
+    got = slot_edge.cpu().numpy().astype(np.int64).reshape(N, 16)[ordr].reshape(-1)      # back to position order
+    assert np.array_equal(got & 0x7fffffff, want)
+    assert np.array_equal((got & 0x80000000) != 0, want_first)
+    rp = np.concatenate([[0], np.cumsum(np.bincount(uniq // U, minlength=N))])
+    assert np.array_equal(rowptr.cpu().numpy().astype(np.int64), rp)
+    # ---- the kernel in slot mode against the edge-row mode and fp64
+    g = torch.Generator().manual_seed(H + B)
+    mk = lambda *s, sc=1.0: (sc * torch.randn(*s, generator=g)).to(DEV)
+    P, Q, wc, W2, b2 = mk(N, H, sc=0.5), mk(N, H, sc=0.5), mk(H, sc=0.3), mk(16, H, sc=0.1), mk(16, sc=0.1)
+    dMi = mk(N, 16)
+    S2 = torch.empty(N * 16, 16, device=DEV); Mi = torch.empty(N, 16, device=DEV)
+    ops._call("eqh_egnn_edge_fwd_tc_ordered", 1, P.data_ptr(), Q.data_ptr(), wc.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+              idx.data_ptr(), d2.data_ptr(), N, H, S2.data_ptr(), None, Mi.data_ptr(), ops._p(order), ops._stream())
+    res = {}
+    for mode in ("rows", "slots", "slots2"):
+        dP = torch.full_like(P, float("nan")); dPre = torch.full((N * 16, H), float("nan"), device=DEV)
+        part = torch.full((S, 17 * H + 16), float("nan"), device=DEV)
+        ops._call("eqh_egnn_edge_bwd_tc_slots", 1, P.data_ptr(), Q.data_ptr(), H, wc.data_ptr(), W2.data_ptr(), idx.data_ptr(),
+                  d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), 16, N, H, dP.data_ptr(), H, dPre.data_ptr(), part.data_ptr(),
+                  ops._p(order), None if mode == "rows" else slot_edge.data_ptr(), ops._stream())
+        dQ = torch.empty(N, H, device=DEV)
+        if mode == "rows":
+            rpj, pj, _, _ = ops.csr_build(idx.view(-1), N, None)
+            ops._call("eqh_gather_reduce_ld", 1, dPre.data_ptr(), H, pj.data_ptr(), rpj.data_ptr(), None, N, H, ops.SUM,
+                      dQ.data_ptr(), H, ops._stream())
+        else:
+            ops._call("eqh_gather_reduce_ld", 1, dPre.data_ptr(), H, None, rowptr.data_ptr(), None, N, H, ops.SUM,
+                      dQ.data_ptr(), H, ops._stream())
+        res[mode] = (dP, dQ, ops.colsum_raw(part))
+    torch.cuda.synchronize()
+    Pd, Qd, wcd, W2d = (t.double().cpu() for t in (P, Q, wc, W2))
+    jl = idx.cpu().long()
+    pre = Pd[:, None, :] + Qd[jl] + d2.cpu().double()[..., None] * wcd
+    sg = torch.sigmoid(pre)
+    s2 = S2.cpu().double().view(N, 16, 16)
+    s2g = torch.sigmoid(s2)
+    dS2 = dMi.cpu().double()[:, None, :] * (s2g * (1 + s2 * (1 - s2g)))
+    dpre = (dS2 @ W2d) * (sg * (1 + pre * (1 - sg)))
+    dQ64 = torch.zeros(N, H, dtype=torch.float64).index_add_(0, jl.reshape(-1), dpre.reshape(N * 16, H))
+    for mode in ("rows", "slots"):
+        assert torch.isfinite(res[mode][1]).all(), mode
+        assert rel_err(res[mode][0], dpre.sum(1)) < TOL and rel_err(res[mode][1], dQ64) < TOL, mode
+    assert rel_err(res["slots"][2], res["rows"][2].double()) < TOL
+    for a_, b_ in zip(res["slots"], res["slots2"]):        # deterministic
+        assert torch.equal(a_, b_)

@@ -860,3 +860,32 @@ def test_conv_stack_steps_aside_for_dropout_and_other_activations():
     for _ in range(2):
         want = torch.relu(conv(drop(want), b.edge_index0, b.edge_index1, x, incidence=inc))
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("profile,B", [("qm9", 40), ("molecule3d", 300)])
+def test_egnn_slot_mode_matches_edge_row_mode(profile, B, monkeypatch):
+    """The EGNN layer's backward with the dQ partial sums inside the phi_e kernel (one row per (sub-slice, neighbour)
+    pair) against one dPre row per edge + segmented sum over the transposed neighbour lists: same forward bits, gradients
+    equal up to the fp32 summation order (egnn_layer.py:298-310 autograd)."""
+    from equihgnn_b200.train import Trainer
+    C = 64
+    b = synthetic.make_batch(profile, B, 31).to(DEV)
+    args = synthetic.model_args(hidden=C)
+
+    def run(slots):
+        monkeypatch.setattr(ops, "EDGE_SLOTS", slots)
+        torch.manual_seed(12)
+        m = EGNNEquiHNNS(1, args).to(DEV).train()
+        tr = Trainer(m, lr=1e-3)
+        loss = tr.forward_backward(b)
+        torch.cuda.synchronize()
+        out = (float(loss), {k: q.grad.clone() for k, q in m.named_parameters()})
+        tr.close()
+        return out
+
+    la, ga = run(True)
+    lz, gz = run(False)
+    assert la == lz
+    scale = max(float(v.abs().max()) for v in gz.values())
+    for k in gz:
+        assert float((ga[k] - gz[k]).abs().max()) / scale < 2e-6, k
