@@ -63,6 +63,47 @@ __global__ void __launch_bounds__(256) k_gather_reduce(const float* __restrict__
   }
 }
 
+// Wide rows whose width is a multiple of 4 but not of 128 (the phi_e hidden width 1088 = 8.5 x 128): column blocks of 128
+// floats, one float4 per lane (a 512-byte run per warp instruction instead of the 256 bytes of the 64-column blocks the
+// divisor rule would pick), lanes past the row's end idle.  Unweighted sum only (the dQ reduction of the EGNN backward).
+__global__ void __launch_bounds__(256) k_gather_reduce_wide(const float* __restrict__ table, const int32_t* __restrict__ idx,
+                                                            const int32_t* __restrict__ rowptr, int64_t n_out, int64_t C,
+                                                            float* __restrict__ out, int64_t ld, int64_t ld_out) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int64_t col = (int64_t)blockIdx.y * 128 + lane * 4;
+  const bool live = col < C;                    // (C % 4 == 0: a float4 is entirely inside or outside)
+  table += col;
+  out += col;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp; s < n_out; s += nwarps) {
+    const int32_t lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t k = lo;
+    for (; k + 8 <= hi; k += 8) {
+      int32_t r[8];
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = idx ? __ldg(idx + k + u) : (k + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        x[u] = (live && r[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(table + (int64_t)r[u] * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {             // strictly ascending k: same association as a sequential scatter_add_
+        acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w;
+      }
+    }
+    for (; k < hi; ++k) {
+      const int32_t r = idx ? __ldg(idx + k) : k;
+      if (!live || r < 0) continue;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(table + (int64_t)r * ld));
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    if (live) *reinterpret_cast<float4*>(out + s * ld_out) = acc;
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ table, const int32_t* __restrict__ idx,
                                                       const int32_t* __restrict__ scale_rowptr, int64_t n_rows,
@@ -127,6 +168,11 @@ int eqh_gather_reduce_ld(const float* table, int64_t ld_table, const int32_t* id
   if (C <= 0 || CB == 0 || C / CB > 65535) return EQH_ERR_UNSUPPORTED;
   if (n_out == 0) return EQH_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (CB < 128 && C > 128 && C % 4 == 0 && !src_rowptr && mode == EQH_REDUCE_SUM) {
+    const dim3 gridw(grid_for_warps(n_out, 256), (unsigned)((C + 127) / 128));
+    launch_kernel(k_gather_reduce_wide, dim3(gridw), dim3(256), 0, st, table, idx, rowptr, n_out, C, out, ld_table, ld_out);
+    EQH_LAUNCH_RC();
+  }
   const dim3 grid(grid_for_warps(n_out, 256), (unsigned)(C / CB));
   EQH_DISPATCH_V(CB, {
     if (src_rowptr)

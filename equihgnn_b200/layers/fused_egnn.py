@@ -119,12 +119,18 @@ class EGNNFused(torch.autograd.Function):
         sink.weight(w5, dt_pre, node_in)
         sink.bias(b5, dt_pre)
         # dh0 = dOut (residual) + LayerNorm backward of dni[:, :C]
+        # (the edge kernel needs only the d m_i half of dni: the LayerNorm backward and its affine column sums run on a
+        # parallel branch, joined before the dh GEMM)
         dh0 = torch.empty_like(h)
         part_ln = torch.empty((ops.partial_rows(), 2 * C), dtype=torch.float32, device=dev)
-        _call("eqh_rowln_bwd_ld", 1, _p(h), C, _p(g), eps, 0, _p(dni), ldn, N, C, _p(dh0), C, _p(dOut), _p(part_ln),
-              _stream())
-        sink.affine(g, t, part_ln)
-        sink.flush()                                # bias / LayerNorm-affine column sums: every input exists already
+        with ops.branch_work.fork(dev, keep=(h, dni, dh0, dOut, part_ln)):
+            _call("eqh_rowln_bwd_ld", 1, _p(h), C, _p(g), eps, 0, _p(dni), ldn, N, C, _p(dh0), C, _p(dOut), _p(part_ln),
+                  _stream())
+            ln_batch = ops.ColsumBatch(dev)         # LayerNorm affine gradients, straight into their .grad slices
+            ln_batch.add(part_ln, sink.out[id(g)], col0=0, cols=C, accumulate=True)
+            ln_batch.add(part_ln, sink.out[id(t)], col0=C, cols=C, accumulate=True)
+            ln_batch.run()
+        sink.flush()                                # node-MLP weight / bias gradients: every input exists already
         # ---- phi_e
         slots = getattr(graph, "slots", None) if _slot_mode(graph, N) else None
         if slots is not None and slots[2] != Hp:
@@ -167,6 +173,7 @@ class EGNNFused(torch.autograd.Function):
         # 365 us with the planner's split vs ~180 us).  Splitting it into a dP half under the dQ reduction and a dQ half
         # after it was measured slower (QM9-128: 65 + 43 us instead of 49: the tail of the step is bound by SM time, the
         # extra launch only adds to the contention).
+        ops.branch_work.join(dev)
         dh = gemm_raw(dPQ, True, W1ab, False, N, C, 2 * Hp, residual=dh0, splits=0 if N < 8192 else 1)
         return (dh, None, None, None) + (None,) * 10
 
