@@ -401,6 +401,19 @@ def measure_workload(cx: Ctx, name: str, steps: int, warmup: int, n_batches: int
         trainer.step(resident[i % len(resident)])
     cx.barrier()
 
+    if os.environ.get("EQH_BENCH_TRACE") and rank == 0 and full:
+        # kernel timeline of three steps on rank 0 (torch.profiler / CUPTI), for scratch/trace_summary.py; not timed
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                trainer.step(resident[i % len(resident)])
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(os.environ["EQH_BENCH_TRACE"])
+    elif os.environ.get("EQH_BENCH_TRACE") and full:
+        for i in range(3):
+            trainer.step(resident[i % len(resident)])
+    cx.barrier()
+
     def launches_now():
         return (trainer.own_launches + (0 if trainer.in_graph_step else trainer.t)) if graphed else ops.STATS["launches"]
 

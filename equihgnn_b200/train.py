@@ -230,8 +230,14 @@ class Trainer:
         ops.side_work.join()
         ops.side_work_b.join()
         if self._early_done:
-            self._exchange_and_update(0, self.split, advance=True)
+            # the early bucket's update reads the device-side step counter: it must have run before the last update
+            # advances it (with several ranks its all-reduce may still be in flight here)
+            if self.distributed:
+                dist.all_reduce(self.fp.grad[:self.split], op=dist.ReduceOp.SUM, group=self.pg)
             torch.cuda.current_stream(self.fp.flat.device).wait_stream(self._comm)
+            ops.adam_step_dev_(self.fp.flat[:self.split], self.fp.grad[:self.split], self.exp_avg[:self.split],
+                               self.exp_avg_sq[:self.split], self.step_dev, self.lr, self.betas, self.eps, self.wd,
+                               grad_scale=1.0 / self.world, advance=True)
         else:
             self._exchange_and_update(0, self.fp.numel, advance=True)
         return loss.detach()
