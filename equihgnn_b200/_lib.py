@@ -52,6 +52,7 @@ _SIGNATURES = {
     "eqh_egnn_edge_fwd_tc_ordered": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "eqh_egnn_edge_bwd_ordered": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "eqh_egnn_edge_bwd_tc_rows": (c_int, [c_int64]),
+    "eqh_egnn_edge_bwd_tc_slices": (c_int, [c_int64, c_int64]),
     "eqh_egnn_edge_bwd_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "eqh_head_mse_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "eqh_head_mse_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_int, _P]),

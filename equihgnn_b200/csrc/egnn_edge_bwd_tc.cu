@@ -588,7 +588,7 @@ __device__ __forceinline__ int sub_slice_of(int64_t ap, int64_t N, int nslices) 
 
 // pass 1: mark[j * U + u] = first position-edge (ap * 16 + k) of the pair (neighbour j, sub-slice u); mark starts at INT_MAX
 __global__ void __launch_bounds__(256) k_slots_mark(const int32_t* __restrict__ idx, const int32_t* __restrict__ order,
-                                                    int64_t N, int nslices, int32_t* __restrict__ mark) {
+                                                    int64_t N, int nslices, int U, int32_t* __restrict__ mark) {
   pdl_prologue();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= N * kNbr) return;
@@ -596,13 +596,12 @@ __global__ void __launch_bounds__(256) k_slots_mark(const int32_t* __restrict__ 
   const int k = (int)(t % kNbr);
   const int64_t atom = order ? __ldg(order + ap) : ap;
   const int32_t j = __ldg(idx + atom * kNbr + k);
-  const int U = nslices * kEpiWG;
   atomicMin(mark + (int64_t)j * U + sub_slice_of(ap, N, nslices), (int32_t)t);
 }
 
 // pass 2 (after an exclusive scan of [mark != INT_MAX] into slot_ext): slot_edge[atom * 16 + k] = slot | first-edge flag
 __global__ void __launch_bounds__(256) k_slots_assign(const int32_t* __restrict__ idx, const int32_t* __restrict__ order,
-                                                      int64_t N, int nslices, const int32_t* __restrict__ mark,
+                                                      int64_t N, int nslices, int U, const int32_t* __restrict__ mark,
                                                       const int32_t* __restrict__ slot_ext, int32_t* __restrict__ slot_edge) {
   pdl_prologue();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -611,24 +610,34 @@ __global__ void __launch_bounds__(256) k_slots_assign(const int32_t* __restrict_
   const int k = (int)(t % kNbr);
   const int64_t atom = order ? __ldg(order + ap) : ap;
   const int32_t j = __ldg(idx + atom * kNbr + k);
-  const int U = nslices * kEpiWG;
   const int64_t key = (int64_t)j * U + sub_slice_of(ap, N, nslices);
   const int32_t slot = __ldg(slot_ext + key);
   slot_edge[atom * kNbr + k] = __ldg(mark + key) == (int32_t)t ? (slot | (int32_t)0x80000000) : slot;
 }
 
 static int groups_of(int64_t H) { return (int)((H + GC - 1) / GC); }
-static int slices_of(int64_t H) {
-  const int gr = groups_of(H);
-  // CTAs = groups x slices, one per SM (200 KB of shared memory each).  EQH_EDGE_BWD_FREE_SMS leaves that many SMs to the
-  // kernels of the parallel graph branches (weight-gradient GEMMs, column sums, the bucketed gradient exchange) that would
-  // otherwise wait for this kernel to end: it is the longest single kernel of the backward's tail.
-  static const int free_sms = []() {
+// CTAs = groups x slices, one per SM (200 KB of shared memory, the whole register file each).
+// slices_of: the most slices a launch uses (= rows of `part` the callers allocate, = sub-slice keys per neighbour / 3);
+// slices_for: the slices of a launch over N atoms.  Small batches leave 8 SMs to the kernels of the parallel graph branches
+// (weight-gradient GEMMs, column sums, the bucketed gradient exchange), which otherwise wait for this kernel -- the longest
+// of the backward's tail -- to end: QM9-128 step 1.058 -> 1.042 ms (same box; 16 / 24 free SMs: 1.042 / 1.049).  Large
+// batches are bound by SM time, not by the length of the chain: all SMs (PCQM4Mv2-768 5.33 vs 5.38 ms with 8 left free).
+// EQH_EDGE_BWD_FREE_SMS overrides both.
+static int free_sms_env() {
+  static const int v = []() {
     const char* e = getenv("EQH_EDGE_BWD_FREE_SMS");
-    const int v = e ? atoi(e) : 0;
-    return v < 0 ? 0 : (v > kSMs / 2 ? kSMs / 2 : v);
+    const int x = e ? atoi(e) : -1;
+    return x > kSMs / 2 ? kSMs / 2 : x;
   }();
-  const int s = (kSMs - free_sms) / gr;
+  return v;
+}
+static int slices_of(int64_t H) {
+  const int s = (kSMs - (free_sms_env() > 0 ? free_sms_env() : 0)) / groups_of(H);
+  return s < 1 ? 1 : s;
+}
+static int slices_for(int64_t H, int64_t N) {
+  if (free_sms_env() >= 0) return slices_of(H);
+  const int s = (kSMs - (N < 8192 ? 8 : 0)) / groups_of(H);
   return s < 1 ? 1 : s;
 }
 
@@ -638,6 +647,7 @@ static int slices_of(int64_t H) {
 extern "C" {
 
 int eqh_egnn_edge_bwd_tc_rows(int64_t H) { return H > 0 ? eqh::edge_bwd_tc::slices_of(H) : 0; }
+int eqh_egnn_edge_bwd_tc_slices(int64_t H, int64_t N) { return H > 0 ? eqh::edge_bwd_tc::slices_for(H, N) : 0; }
 
 int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const int32_t* idx,
                          const float* d2, const float* S2, const float* dMi, int64_t N, int64_t H, float* dP, float* dPre,
@@ -668,7 +678,7 @@ int eqh_egnn_edge_slots_mark(const int32_t* idx, const int32_t* order, int64_t N
   EQH_CHECK_ARG(idx && mark && N >= 0 && H > 0 && N * (int64_t)slices_of(H) * kEpiWG < ((int64_t)1 << 31));
   if (N == 0) return EQH_OK;
   launch_kernel(k_slots_mark, dim3((unsigned)((N * kNbr + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), idx,
-                order, N, slices_of(H), mark);
+                order, N, slices_for(H, N), slices_of(H) * kEpiWG, mark);
   EQH_LAUNCH_RC();
 }
 
@@ -679,7 +689,7 @@ int eqh_egnn_edge_slots_assign(const int32_t* idx, const int32_t* order, int64_t
   EQH_CHECK_ARG(idx && mark && slot_ext && slot_edge && N >= 0 && H > 0);
   if (N == 0) return EQH_OK;
   launch_kernel(k_slots_assign, dim3((unsigned)((N * kNbr + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), idx,
-                order, N, slices_of(H), mark, slot_ext, slot_edge);
+                order, N, slices_for(H, N), slices_of(H) * kEpiWG, mark, slot_ext, slot_edge);
   EQH_LAUNCH_RC();
 }
 
@@ -695,8 +705,13 @@ int eqh_egnn_edge_bwd_tc_slots(const float* P, const float* Q, int64_t ldpq, con
   EQH_CHECK_ARG(aligned16(S2) && aligned16(dMi) && aligned16(P) && aligned16(Q));
   EQH_CHECK_ARG(ldpq >= H && ldpq % 4 == 0 && lddp >= H && lddmi >= kM && lddmi % 4 == 0);
   if (H <= 0 || H % 64 != 0 || groups_of(H) > kSMs) return EQH_ERR_UNSUPPORTED;
-  const int gr = groups_of(H), sl = slices_of(H);
+  const int gr = groups_of(H), sl = slices_for(H, N);
   const int64_t part_cols = (int64_t)(kM + 1) * H + kM;
+  if (sl < slices_of(H)) {       // `part` has slices_of(H) rows: the ones this launch does not write hold zeros
+    cudaError_t e = cudaMemsetAsync(part + (int64_t)sl * part_cols, 0, sizeof(float) * (size_t)(slices_of(H) - sl) * (size_t)part_cols,
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return (int)e;
+  }
   if (slot_edge) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return (int)e;

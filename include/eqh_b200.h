@@ -255,6 +255,9 @@ EQH_API int eqh_egnn_edge_bwd_ordered(const float* P, const float* Q, const floa
  * rounding of the contraction), except that `part` has eqh_egnn_edge_bwd_tc_rows(H) rows (<= eqh_partial_rows()),
  * every one of them fully written.  order: optional visiting order of the atoms (NULL = natural). */
 EQH_API int eqh_egnn_edge_bwd_tc_rows(int64_t H);
+/* edge slices a launch over N atoms really uses (<= eqh_egnn_edge_bwd_tc_rows(H): small batches leave a few SMs to the
+ * parallel branches of the step; the rows of `part` it does not write are zeroed by the launch) */
+EQH_API int eqh_egnn_edge_bwd_tc_slices(int64_t H, int64_t N);
 EQH_API int eqh_egnn_edge_bwd_tc(const float* P, const float* Q, const float* wc, const float* W2, const int32_t* idx,
                          const float* d2, const float* S2, const float* dMi, int64_t N, int64_t H, float* dP, float* dPre,
                          float* part, const int32_t* order, eqh_stream_t stream);

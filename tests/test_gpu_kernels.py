@@ -810,8 +810,10 @@ def test_egnn_edge_bwd_slot_mode(profile, B, H, ordered):
     graph = ops.KnnGraph(idx, d2, None, None, order)
     slot_edge, rowptr = _build_slots(graph, N, H)
     # ---- numpy restatement of the numbering
-    S, U = lib.eqh_egnn_edge_bwd_tc_rows(H), lib.eqh_egnn_edge_slot_keys(H)
-    assert U == 3 * S
+    U = lib.eqh_egnn_edge_slot_keys(H)                   # keys per neighbour: 3 sub-slices for each of the most slices a launch uses
+    assert U == 3 * lib.eqh_egnn_edge_bwd_tc_rows(H)
+    S = lib.eqh_egnn_edge_bwd_tc_slices(H, N)            # ... and the slices of THIS launch
+    assert 1 <= S <= U // 3
     nblk = (N + 1) // 2
     ordr = order.cpu().numpy().astype(np.int64) if order is not None else np.arange(N)
     sub = np.empty(N, dtype=np.int64)                     # sub-slice of every position of the visiting order
@@ -848,7 +850,7 @@ def test_egnn_edge_bwd_slot_mode(profile, B, H, ordered):
     res = {}
     for mode in ("rows", "slots", "slots2"):
         dP = torch.full_like(P, float("nan")); dPre = torch.full((N * 16, H), float("nan"), device=DEV)
-        part = torch.full((S, 17 * H + 16), float("nan"), device=DEV)
+        part = torch.full((U // 3, 17 * H + 16), float("nan"), device=DEV)
         ops._call("eqh_egnn_edge_bwd_tc_slots", 1, P.data_ptr(), Q.data_ptr(), H, wc.data_ptr(), W2.data_ptr(), idx.data_ptr(),
                   d2.data_ptr(), S2.data_ptr(), dMi.data_ptr(), 16, N, H, dP.data_ptr(), H, dPre.data_ptr(), part.data_ptr(),
                   ops._p(order), None if mode == "rows" else slot_edge.data_ptr(), ops._stream())
