@@ -88,8 +88,11 @@ class Trainer:
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 0.0,
                  betas=(0.9, 0.999), eps: float = 1e-8, process_group: Optional[dist.ProcessGroup] = None,
-                 distributed: Optional[bool] = None):
+                 distributed: Optional[bool] = None, grad_buckets: Optional[int] = None):
         self.model = model
+        # 1: one all-reduce + Adam at the end of the step; 2: the early bucket (model.early_gradient_modules) exchanged at the
+        # model's grad_boundary, under the rest of the backward.  Default (EQH_GRAD_BUCKETS, else 1): see _plan_buckets.
+        self.grad_buckets = int(grad_buckets if grad_buckets is not None else os.environ.get("EQH_GRAD_BUCKETS", "1"))
         self.fp = FlatParams(model)
         for m in model.modules():       # kernels accumulate parameter gradients straight into the flat buffer
             if hasattr(m, "direct_param_grad"):
@@ -120,6 +123,13 @@ class Trainer:
         the model declares no such modules or they are not a suffix of the parameter order (single bucket)."""
         early = tuple(getattr(self.model, "early_gradient_modules", ()) or ())
         if not early:
+            return None
+        # One bucket by default.  The two-bucket scheme hid the conv + readout exchange under the EGNN backward as long as that
+        # bucket's last gradients were ready ~200 us before the end of the step; since the conv layers' merged-weight
+        # gradients are converted once, on the low-priority branch, they are ready ~60 us before the end, both collectives
+        # are exposed, and two latency-bound all-reduces cost more than one: QM9-128 step at 1 / 2 / 8 GPUs 1.035 / 1.106 /
+        # 1.171 ms with two buckets, 1.031 / 1.075 / 1.113 ms with one (same gpurun calls).
+        if self.grad_buckets < 2:
             return None
         ids = set()
         for name in early:

@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir):
         torch.manual_seed(0)                              # same initial weights on every rank
         model = EGNNEquiHNNS(1, synthetic.model_args(hidden=32))
         ops.adam_step_ = _adam_reference                  # no GPU here: the kernel's formula in torch
-        tr = Trainer(model, lr=1e-2)
+        tr = Trainer(model, lr=1e-2, grad_buckets=2)
         assert tr.distributed and tr.world == world
         names = [n for n, _ in model.named_parameters()]
         # .grad fields are views of ONE buffer

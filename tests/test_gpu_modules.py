@@ -634,7 +634,7 @@ def test_in_graph_step_matches_host_driven_step():
                     p_.normal_(0, 0.05)
         return m.to(DEV).train()
 
-    a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=True)
+    a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=True, grad_buckets=2)
     b = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=False)
     assert a.in_graph_step and not b.in_graph_step and a.split is not None
     la, lb = [], []
@@ -678,22 +678,26 @@ def _ddp_worker(rank, world, port, out_dir):
                         p_.normal_(0, 0.05)
             return m.to(dev).train()
 
-        a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, uniform_shapes=True)               # exchange inside the graph
+        a = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, uniform_shapes=True, grad_buckets=2)   # exchange inside the graph
         b = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, in_graph_step=False)               # one all-reduce after it
-        assert a.in_graph_step and a.distributed and a.world == world
+        c = GraphedTrainer(fresh(), real_graphs=B, lr=1e-3, uniform_shapes=True)                   # the default: one bucket, in the graph
+        assert a.in_graph_step and a.distributed and a.world == world and a.split is not None and c.split is None
         for step in range(4):
             la = a.step_from_host(host[step % 3], dev)
             lb = b.step_from_host(host[step % 3], dev)
-            assert la == lb, (rank, step, la, lb)
+            lc = c.step_from_host(host[step % 3], dev)
+            assert la == lb == lc, (rank, step, la, lb, lc)
         torch.cuda.synchronize()
         # two bucket all-reduces == one all-reduce of the flat buffer (element-wise sums): bit-identical state
         assert torch.equal(a.fp.flat, b.fp.flat) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+        assert torch.equal(c.fp.flat, b.fp.flat) and torch.equal(c.exp_avg_sq, b.exp_avg_sq)
         flats = [torch.empty_like(a.fp.flat) for _ in range(world)]
         dist.all_gather(flats, a.fp.flat)
         assert all(torch.equal(flats[0], f) for f in flats[1:])                                # ranks stay in lock step
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
         a.release()                      # graphs holding captured NCCL work go before the communicator
         b.release()
+        c.release()
         dist.barrier()
     finally:
         dist.destroy_process_group()
