@@ -4,22 +4,66 @@
 
 namespace eqh {
 
+// one element of the update (the same expression order in the scalar and the float4 loops: bit-identical results)
+__device__ __forceinline__ void adam_elem(float& pi, float g, float& mi, float& vi, float lr, float b1, float b2, float eps, float wd,
+                                          float bc1, float bc2_sqrt, float gscale) {
+  float gi = g * gscale;
+  if (wd != 0.f) gi += wd * pi;
+  mi = b1 * mi + (1.f - b1) * gi;
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi = pi - (lr / bc1) * (mi / denom);
+}
+
+// the whole buffer as float4 lanes when it is 16-byte aligned (flat parameter buffers are 128-byte aligned and every
+// bucket boundary is a multiple of 32 floats): 4 loads + 3 stores of 16 B per 4 elements, two groups in flight per thread
+__device__ __forceinline__ void adam_body(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                          float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                                          float bc1, float bc2_sqrt, float gscale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = tid; i < n4; i += 2 * stride) {
+      const int64_t j = i + stride;
+      const bool two = j < n4;
+      float4 pa = p4[i], ga = g4[i], ma = m4[i], va = v4[i];
+      float4 pb = pa, gb = ga, mb = ma, vb = va;
+      if (two) { pb = p4[j]; gb = g4[j]; mb = m4[j]; vb = v4[j]; }
+      adam_elem(pa.x, ga.x, ma.x, va.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      adam_elem(pa.y, ga.y, ma.y, va.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      adam_elem(pa.z, ga.z, ma.z, va.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      adam_elem(pa.w, ga.w, ma.w, va.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      m4[i] = ma; v4[i] = va; p4[i] = pa;
+      if (two) {
+        adam_elem(pb.x, gb.x, mb.x, vb.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+        adam_elem(pb.y, gb.y, mb.y, vb.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+        adam_elem(pb.z, gb.z, mb.z, vb.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+        adam_elem(pb.w, gb.w, mb.w, vb.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+        m4[j] = mb; v4[j] = vb; p4[j] = pb;
+      }
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_elem(pi, g[i], mi, vi, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                                float wd, float bc1, float bc2_sqrt, float gscale) {
   pdl_prologue();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    float pi = p[i];
-    float gi = g[i] * gscale;
-    if (wd != 0.f) gi += wd * pi;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
-  }
+  adam_body(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
 }
 
 // Same update with the step count in DEVICE memory, so that the optimizer can live inside a captured CUDA graph
@@ -40,18 +84,7 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   }
   __syncthreads();
   const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    float pi = p[i];
-    float gi = g[i] * gscale;
-    if (wd != 0.f) gi += wd * pi;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
-  }
+  adam_body(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
   if (advance) {
     __syncthreads();                       // every thread of this block has read *step
     if (threadIdx.x == 0) {
@@ -111,8 +144,9 @@ int eqh_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   // bias corrections in double on the host, as torch.optim.Adam computes them (1 - 0.999f in fp32 carries ~1e-5)
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  int64_t blocks = (n + 255) / 256;
+  int64_t blocks = (n / 4 + 255) / 256;          // one float4 group per thread and pass
   if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  if (blocks < 1) blocks = 1;
   launch_kernel(k_adam, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                          beta2, eps, weight_decay, bc1, sqrtf(bc2),
                                                                          grad_scale);
@@ -125,7 +159,7 @@ int eqh_adam_step_dev(float* param, const float* grad, float* exp_avg, float* ex
   using namespace eqh;
   EQH_CHECK_ARG(n >= 0 && step_dev && (!advance || counter) && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
   if (n == 0 && !advance) return EQH_OK;
-  int64_t blocks = (n + 255) / 256;
+  int64_t blocks = (n / 4 + 255) / 256;          // one float4 group per thread and pass
   if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
   if (blocks < 1) blocks = 1;
   launch_kernel(k_adam_dev, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg,
