@@ -19,6 +19,21 @@ from .graphed import GHOST_OFFSET, GraphedTrainer
 from .synthetic import HBatch
 
 
+def local_csr(mols) -> dict:
+    """Per-molecule LOCAL incidence CSR in both groupings, concatenated over the molecules (int32 numpy arrays):
+    rowptr_e_loc (n_he + 1 entries per molecule), perm_e_loc (the molecule's incidences in by-hyperedge order, stable),
+    rowptr_v_loc (n_atoms + 1 per molecule), perm_v_loc.  mols: tuples (n_atoms, n_he, x, pos, v_loc, e_loc, ...)."""
+    rp_e, pm_e, rp_v, pm_v = [], [], [], []
+    for m in mols:
+        v_loc, e_loc = np.asarray(m[4], dtype=np.int64), np.asarray(m[5], dtype=np.int64)
+        pm_e.append(np.argsort(e_loc, kind="stable"))
+        pm_v.append(np.argsort(v_loc, kind="stable"))
+        rp_e.append(np.concatenate([[0], np.cumsum(np.bincount(e_loc, minlength=m[1]))]))
+        rp_v.append(np.concatenate([[0], np.cumsum(np.bincount(v_loc, minlength=m[0]))]))
+    cat32 = lambda parts: np.ascontiguousarray(np.concatenate(parts).astype(np.int32))
+    return {"rowptr_e_loc": cat32(rp_e), "perm_e_loc": cat32(pm_e), "rowptr_v_loc": cat32(rp_v), "perm_v_loc": cat32(pm_v)}
+
+
 class MoleculeStore:
     """Packed dataset: concatenated per-molecule arrays on the device + per-molecule counts on the host."""
 
@@ -43,16 +58,7 @@ class MoleculeStore:
         self.size = len(mols)
         # per-molecule LOCAL incidence CSR in both groupings (stable orders, computed once per dataset): the collation
         # emits the batch's CSR from these by gather + offset (eqh_collate_incidence) instead of rebuilding it every step
-        rp_e, pm_e, rp_v, pm_v = [], [], [], []
-        for m in mols:
-            v_loc, e_loc = np.asarray(m[4], dtype=np.int64), np.asarray(m[5], dtype=np.int64)
-            pm_e.append(np.argsort(e_loc, kind="stable"))
-            pm_v.append(np.argsort(v_loc, kind="stable"))
-            rp_e.append(np.concatenate([[0], np.cumsum(np.bincount(e_loc, minlength=m[1]))]))
-            rp_v.append(np.concatenate([[0], np.cumsum(np.bincount(v_loc, minlength=m[0]))]))
-        cat32 = lambda parts: dev(np.concatenate(parts).astype(np.int32))
-        self.csr = {"rowptr_e_loc": cat32(rp_e), "perm_e_loc": cat32(pm_e), "rowptr_v_loc": cat32(rp_v),
-                    "perm_v_loc": cat32(pm_v)}
+        self.csr = {k: dev(v) for k, v in local_csr(mols).items()}
         self.c_csr = _lib.StoreCsr(**{k: v.data_ptr() for k, v in self.csr.items()})
 
     def shape_of(self, ids: Sequence[int]) -> Tuple[int, int, int]:

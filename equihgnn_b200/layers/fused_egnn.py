@@ -86,7 +86,10 @@ class EGNNFused(torch.autograd.Function):
         _call("eqh_egnn_edge_fwd_tc_ld", 1, _p(PQ), PQ.data_ptr() + 4 * Hp, 2 * Hp, _p(wc), _p(W2p), _p(b2), _p(graph.idx),
               _p(graph.d2), N, Hp, _p(S2), None, node_in.data_ptr() + 4 * C, ldn, _p(graph.order), _stream(),
               nbytes=2.0 * N * KNN_K * Hp * M_DIM)
-        if _slot_mode(graph, N):                          # slot numbering for the backward's in-kernel dQ partial sums ...
+        needs_bwd = any(ctx.needs_input_grad)
+        if not needs_bwd:
+            pass                                          # inference: nothing to prepare for a backward
+        elif _slot_mode(graph, N):                        # slot numbering for the backward's in-kernel dQ partial sums ...
             if getattr(graph, "slots", None) is None or graph.slots[2] != Hp:
                 with ops.prep_work_b.fork(dev, keep=(graph.idx,)):
                     graph.slots = _build_slots(graph, N, Hp) + (Hp,)

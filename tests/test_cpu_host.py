@@ -270,3 +270,45 @@ def test_torch_extension_loads_and_registers_its_ops():
         assert hasattr(torch.ops.eqh, name), name
     with pytest.raises(RuntimeError):
         torch.ops.eqh.scatter(torch.randn(4, 32), torch.tensor([0, 1, 1, 0]), 2, "sum")
+
+
+@pytest.mark.parametrize("profile", ["qm9", "opv"])
+def test_local_csr_composes_into_the_batch_csr(profile):
+    """What eqh_collate_incidence relies on (host restatement, numpy): a batch is a block-diagonal concatenation of
+    molecules in id order, so its stable by-hyperedge / by-vertex orders are the molecules' LOCAL orders shifted by the
+    molecule's offsets (data/utils.py:172-178 numbering)."""
+    import numpy as np
+    from equihgnn_b200.collate import local_csr
+    mols, y = synthetic.make_molecules(profile, 12, 3)
+    csr = local_csr(mols)
+    ids = [7, 2, 9, 0, 5]
+    host = synthetic.collate_host(mols, y, ids)
+    V, E = host.edge_index0.numpy(), host.edge_index1.numpy()
+    n_at = np.array([m[0] for m in mols]); n_he = np.array([m[1] for m in mols]); n_in = np.array([len(m[4]) for m in mols])
+    inc_off = np.concatenate([[0], np.cumsum(n_in)]); he_off = np.concatenate([[0], np.cumsum(n_he)])
+    at_off = np.concatenate([[0], np.cumsum(n_at)])
+    a0 = h0 = z0 = 0
+    perm_e, perm_v, rp_e, rp_v = [], [], [0], [0]
+    for m in ids:
+        pe = csr["perm_e_loc"][inc_off[m]:inc_off[m + 1]]
+        pv = csr["perm_v_loc"][inc_off[m]:inc_off[m + 1]]
+        perm_e += list(z0 + pe); perm_v += list(z0 + pv)
+        rp_e += list(z0 + csr["rowptr_e_loc"][he_off[m] + m + 1:he_off[m + 1] + m + 1])
+        rp_v += list(z0 + csr["rowptr_v_loc"][at_off[m] + m + 1:at_off[m + 1] + m + 1])
+        a0 += n_at[m]; h0 += n_he[m]; z0 += n_in[m]
+    assert np.array_equal(np.array(perm_e), np.argsort(E, kind="stable"))
+    assert np.array_equal(np.array(perm_v), np.argsort(V, kind="stable"))
+    assert np.array_equal(np.array(rp_e), np.concatenate([[0], np.cumsum(np.bincount(E, minlength=h0))]))
+    assert np.array_equal(np.array(rp_v), np.concatenate([[0], np.cumsum(np.bincount(V, minlength=a0))]))
+
+
+def test_trainer_uses_one_gradient_bucket_unless_asked():
+    from equihgnn_b200.train import Trainer
+    args = synthetic.model_args(hidden=32)
+    torch.manual_seed(0)
+    one = Trainer(EGNNEquiHNNS(1, args))
+    assert one.split is None and one.bucket_ranges() == [(0, one.fp.numel)]
+    one.close()
+    two = Trainer(EGNNEquiHNNS(1, args), grad_buckets=2)
+    assert two.split is not None and len(two.bucket_ranges()) == 2
+    two.close()
