@@ -148,7 +148,7 @@ class GraphedTrainer(Trainer):
     def _fwd_bwd(self, data) -> torch.Tensor:
         self.fp.zero_grad()
         loss = model_loss(self.model, data, self.B)                    # the ghost molecule is not in the loss
-        loss.backward()
+        loss.backward(self._one_like(loss))
         ops.side_work.join()
         ops.side_work_b.join()        # the side-stream branch rejoins before the capture ends
         return loss.detach()

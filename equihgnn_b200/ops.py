@@ -1379,6 +1379,7 @@ class _HeadMSE(torch.autograd.Function):
         ctx.save_for_backward(z, wv, resid)
         ctx.w_param, ctx.b_param = w, b
         ctx.mark_non_differentiable(pred)
+        ctx.set_materialize_grads(False)        # no zero-fill launch for the gradient of `pred` on the tail of the step
         return loss, pred
 
     @staticmethod

@@ -114,6 +114,7 @@ class Trainer:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)      # t - 1 of the fused step (device-side counter)
         self._comm = None
         self._early_done = False
+        self._ones = {}
         self.timing = {}                 # filled by bench.py: measured all-reduce time etc.
 
     # -- gradient buckets -----------------------------------------------------------------------
@@ -145,6 +146,13 @@ class Trainer:
             return None
         return self.fp.offsets[first]
 
+    def _one_like(self, loss: torch.Tensor) -> torch.Tensor:
+        """The root gradient as a cached constant (autograd would launch a fill kernel for it every step)."""
+        one = self._ones.get((loss.device, loss.dtype, tuple(loss.shape)))
+        if one is None:
+            one = self._ones[(loss.device, loss.dtype, tuple(loss.shape))] = torch.ones_like(loss)
+        return one
+
     def bucket_ranges(self):
         n = self.fp.numel
         return [(0, n)] if self.split is None else [(0, self.split), (self.split, n)]
@@ -172,7 +180,7 @@ class Trainer:
         self._check_binding()
         self.fp.zero_grad()
         loss = model_loss(self.model, data, data.y.view(-1).shape[0])
-        loss.backward()
+        loss.backward(self._one_like(loss))
         ops.side_work.join()
         ops.side_work_b.join()
         return loss.detach()
@@ -234,7 +242,7 @@ class Trainer:
         ops.BOUNDARY_HOOK = self._on_boundary if (self.split is not None and self.fp.flat.is_cuda) else None
         try:
             loss = model_loss(self.model, data, data.y.view(-1).shape[0] if n_loss is None else n_loss)
-            loss.backward()
+            loss.backward(self._one_like(loss))
         finally:
             ops.BOUNDARY_HOOK = None
         ops.side_work.join()
