@@ -194,6 +194,8 @@ class MHNN(_SharedConvBase):
 class EGNNEquiHNN(_SharedConvBase):
     """`--method egnn_equihnn` (equihnn_egnn.py:12-95): EGNN layer, then the shared MHNNConv."""
 
+    no_gradient_modules = ("egnn_layer.coors_mlp", "egnn_layer.coors_norm")     # coors_out discarded (:77)
+
     def __init__(self, num_target, args):
         super().__init__(num_target, args, with_egnn=True)
 
@@ -255,6 +257,8 @@ class EGNNEquiHNNS(nn.Module):
 
     # gradients of these sub-modules are complete once the backward reaches ops.grad_boundary (the EGNN output)
     early_gradient_modules = ("conv", "mlp_out")
+    # phi_x never receives a gradient (coors_out is discarded, :158): torch.optim.Adam skips such parameters
+    no_gradient_modules = ("egnn_layer.coors_mlp", "egnn_layer.coors_norm")
 
     def __init__(self, num_target, args):
         super().__init__()
@@ -317,6 +321,7 @@ class MHNNM(nn.Module):
     same network behind an EGNN layer."""
 
     _with_egnn = False
+    no_gradient_modules = ("egnn_layer.coors_mlp", "egnn_layer.coors_norm")     # (egnn_equihnnm: coors_out discarded, :242)
 
     def __init__(self, num_target, args):
         super().__init__()

@@ -115,6 +115,10 @@ class Trainer:
         self._comm = None
         self._early_done = False
         self._ones = {}
+        # torch.optim.Adam skips parameters whose .grad is None (phi_x of egnn_equihnns never receives one: every wrapper
+        # discards coors_out); here they own a zero slice of the flat gradient, which is the same thing as long as there
+        # is no weight decay.  With weight decay their slices are left out of the update.
+        self._skip = self._ranges_without_gradient() if weight_decay != 0.0 else []
         self.timing = {}                 # filled by bench.py: measured all-reduce time etc.
 
     # -- gradient buckets -----------------------------------------------------------------------
@@ -152,6 +156,41 @@ class Trainer:
         if one is None:
             one = self._ones[(loss.device, loss.dtype, tuple(loss.shape))] = torch.ones_like(loss)
         return one
+
+    def _ranges_without_gradient(self):
+        """Float ranges of the flat buffers owned by parameters under `model.no_gradient_modules` (ascending, merged)."""
+        ids = set()
+        for path in tuple(getattr(self.model, "no_gradient_modules", ()) or ()):
+            sub = self.model
+            for part in path.split("."):
+                sub = getattr(sub, part, None)
+                if sub is None:
+                    break
+            if isinstance(sub, torch.nn.Module):
+                ids.update(id(q) for q in sub.parameters())
+        out = []
+        for i, q in enumerate(self.fp.params):
+            if id(q) in ids:
+                lo = self.fp.offsets[i]
+                hi = self.fp.offsets[i + 1] if i + 1 < len(self.fp.params) else self.fp.numel
+                if out and out[-1][1] == lo:
+                    out[-1] = (out[-1][0], hi)
+                else:
+                    out.append((lo, hi))
+        return out
+
+    def _update_ranges(self, lo: int, hi: int):
+        """[lo, hi) minus the ranges that take no update (never empty: a zero-length range still carries `advance`)."""
+        out, at = [], lo
+        for a, b in self._skip:
+            if b <= lo or a >= hi:
+                continue
+            if a > at:
+                out.append((at, a))
+            at = max(at, b)
+        if at < hi or not out:
+            out.append((min(at, hi), hi))
+        return out
 
     def bucket_ranges(self):
         n = self.fp.numel
@@ -193,8 +232,10 @@ class Trainer:
 
     def optimizer_step(self):
         self.t += 1
-        ops.adam_step_(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.t, self.lr, self.betas,
-                       self.eps, self.wd, grad_scale=1.0 / self.world)
+        for lo, hi in self._update_ranges(0, self.fp.numel):
+            if hi > lo:
+                ops.adam_step_(self.fp.flat[lo:hi], self.fp.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.t,
+                               self.lr, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world)
 
     def step(self, data) -> torch.Tensor:
         """One training step on a device-resident batch; returns the (device) loss."""
@@ -215,8 +256,11 @@ class Trainer:
         g = self.fp.grad[lo:hi]
         if self.distributed:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-        ops.adam_step_dev_(self.fp.flat[lo:hi], g, self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_dev, self.lr,
-                           self.betas, self.eps, self.wd, grad_scale=1.0 / self.world, advance=advance)
+        parts = self._update_ranges(lo, hi)
+        for i, (a, b) in enumerate(parts):
+            ops.adam_step_dev_(self.fp.flat[a:b], self.fp.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], self.step_dev,
+                               self.lr, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world,
+                               advance=advance and i == len(parts) - 1)
 
     def _on_boundary(self) -> None:
         """Called from the backward at the model's ops.grad_boundary: the early bucket is final (its weight-gradient work
@@ -253,9 +297,11 @@ class Trainer:
             if self.distributed:
                 dist.all_reduce(self.fp.grad[:self.split], op=dist.ReduceOp.SUM, group=self.pg)
             torch.cuda.current_stream(self.fp.flat.device).wait_stream(self._comm)
-            ops.adam_step_dev_(self.fp.flat[:self.split], self.fp.grad[:self.split], self.exp_avg[:self.split],
-                               self.exp_avg_sq[:self.split], self.step_dev, self.lr, self.betas, self.eps, self.wd,
-                               grad_scale=1.0 / self.world, advance=True)
+            parts = self._update_ranges(0, self.split)
+            for i, (a, b) in enumerate(parts):
+                ops.adam_step_dev_(self.fp.flat[a:b], self.fp.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
+                                   self.step_dev, self.lr, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world,
+                                   advance=i == len(parts) - 1)
         else:
             self._exchange_and_update(0, self.fp.numel, advance=True)
         return loss.detach()

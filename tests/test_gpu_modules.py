@@ -893,3 +893,38 @@ def test_egnn_slot_mode_matches_edge_row_mode(profile, B, monkeypatch):
     scale = max(float(v.abs().max()) for v in gz.values())
     for k in gz:
         assert float((ga[k] - gz[k]).abs().max()) / scale < 2e-6, k
+
+
+def test_trainer_weight_decay_skips_parameters_without_gradient():
+    """torch.optim.Adam skips parameters whose .grad is None -- phi_x of egnn_equihnns never gets one -- so weight decay
+    must not touch them; everything else follows torch's Adam with the same weight decay."""
+    from equihgnn_b200.train import Trainer
+    C, B = 32, 16
+    b = synthetic.make_batch("qm9", B, 41).to(DEV)
+    args = synthetic.model_args(hidden=C)
+
+    def fresh():
+        torch.manual_seed(8)
+        return EGNNEquiHNNS(1, args).to(DEV).train()
+
+    ref = fresh()
+    init = {k: q.detach().clone() for k, q in ref.named_parameters()}
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=0.05)
+    tr = Trainer(fresh(), lr=1e-3, weight_decay=0.05)
+    assert tr._skip, "the model declares its gradient-free modules"
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        F.mse_loss(ref(b), b.y).backward()
+        opt.step()
+        tr.step(b)
+    torch.cuda.synchronize()
+    got = dict(tr.model.named_parameters())
+    for k, q in ref.named_parameters():
+        if k.startswith(("egnn_layer.coors_mlp", "egnn_layer.coors_norm")):
+            assert q.grad is None and torch.equal(q, init[k]) and torch.equal(got[k], init[k]), k
+        else:
+            assert not torch.equal(got[k], init[k]), k
+            # (an element whose gradient is ~0 may get the opposite sign on the two paths: Adam then moves it by +-lr per
+            # step either way -- compare the mean, not the maximum)
+            assert float((got[k] - q).abs().mean()) < 2e-4, k
+    tr.close()
